@@ -1,0 +1,100 @@
+"""Synthetic workloads of the shapes BASELINE.json names (no dataset / checkpoint is reachable offline).
+
+Generators follow SURVEY.md section 8(d): tuples laid out as the reference's sampler emits them
+(/root/reference/train/train.py:503,520: [anchor, P positives, N negatives(, other)]), GPS positions with
+positives within MAX_POS_RADIUS=15 m (train.py:457) and mutually exclusive negatives >= MIN_NEG_RADIUS=15 m
+(train.py:472-495), and the per-loss distance tensors built exactly as train.py:525-571 builds them.
+NumPy only; used by tests, bench.py and smoke().
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MAX_POS_RADIUS = 15.0
+MIN_NEG_RADIUS = 15.0
+
+
+def tuple_xy(rng, T, P, N, other=False, extent=1000.0):
+    """xy [T,S,2] float64: anchor ~ U([0,extent]^2); positives within 15 m; negatives >= 15 m from anchor and each other."""
+    S = 1 + P + N + (1 if other else 0)
+    xy = np.empty((T, S, 2), dtype=np.float64)
+    for t in range(T):
+        a = rng.uniform(0, extent, size=2)
+        xy[t, 0] = a
+        r = rng.uniform(0, MAX_POS_RADIUS, size=P)
+        th = rng.uniform(0, 2 * np.pi, size=P)
+        xy[t, 1:1 + P, 0] = a[0] + r * np.cos(th)
+        xy[t, 1:1 + P, 1] = a[1] + r * np.sin(th)
+        placed = [a]
+        n_need = N + (1 if other else 0)
+        k = 0
+        while k < n_need:
+            c = rng.uniform(0, extent, size=2)
+            if all(np.hypot(*(c - p)) >= MIN_NEG_RADIUS for p in placed):
+                xy[t, 1 + P + k] = c
+                placed.append(c)
+                k += 1
+    return xy
+
+
+def tuple_descriptors(rng, T, P, N, D, other=False, pos_noise=0.7, dtype=np.float32):
+    """emb [T,S,D]: z ~ N(0,I); positives = anchor + pos_noise*z so similarities straddle the mining thresholds."""
+    S = 1 + P + N + (1 if other else 0)
+    emb = rng.standard_normal((T, S, D))
+    emb[:, 1:1 + P] = emb[:, 0:1] + pos_noise * emb[:, 1:1 + P]
+    return emb.astype(dtype)
+
+
+def pairwise_euclid(xy):
+    """train.py:557-563 ('wms'): pairwise Euclidean metres over [anchor, pos..., neg...] -> [T,S,S]."""
+    d = xy[:, :, None, :] - xy[:, None, :, :]
+    return np.sqrt((d * d).sum(-1))
+
+
+def anchor_sq_dists(xy, P):
+    """train.py:529-534 ('anchor'): squared metres anchor -> each positive -> [T,P]."""
+    d = xy[:, 1:1 + P] - xy[:, 0:1]
+    return (d * d).sum(-1)
+
+
+def logratio_sq_dists(xy, P, N):
+    """train.py:564-571 ('logratio'): squared metres anchor->positives [T,P,1] and anchor->negatives [T,N,1]."""
+    dp = xy[:, 1:1 + P] - xy[:, 0:1]
+    dn = xy[:, 1 + P:1 + P + N] - xy[:, 0:1]
+    return (dp * dp).sum(-1)[..., None], (dn * dn).sum(-1)[..., None]
+
+
+def wms_batch(T=32, P=12, N=12, D=4096, seed=42, dtype=np.float32):
+    """BASELINE config 1: T tuples of S=1+P+N descriptors with their [S,S] GPS distance matrices."""
+    rng = np.random.default_rng(seed)
+    xy = tuple_xy(rng, T, P, N)
+    emb = tuple_descriptors(rng, T, P, N, D, dtype=dtype)
+    dist = pairwise_euclid(xy).astype(dtype)
+    return emb, dist, xy
+
+
+def retrieval_problem(R, Q, D, seed=42, noise=0.5, dtype=np.float32, extent=10000.0):
+    """BASELINE config 4/5 shape: db ~ N(0,1); queries = perturbed random db rows; xy ~ U([0,extent]^2)."""
+    rng = np.random.default_rng(seed)
+    db = rng.standard_normal((R, D), dtype=np.float32)
+    src = rng.integers(0, R, size=Q)
+    qry = db[src] + noise * rng.standard_normal((Q, D), dtype=np.float32)
+    ref_xy = rng.uniform(0, extent, size=(R, 2))
+    query_xy = ref_xy[src] + rng.normal(0, 3.0, size=(Q, 2))
+    return db.astype(dtype), qry.astype(dtype), ref_xy, query_xy, src
+
+
+def netvlad_problem(B=2, H=3, W=4, C=512, K=64, Dout=128, seed=42):
+    """BASELINE config 2 shape (scaled by the caller): conv5 maps, assignment weights, centres, PCA (V, m, var)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    aw = (0.05 * rng.standard_normal((C, K))).astype(np.float32)
+    cc = (0.05 * rng.standard_normal((C, K))).astype(np.float32)
+    Din = C * K
+    # random orthonormal rows via QR of a thin Gaussian (Dout << Din)
+    g = rng.standard_normal((Din, Dout))
+    q, _ = np.linalg.qr(g)
+    V = q.T.astype(np.float32)
+    m = (0.01 * rng.standard_normal(Din)).astype(np.float32)
+    var = rng.uniform(0.5, 2.0, size=Dout).astype(np.float32)
+    return x, aw, cc, V, m, var
