@@ -1,0 +1,199 @@
+/* scl_b200.h -- C ABI of libscl_b200.so: the B200 (sm_100a) descriptor-space hot path of
+ * janinethoma/soft_contrastive_learning.
+ *
+ * The reference is pure Python/TF-1.10 and has no FFI of its own; its boundary for this path is a set of
+ * Python call sites.  Each entry point below names the reference call site it replaces (file:line relative
+ * to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host; tensors are
+ *    row-major, contiguous, 16-byte aligned; outputs are pre-allocated by the caller;
+ *  - scalar results (losses) are written to device memory: no entry point synchronises the stream
+ *    except where stated (scl_knn_query_host);
+ *  - no global mutable state: workspace and stream are per call, so concurrent calls from several host
+ *    threads are safe when they use different workspaces (train.py runs up to three threads per session);
+ *  - return value 0 on success, a negative scl_status otherwise; never throws, never exits;
+ *  - there is no CPU fallback: on a device that is not compute capability 10.x every compute entry point
+ *    returns SCL_ERR_ARCH.
+ */
+#ifndef SCL_B200_H
+#define SCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* scl_stream_t; /* cudaStream_t */
+
+typedef enum {
+  SCL_OK = 0,
+  SCL_ERR_BAD_ARG = -1,     /* null pointer / unknown enum */
+  SCL_ERR_BAD_SHAPE = -2,   /* unsupported or inconsistent sizes */
+  SCL_ERR_ALIGN = -3,       /* pointer not 16-byte aligned */
+  SCL_ERR_WORKSPACE = -4,   /* workspace too small */
+  SCL_ERR_CUDA = -5,        /* a CUDA runtime/driver call failed: see scl_last_error() */
+  SCL_ERR_ARCH = -6,        /* device is not sm_100 */
+  SCL_ERR_UNSUPPORTED = -7
+} scl_status;
+
+int scl_version(void);
+const char* scl_strerror(int status);
+const char* scl_last_error(void); /* thread-local detail string of the last SCL_ERR_CUDA */
+int scl_device_ok(void);          /* 0 when the current device is compute capability 10.x */
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-similarity family parameters.
+ * wms_loss(distances, embeddings, d_alpha, d_beta, alpha=2, beta=50, lamb=1, eps=0.1, ms_mining=True,
+ *          wfunction='exp', sumfunction='ms')                         model/losses.py:5
+ * ms_loss(labels, embeddings, alpha=2, beta=50, lamb=1, eps=0.1, ms_mining=True)   model/losses.py:76
+ * ---------------------------------------------------------------------------------------------- */
+enum { SCL_WF_EXP = 0, SCL_WF_LIN = 1, SCL_WF_TANH = 2 };   /* wfunction, losses.py:11-19 */
+enum { SCL_SUM_MS = 0, SCL_SUM_PLAIN = 1 };                 /* sumfunction, losses.py:39-58 */
+
+typedef struct {
+  float d_alpha, d_beta;          /* GPS sigmoid (train.py:852 ALPHA, BETA) */
+  float alpha, beta, lamb, eps;   /* multi-similarity constants */
+  int32_t ms_mining;
+  int32_t wfunction;
+  int32_t sumfunction;
+} scl_ms_params;
+
+/* W1, tuple mode.  Replaces wms_loss at train/train.py:852 (distances placeholder train.py:684-686,
+ * built by train.py:557-563) together with its TF-autodiff backward (train.py:874-878).
+ *   emb   [T,S,D] f32   descriptors, tuple row order [anchor, positives, negatives]   (train.py:503)
+ *   dist  [T,S,S] f32   pairwise Euclidean metres (not squared)
+ *   loss  [1]     f32   mean over tuples of the per-tuple losses.py:5-60 value
+ *   per_tuple [T] f32   optional (may be NULL)
+ *   demb  [T,S,D] f32   d loss / d emb  (may be NULL: forward only)
+ *   kept  [T,S,2] u32   optional: bit j of kept[t,i,0] / kept[t,i,1] = pair (i,j) survived positive /
+ *                       negative mining (losses.py:36-37, tested with >0 at :50,:53)
+ * Requires 2 <= S <= 32, D % 4 == 0. */
+int scl_wms_tuple_workspace_bytes(int T, int S, int D, size_t* bytes);
+int scl_wms_tuple_fwd_bwd(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params* p,
+                          float* loss, float* per_tuple, float* demb, uint32_t* kept,
+                          void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* W1 / W2, flat mode: one Gram matrix over the whole batch (model/losses.py:25, :94).
+ *   wms: dist [B,B] f32; ms: labels [B] i32 (train.py:822-826 classes, any integer coding).
+ *   kept [2,B,B] u8 optional.  Requires D % 4 == 0. */
+int scl_ms_flat_workspace_bytes(int B, int D, size_t* bytes);
+int scl_wms_flat_fwd_bwd(const float* emb, const float* dist, int B, int D, const scl_ms_params* p,
+                         float* loss, float* demb, uint8_t* kept,
+                         void* workspace, size_t workspace_bytes, scl_stream_t stream);
+int scl_ms_flat_fwd_bwd(const float* emb, const int32_t* labels, int B, int D, const scl_ms_params* p,
+                        float* loss, float* demb, uint8_t* kept,
+                        void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * L1-L5: triplet family on tuples.  Replaces, by `kind`:
+ *   SCL_TRIPLET          pointnetvlad_cls.triplet_loss          train/train.py:701
+ *   SCL_LAZY_TRIPLET     pointnetvlad_cls.lazy_triplet_loss     train/train.py:703
+ *   SCL_QUADRUPLET       pointnetvlad_cls.quadruplet_loss       train/train.py:707-708
+ *   SCL_LAZY_QUADRUPLET  pointnetvlad_cls.lazy_quadruplet_loss  train/train.py:710-712
+ *   SCL_EVIL_TRIPLET     evil_triplet_loss                      model/losses.py:63-73
+ *   SCL_EVIL_QUADRUPLET  evil_quadruplet_loss                   model/losses.py:197-214
+ * and, with dist_term != NONE, distance_triplet_loss (model/losses.py:239-264; calls train.py:719-747):
+ *   loss = triplet(kind) + lam * {distance_loss | huber_distance_loss}(a, pos, sq_d_dists, d_max, f_max).
+ *   emb [T,S,D] f32 with S = 1+P+N(+1 if the kind has an `other` negative, last row)   (train.py:589-592,654)
+ *   sq_d_dists [T,P] f32 squared metres anchor->positive (train.py:529-534), NULL when dist_term == NONE
+ * ---------------------------------------------------------------------------------------------- */
+enum { SCL_TRIPLET = 0, SCL_LAZY_TRIPLET = 1, SCL_QUADRUPLET = 2, SCL_LAZY_QUADRUPLET = 3,
+       SCL_EVIL_TRIPLET = 4, SCL_EVIL_QUADRUPLET = 5 };
+enum { SCL_DIST_NONE = 0, SCL_DIST_SQUARED = 1, SCL_DIST_HUBER = 2 };
+
+typedef struct {
+  int32_t kind;
+  int32_t dist_term;
+  float m1, m2;                       /* MARGIN_1, MARGIN_2 (train.py:1254-1256) */
+  float lam;                          /* LAM (train.py:1257) */
+  float d_max_squared, f_max_squared; /* train.py:695-696 */
+} scl_tuple_params;
+
+int scl_tuple_loss_workspace_bytes(int T, int P, int N, int D, size_t* bytes);
+int scl_tuple_loss_fwd_bwd(const float* emb, int T, int P, int N, int D, const float* sq_d_dists,
+                           const scl_tuple_params* p, float* loss, float* demb,
+                           void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* L6: logratio_loss, model/losses.py:125-135 (call train/train.py:854-855, distances train.py:564-571).
+ * Tuple mode = mean over tuples of the reference's T=1 formula.  strict_reference=1 reproduces the
+ * reference's broadcast (feature ratio over all (n,p) pairs, GPS ratio element-wise (k,k); needs P==N);
+ * strict_reference=0 uses the all-pairs GPS ratio of Kim et al.
+ *   emb [T,1+P+N,D], sq_pos [T,P], sq_neg [T,N] (squared metres). */
+int scl_logratio_fwd_bwd(const float* emb, int T, int P, int N, int D, const float* sq_pos, const float* sq_neg,
+                         int strict_reference, float* loss, float* demb,
+                         void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* D1: _pairwise_squared_distances, model/losses.py:656-661:  out[t,i,j] = r_i - 2 x_i.x_j + r_j
+ * (no clamp, diagonal not forced to zero).  x [T,n,D] -> out [T,n,n]. */
+int scl_pairwise_sqdist(const float* x, int T, int n, int D, float* out, scl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N1: NetVLAD head.  Replaces  x = tf.nn.l2_normalize(x, axis=-1); x = layers.netVLAD(x, 64)
+ * at model/nets.py:66-67 (and model/grad_nets.py:66-67) and its autodiff backward.
+ *   x        [B,HW,C] f32   conv5_3 map, NHWC flattened over space (C = 512 in the reference)
+ *   assign_w [C,K]    f32   'assignment/kernel' [1,1,C,K]
+ *   centers  [C,K]    f32   'cluster_centers'  [1,1,1,C,K] (stored negated upstream, hence added)
+ *   out      [B,C*K]  f32   index c*K + k
+ * Workspace keeps what backward needs (soft assignments, raw VLAD, norms); pass the SAME workspace to bwd.
+ * Requires C % 4 == 0, K == 64. */
+int scl_netvlad_workspace_bytes(int B, int HW, int C, int K, size_t* bytes);
+int scl_netvlad_fwd(const float* x, const float* assign_w, const float* centers, int B, int HW, int C, int K,
+                    float* out, void* workspace, size_t workspace_bytes, scl_stream_t stream);
+int scl_netvlad_bwd(const float* x, const float* assign_w, const float* centers, const float* dout,
+                    int B, int HW, int C, int K, float* dx, float* dassign_w, float* dcenters,
+                    void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* P1: PCA-whitening projection.  Replaces train/train.py:646-652
+ *   y = matmul(x - m, v, adjoint_b=True) / sqrt(var)           (eval twin: evaluation/top-n.py:74-77)
+ *   x [B,Din], v [Dout,Din], m [Din], var [Dout] -> y [B,Dout];  backward: dx = (dy / sqrt(var)) v. */
+int scl_pca_fwd(const float* x, const float* v, const float* m, const float* var, int B, int Din, int Dout,
+                float* y, scl_stream_t stream);
+int scl_pca_bwd(const float* dy, const float* v, const float* var, int B, int Din, int Dout,
+                float* dx, scl_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * R1: exact brute-force kNN.  Replaces
+ *   KDTree(ref_f).query(query_f, k=N, return_distance=True, sort_results=True)
+ * at evaluation/top-n.py:103-106 (and train/train.py:1181-1182 k=5, :451 k=MINING_CACHE_SIZE).
+ *
+ * An index is the fp32 database shard itself plus a device-side "shadow": fp16 copy (row pitch Dp =
+ * round_up(D,64)) for the tensor-core candidate pass and exact fp32 squared norms.
+ *   scl_knn_shadow_bytes   size of the shadow for R rows
+ *   scl_knn_build          fills the shadow from db [R,D] f32 (one pass over the database)
+ *   scl_knn_query          dist [Q,k] f64 Euclidean ascending, idx [Q,k] i64 = local row + idx_offset,
+ *                          ties ordered by index; exact (every query is either certified against the
+ *                          fp16 rounding bound or recomputed by the exact fp32->fp64 path).
+ *                          stats (optional, device i32[4]): {n_queries, n_certified, n_fallback, path}
+ *   force_path: 0 auto, 1 exact scan only, 2 tensor pass (+fallback), 3 tensor pass with every query
+ *               forced through the fallback as well (test hook).
+ * Requires D % 4 == 0, k <= 1024 (tensor pass used when k <= 64 and the problem is large enough). */
+int scl_knn_shadow_bytes(int64_t R, int D, size_t* bytes);
+int scl_knn_build(const float* db, int64_t R, int D, void* shadow, size_t shadow_bytes, scl_stream_t stream);
+int scl_knn_query_workspace_bytes(int64_t R, int D, int Q, int k, size_t* bytes);
+int scl_knn_query(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                  int64_t idx_offset, int force_path, double* dist, int64_t* idx, int32_t* stats,
+                  void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* Merge of G per-shard sorted top-k lists (after an all-gather): d_all [G,Q,k] f64, i_all [G,Q,k] i64
+ * -> d [Q,k], i [Q,k], ordered by (distance, index).  SURVEY.md section 8(e). */
+int scl_topk_merge(const double* d_all, const int64_t* i_all, int G, int Q, int k,
+                   double* d, int64_t* i, scl_stream_t stream);
+
+/* R2: geographic bookkeeping of evaluation/top-n.py:69,110-113 without materialising the [Q,R] matrix:
+ *   top_g_dists[q,j] = |query_xy[q] - ref_xy[top_i[q,j]]|,  gt_i[q] = argmin_r |query_xy[q]-ref_xy[r]|,
+ *   gt_g_dist[q] = that minimum.  xy arrays are f64 [.,2]; top_i indexes ref_xy directly. */
+int scl_geo_topn(const double* query_xy, const double* ref_xy, int Q, int64_t R, const int64_t* top_i, int k,
+                 double* top_g_dists, int64_t* gt_i, double* gt_g_dist, scl_stream_t stream);
+
+/* R3: recall curves.  evaluation/roc.py:213-216 / train/train.py:368-375:
+ *   curve[n,x] = 100 * |{q : min_{j<=n} top_g_dists[q,j] < thresholds[x]}| / Q   for n < k. */
+int scl_recall_curves(const double* top_g_dists, int Q, int k, const double* thresholds, int n_thresholds,
+                      double* curves, scl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCL_B200_H */

@@ -297,7 +297,7 @@ def value_and_grad(fn, diff_args, *args, **kw):
     xs = [_t(a).clone().requires_grad_(True) for a in diff_args]
     loss = fn(*xs, *args, **kw)
     grads = torch.autograd.grad(loss, xs, allow_unused=True)
-    return float(loss), [None if g is None else g.numpy() for g in grads]
+    return float(loss.detach()), [None if g is None else g.numpy() for g in grads]
 
 
 def split_tuple(emb, P, N, other=False):

@@ -1,0 +1,102 @@
+"""ctypes binding of libscl_b200.so (include/scl_b200.h).  No fallback: a missing library raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscl_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+c_f32p = C.c_void_p
+c_ptr = C.c_void_p
+
+
+class MsParams(C.Structure):
+    _fields_ = [("d_alpha", C.c_float), ("d_beta", C.c_float), ("alpha", C.c_float), ("beta", C.c_float),
+                ("lamb", C.c_float), ("eps", C.c_float), ("ms_mining", C.c_int32), ("wfunction", C.c_int32),
+                ("sumfunction", C.c_int32)]
+
+
+class TupleParams(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("dist_term", C.c_int32), ("m1", C.c_float), ("m2", C.c_float),
+                ("lam", C.c_float), ("d_max_squared", C.c_float), ("f_max_squared", C.c_float)]
+
+
+WF = {"exp": 0, "lin": 1, "tanh": 2}
+SUMF = {"ms": 0, "plain": 1}
+TUPLE_KIND = {"triplet_loss": 0, "lazy_triplet_loss": 1, "quadruplet_loss": 2, "lazy_quadruplet_loss": 3,
+              "evil_triplet_loss": 4, "evil_quadruplet_loss": 5}
+DIST_TERM = {"none": 0, "distance_loss": 1, "huber_distance_loss": 2}
+
+# name -> (restype, argtypes); mirrors include/scl_b200.h one to one
+_SIZE_P = C.POINTER(C.c_size_t)
+PROTOTYPES = {
+    "scl_version": (C.c_int, []),
+    "scl_strerror": (C.c_char_p, [C.c_int]),
+    "scl_last_error": (C.c_char_p, []),
+    "scl_device_ok": (C.c_int, []),
+    "scl_wms_tuple_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, _SIZE_P]),
+    "scl_wms_tuple_fwd_bwd": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.POINTER(MsParams), c_ptr, c_ptr,
+                                        c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "scl_ms_flat_workspace_bytes": (C.c_int, [C.c_int, C.c_int, _SIZE_P]),
+    "scl_wms_flat_fwd_bwd": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.POINTER(MsParams), c_ptr, c_ptr, c_ptr, c_ptr,
+                                       C.c_size_t, c_ptr]),
+    "scl_ms_flat_fwd_bwd": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.POINTER(MsParams), c_ptr, c_ptr, c_ptr, c_ptr,
+                                      C.c_size_t, c_ptr]),
+    "scl_tuple_loss_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _SIZE_P]),
+    "scl_tuple_loss_fwd_bwd": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.POINTER(TupleParams), c_ptr,
+                                         c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "scl_logratio_fwd_bwd": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr,
+                                       c_ptr, C.c_size_t, c_ptr]),
+    "scl_pairwise_sqdist": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "scl_netvlad_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _SIZE_P]),
+    "scl_netvlad_fwd": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t,
+                                  c_ptr]),
+    "scl_netvlad_bwd": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr,
+                                  c_ptr, C.c_size_t, c_ptr]),
+    "scl_pca_fwd": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "scl_pca_bwd": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "scl_knn_shadow_bytes": (C.c_int, [C.c_int64, C.c_int, _SIZE_P]),
+    "scl_knn_build": (C.c_int, [c_ptr, C.c_int64, C.c_int, c_ptr, C.c_size_t, c_ptr]),
+    "scl_knn_query_workspace_bytes": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, _SIZE_P]),
+    "scl_knn_query": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int64, C.c_int, c_ptr,
+                                c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "scl_topk_merge": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "scl_geo_topn": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int64, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "scl_recall_curves": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr]),
+}
+
+
+class SclError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library.  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise SclError(
+                        f"{LIB_PATH} is missing. Build it with `python -m soft_contrastive_learning_b200.build` "
+                        "(nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in PROTOTYPES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        L = lib()
+        msg = L.scl_strerror(status).decode()
+        detail = L.scl_last_error().decode() if status == -5 else ""
+        raise SclError(f"{what}: {msg}" + (f" [{detail}]" if detail else ""))

@@ -1,0 +1,90 @@
+// common.cuh -- shared helpers for libscl_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/scl_b200.h"
+
+namespace scl {
+
+void set_last_error(const char* what, cudaError_t e);
+int check_device();  // SCL_OK or SCL_ERR_ARCH / SCL_ERR_CUDA
+int num_sms();
+
+#define SCL_CUDA_TRY(expr)                                   \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) {                                 \
+      ::scl::set_last_error(#expr, _e);                      \
+      return SCL_ERR_CUDA;                                   \
+    }                                                        \
+  } while (0)
+
+#define SCL_LAUNCH_CHECK()                                   \
+  do {                                                       \
+    cudaError_t _e = cudaGetLastError();                     \
+    if (_e != cudaSuccess) {                                 \
+      ::scl::set_last_error("kernel launch", _e);            \
+      return SCL_ERR_CUDA;                                   \
+    }                                                        \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace (256-byte granules).
+struct Carver {
+  char* base;
+  size_t off;
+  size_t cap;
+  Carver(void* p, size_t bytes) : base(static_cast<char*>(p)), off(0), cap(bytes) {}
+  template <typename T>
+  T* take(size_t n) {
+    size_t b = round_up(n * sizeof(T), 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += b;
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+static inline size_t carve_bytes(size_t n, size_t elem) { return round_up(n * elem, 256); }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// streaming 128-bit global load / store (read-once data: keep it out of L1)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+#endif
+
+}  // namespace scl

@@ -1,0 +1,800 @@
+// knn.cu -- R1/R2/R3: exact brute-force kNN over a database shard, shard merge, geo bookkeeping, recall.
+//
+// Replaces KDTree(ref_f).query(query_f, k=N, return_distance=True, sort_results=True)
+// (/root/reference/evaluation/top-n.py:103-106; train/train.py:1181-1182, :451) and the bookkeeping of
+// top-n.py:69,110-117 / roc.py:213-216 / train.py:368-375.
+//
+// Two device paths, both returning EXACT float64 results ordered by (distance, index):
+//   exact scan   d^2(q,r) = sum (q_i - r_i)^2 accumulated in float64 for every row, radix-select of the k smallest.
+//   tensor pass  (knn_tc.cu) fp16 scores on tcgen05 keep k'=64 candidates per (query, database range);
+//                here: merge the ranges, rescore the 64 best candidates exactly (float64), order them and
+//                CERTIFY each query: with T the 64th smallest fp16 score and eps a rigorous bound on
+//                |fp16 score - exact score|, every row that is not a candidate has d^2 >= T + |q|^2 - eps, so
+//                when the k-th exact candidate distance is below that, the exact top-k is inside the candidate set.
+//                Queries that fail the certificate are recomputed by the exact scan.  No approximation is returned.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "knn_internal.cuh"
+
+namespace scl {
+
+// ---------------------------------------------------------------------------------------------
+// index build
+// ---------------------------------------------------------------------------------------------
+static inline size_t shadow_norm_off() { return sizeof(ShadowHeader); }
+static inline size_t shadow_data_off(int64_t R) { return sizeof(ShadowHeader) + round_up(size_t(R) * sizeof(float), 1024); }
+static inline int pad64(int D) { return (D + 63) / 64 * 64; }
+
+__global__ void knn_header_init_kernel(ShadowHeader* h, long long R, int D, int Dp) {
+  h->R = R; h->D = D; h->Dp = Dp;
+  h->maxabs_bits = 0u; h->scale_exp = 0; h->rmax2_bits = 0ull; h->built = 0;
+}
+
+// pass 1: exact squared norms (float64 accumulate), max |x|, max norm.  One warp per row.
+__global__ void __launch_bounds__(256) knn_build_stats_kernel(const float* __restrict__ db, long long R, int D,
+                                                              float* __restrict__ rn, ShadowHeader* h) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  float mx = 0.0f;
+  double rmax = 0.0;
+  for (long long r = warp; r < R; r += nw) {
+    const float4* row = reinterpret_cast<const float4*>(db + size_t(r) * D);
+    double acc = 0.0;
+    for (int c = lane; c < (D >> 2); c += 32) {
+      const float4 v = ldg_stream(row + c);
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      acc = fma(double(v.x), double(v.x), acc);
+      acc = fma(double(v.y), double(v.y), acc);
+      acc = fma(double(v.z), double(v.z), acc);
+      acc = fma(double(v.w), double(v.w), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) rn[r] = float(acc);
+    rmax = fmax(rmax, acc);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) {
+    atomicMax(&h->maxabs_bits, __float_as_uint(mx));
+    atomicMax(&h->rmax2_bits, (unsigned long long)__double_as_longlong(rmax));
+  }
+}
+
+// power-of-two scale that puts max|x| in [2^13, 2^14): fp16 keeps 11 significant bits for everything within
+// 2^-27 of the largest magnitude and cannot overflow
+__device__ __forceinline__ int scale_exp_for(float maxabs) {
+  if (!(maxabs > 0.0f) || isinf(maxabs)) return 0;
+  return 13 - ilogbf(maxabs);
+}
+
+__global__ void knn_build_scale_kernel(ShadowHeader* h) {
+  h->scale_exp = scale_exp_for(__uint_as_float(h->maxabs_bits));
+  h->built = 1;
+}
+
+// pass 2: fp16 shadow rows (pitch Dp, zero padded)
+__global__ void __launch_bounds__(256) knn_build_convert_kernel(const float* __restrict__ db, long long R, int D, int Dp,
+                                                                const ShadowHeader* __restrict__ h,
+                                                                __half* __restrict__ out) {
+  const float sc = ldexpf(1.0f, h->scale_exp);
+  const long long total4 = R * (long long)(Dp >> 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (Dp >> 2);
+    const int c = int(i - r * (Dp >> 2)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < D) v = ldg_stream(reinterpret_cast<const float4*>(db + size_t(r) * D + c));
+    __half2 lo = __floats2half2_rn(v.x * sc, v.y * sc), hi = __floats2half2_rn(v.z * sc, v.w * sc);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + size_t(r) * Dp + c) = pk;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// query preparation: fp16 copy with a per-query power-of-two scale, |q|^2 in float64
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) knn_query_prep_kernel(const float* __restrict__ q, int Q, int D, int Dp,
+                                                             const ShadowHeader* __restrict__ h, __half* __restrict__ qh,
+                                                             float* __restrict__ qmul, double* __restrict__ qn2,
+                                                             int* __restrict__ qexp) {
+  __shared__ float s_mx[8];
+  __shared__ double s_acc[8];
+  const int qi = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* row = q + size_t(qi) * D;
+  float mx = 0.0f;
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float v = row[c];
+    mx = fmaxf(mx, fabsf(v));
+    acc = fma(double(v), double(v), acc);
+  }
+  mx = warp_max(mx);
+  acc = warp_sum(acc);
+  if (lane == 0) { s_mx[warp] = mx; s_acc[warp] = acc; }
+  __syncthreads();
+  mx = 0.0f; acc = 0.0;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) { mx = fmaxf(mx, s_mx[w]); acc += s_acc[w]; }
+  const int e = scale_exp_for(mx);
+  const float sc = ldexpf(1.0f, e);
+  for (int c = threadIdx.x; c < Dp; c += blockDim.x) qh[size_t(qi) * Dp + c] = __float2half_rn(c < D ? row[c] * sc : 0.0f);
+  if (threadIdx.x == 0) {
+    qmul[qi] = -2.0f * ldexpf(1.0f, -(e + h->scale_exp));
+    qn2[qi] = acc;
+    qexp[qi] = e;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tensor pass, stage 2: merge the per-range candidate lists of one query, keep the kKeep best fp16 scores
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long cand_key64(float s, uint32_t idx) {
+  uint32_t u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return (static_cast<unsigned long long>(u) << 32) | idx;
+}
+__device__ __forceinline__ float key64_score(unsigned long long k) {
+  uint32_t u = uint32_t(k >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(u);
+}
+
+template <typename K>
+__device__ __forceinline__ void bitonic_sort_smem(K* keys, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < (n_pow2 >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        K a = keys[lo], b = keys[hi];
+        if ((b < a) == up) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __restrict__ cand_s,
+                                                             const uint32_t* __restrict__ cand_i,
+                                                             const int* __restrict__ cand_cnt, int NR, int n_pow2,
+                                                             uint32_t* __restrict__ sel_idx, float* __restrict__ sel_T,
+                                                             int* __restrict__ sel_n) {
+  extern __shared__ unsigned long long mkeys[];
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) mkeys[i] = ~0ull;
+  __syncthreads();
+  // slot layout: range r occupies [r*kKeep, (r+1)*kKeep)
+  int total = 0;
+  for (int r = 0; r < NR; ++r) {
+    const int c = cand_cnt[size_t(q) * NR + r];
+    total += c;
+    const size_t base = (size_t(q) * NR + r) * kCandCap;
+    for (int e = threadIdx.x; e < c; e += blockDim.x) mkeys[r * kKeep + e] = cand_key64(cand_s[base + e], cand_i[base + e]);
+  }
+  bitonic_sort_smem(mkeys, n_pow2);
+  if (threadIdx.x < kKeep) {
+    const unsigned long long k = mkeys[threadIdx.x];
+    sel_idx[size_t(q) * kKeep + threadIdx.x] = (threadIdx.x < total) ? uint32_t(k & 0xffffffffu) : 0xffffffffu;
+  }
+  if (threadIdx.x == 0) {
+    sel_n[q] = total;
+    sel_T[q] = total >= kKeep ? key64_score(mkeys[kKeep - 1]) : INFINITY;
+  }
+}
+
+// exact squared distances of the selected candidates: one warp per (query, candidate), float64 accumulation of
+// direct differences (what KDTree's leaf scan computes)
+__global__ void __launch_bounds__(256) knn_rescore_kernel(const float* __restrict__ db, const float* __restrict__ q,
+                                                          int D, const uint32_t* __restrict__ sel_idx, long long pairs,
+                                                          double* __restrict__ d2) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= pairs) return;
+  const uint32_t r = sel_idx[p];
+  if (r == 0xffffffffu) {
+    if (lane == 0) d2[p] = INFINITY;
+    return;
+  }
+  const long long qi = p / kKeep;
+  const float4* qr = reinterpret_cast<const float4*>(q + size_t(qi) * D);
+  const float4* rr = reinterpret_cast<const float4*>(db + size_t(r) * D);
+  double acc = 0.0;
+  for (int c = lane; c < (D >> 2); c += 32) {
+    const float4 a = __ldg(qr + c);
+    const float4 b = ldg_stream(rr + c);
+    double d;
+    d = double(a.x) - double(b.x); acc = fma(d, d, acc);
+    d = double(a.y) - double(b.y); acc = fma(d, d, acc);
+    d = double(a.z) - double(b.z); acc = fma(d, d, acc);
+    d = double(a.w) - double(b.w); acc = fma(d, d, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) d2[p] = acc;
+}
+
+// rigorous bound on |fp16-pass score - exact score| for query q against ANY row of the shard
+__device__ double knn_eps(double qnorm, int eq, const ShadowHeader* h) {
+  const double u = ldexp(1.0, -11), a = ldexp(1.0, -25);
+  const double rmax = sqrt(__longlong_as_double((long long)h->rmax2_bits));
+  const double Qn = ldexp(qnorm, eq), Rn = ldexp(rmax, h->scale_exp);
+  const double sD = sqrt(double(h->Dp));
+  const double Qt = Qn * (1.0 + u) + a * sD, Rt = Rn * (1.0 + u) + a * sD;        // norms of the rounded vectors
+  double e = u * (2.0 + u) * Qn * Rn + a * (1.0 + u) * sD * (Qn + Rn) + double(h->Dp) * a * a;   // input rounding
+  e += (double(h->Dp) / 16.0 + 1.0) * ldexp(1.0, -21) * Qt * Rt;                // tensor-core fp32 accumulation
+  const double e_dot = ldexp(e, -(eq + h->scale_exp));
+  const double smax = rmax * rmax + 2.0 * qnorm * rmax + 2.0 * e_dot;
+  return 2.0 * e_dot + ldexp(1.0, -23) * (rmax * rmax + smax);                    // + norm and fma rounding
+}
+
+// order the kKeep rescored candidates of one query by (d^2, idx), emit the top-k, certify.  One warp per query.
+__global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __restrict__ sel_idx,
+                                                           const double* __restrict__ d2, const float* __restrict__ sel_T,
+                                                           const int* __restrict__ sel_n, const double* __restrict__ qn2,
+                                                           const int* __restrict__ qexp, const ShadowHeader* __restrict__ h,
+                                                           int Q, int k, long long idx_offset, int force_all,
+                                                           double* __restrict__ out_d, long long* __restrict__ out_i,
+                                                           int* __restrict__ flag_list, int* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  double md[2];
+  uint32_t mi[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    md[u] = d2[size_t(q) * kKeep + lane + 32 * u];
+    mi[u] = sel_idx[size_t(q) * kKeep + lane + 32 * u];
+  }
+  int rank[2] = {0, 0};
+  for (int src = 0; src < 32; ++src) {
+#pragma unroll
+    for (int su = 0; su < 2; ++su) {
+      const double od = __shfl_sync(0xffffffffu, md[su], src);
+      const uint32_t oi = __shfl_sync(0xffffffffu, mi[su], src);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) rank[u] += (od < md[u] || (od == md[u] && oi < mi[u])) ? 1 : 0;
+    }
+  }
+  double kth = INFINITY;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (rank[u] < k) {
+      const bool real = mi[u] != 0xffffffffu;
+      out_d[size_t(q) * k + rank[u]] = real ? sqrt(md[u]) : INFINITY;
+      out_i[size_t(q) * k + rank[u]] = real ? (long long)mi[u] + idx_offset : -1ll;
+    }
+    if (rank[u] == k - 1) kth = md[u];
+  }
+  // broadcast the k-th exact distance
+  for (int o = 16; o > 0; o >>= 1) kth = fmin(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+  if (lane == 0) {
+    bool ok;
+    if ((long long)sel_n[q] >= h->R) {
+      ok = true;                                   // every row of the shard was rescored
+    } else {
+      const double eps = knn_eps(sqrt(qn2[q]), qexp[q], h);
+      ok = kth < double(sel_T[q]) + qn2[q] - eps;
+    }
+    if (force_all) ok = false;
+    if (ok) {
+      atomicAdd(&stats[1], 1);
+    } else {
+      const int slot = atomicAdd(&stats[2], 1);
+      flag_list[slot] = q;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact scan: float64 distances of QT staged queries against every row, then radix select
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanQT = 8;
+
+// qsel == nullptr: queries q0..q0+qt-1; else queries qsel[q0..].  d2 [qt, R].
+__global__ void __launch_bounds__(256) knn_scan_kernel(const float* __restrict__ db, long long R, int D,
+                                                       const float* __restrict__ q, const int* __restrict__ qsel,
+                                                       int q0, int qt, double* __restrict__ d2) {
+  extern __shared__ __align__(16) float sq[];   // [qt][D]
+  for (int i = threadIdx.x; i < qt * (D >> 2); i += blockDim.x) {
+    const int qq = i / (D >> 2), c = i - qq * (D >> 2);
+    const int qi = qsel ? qsel[q0 + qq] : q0 + qq;
+    reinterpret_cast<float4*>(sq)[i] = __ldg(reinterpret_cast<const float4*>(q + size_t(qi) * D) + c);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long r = warp; r < R; r += nw) {
+    const float4* row = reinterpret_cast<const float4*>(db + size_t(r) * D);
+    double acc[kScanQT];
+#pragma unroll
+    for (int u = 0; u < kScanQT; ++u) acc[u] = 0.0;
+    for (int c = lane; c < (D >> 2); c += 32) {
+      const float4 b = ldg_stream(row + c);
+      const double bx = b.x, by = b.y, bz = b.z, bw = b.w;
+#pragma unroll
+      for (int u = 0; u < kScanQT; ++u) {
+        if (u < qt) {
+          const float4 a = reinterpret_cast<const float4*>(sq)[u * (D >> 2) + c];
+          double d;
+          d = double(a.x) - bx; acc[u] = fma(d, d, acc[u]);
+          d = double(a.y) - by; acc[u] = fma(d, d, acc[u]);
+          d = double(a.z) - bz; acc[u] = fma(d, d, acc[u]);
+          d = double(a.w) - bw; acc[u] = fma(d, d, acc[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kScanQT; ++u) {
+      if (u < qt) {
+        const double s = warp_sum(acc[u]);
+        if (lane == 0) d2[size_t(u) * R + r] = s;
+      }
+    }
+  }
+}
+
+constexpr int kSelThreads = 1024;
+constexpr int kTieCap = 4096;
+
+struct SelKey {
+  unsigned long long d;   // bit pattern of a non-negative double: orders like the double
+  unsigned long long i;
+  __device__ bool operator<(const SelKey& o) const { return d < o.d || (d == o.d && i < o.i); }
+};
+
+// One CTA per query: MSB-first radix select (8 bits per pass) of the k-th smallest d^2, then gather + sort.
+// d2 [nq, R]; out slot given by qsel (or q0 + blockIdx.x).
+__global__ void __launch_bounds__(kSelThreads) knn_select_kernel(const double* __restrict__ d2, long long R, int k,
+                                                                 const int* __restrict__ qsel, int q0,
+                                                                 long long idx_offset, SelKey* __restrict__ scratch,
+                                                                 double* __restrict__ out_d,
+                                                                 long long* __restrict__ out_i) {
+  extern __shared__ unsigned char sel_smem[];
+  SelKey* skeys = reinterpret_cast<SelKey*>(sel_smem);     // [kpow2]
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned int s_krem, s_nless, s_neq;
+  const int qq = blockIdx.x;
+  const int qi = qsel ? qsel[q0 + qq] : q0 + qq;
+  const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(d2 + size_t(qq) * R);
+  const int kk = int(min((long long)k, R));
+  if (threadIdx.x == 0) { s_prefix = 0ull; s_krem = unsigned(kk); }
+  for (int pass = 0; pass < 8; ++pass) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    const int shift = 56 - 8 * pass;
+    for (long long r = threadIdx.x; r < R; r += blockDim.x) {
+      const unsigned long long key = keys[r];
+      const bool match = pass == 0 ? true : ((key >> (shift + 8)) == (prefix >> (shift + 8)));
+      if (match) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int krem = s_krem, cum = 0;
+      int b = 0;
+      for (; b < 256; ++b) {
+        if (cum + hist[b] >= krem) break;
+        cum += hist[b];
+      }
+      s_krem = krem - cum;
+      s_prefix = prefix | ((unsigned long long)b << shift);
+    }
+    __syncthreads();
+  }
+  const unsigned long long kth = s_prefix;      // exact bit pattern of the k-th smallest d^2
+  const unsigned int need_eq = s_krem;           // how many rows equal to kth belong to the answer
+  if (threadIdx.x == 0) { s_nless = 0u; s_neq = 0u; }
+  int kpow2 = 1;
+  while (kpow2 < kk) kpow2 <<= 1;
+  SelKey* ties = scratch + size_t(qq) * kTieCap;
+  __syncthreads();
+  for (long long r = threadIdx.x; r < R; r += blockDim.x) {
+    const unsigned long long key = keys[r];
+    if (key < kth) {
+      const unsigned int slot = atomicAdd(&s_nless, 1u);
+      skeys[slot].d = key;
+      skeys[slot].i = (unsigned long long)r;
+    } else if (key == kth) {
+      const unsigned int slot = atomicAdd(&s_neq, 1u);
+      if (slot < kTieCap) { ties[slot].d = key; ties[slot].i = (unsigned long long)r; }
+    }
+  }
+  __syncthreads();
+  const unsigned int nless = s_nless, neq = min(s_neq, (unsigned int)kTieCap);
+  // among the rows tied at the k-th distance keep the need_eq smallest indices
+  if (neq == need_eq) {
+    for (unsigned int e = threadIdx.x; e < neq; e += blockDim.x) skeys[nless + e] = ties[e];
+  } else {
+    for (unsigned int e = threadIdx.x; e < neq; e += blockDim.x) {
+      const unsigned long long mine = ties[e].i;
+      unsigned int rank = 0;
+      for (unsigned int x = 0; x < neq; ++x) rank += ties[x].i < mine ? 1u : 0u;
+      if (rank < need_eq) skeys[nless + rank] = ties[e];
+    }
+  }
+  for (int e = int(nless + need_eq) + threadIdx.x; e < kpow2; e += blockDim.x) { skeys[e].d = ~0ull; skeys[e].i = ~0ull; }
+  bitonic_sort_smem(skeys, kpow2);
+  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+    if (e < kk) {
+      out_d[size_t(qi) * k + e] = sqrt(__longlong_as_double((long long)skeys[e].d));
+      out_i[size_t(qi) * k + e] = (long long)skeys[e].i + idx_offset;
+    } else {
+      out_d[size_t(qi) * k + e] = INFINITY;
+      out_i[size_t(qi) * k + e] = -1ll;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shard merge, geo bookkeeping, recall
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pair_less(double d0, long long i0, double d1, long long i1) {
+  // padding entries (index < 0) sort last
+  if ((i0 < 0) != (i1 < 0)) return i1 < 0;
+  return d0 < d1 || (d0 == d1 && i0 < i1);
+}
+
+__global__ void __launch_bounds__(256) topk_merge_kernel(const double* __restrict__ d_all, const long long* __restrict__ i_all,
+                                                         int G, int Q, int k, double* __restrict__ d,
+                                                         long long* __restrict__ i) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)G * Q * k) return;
+  const int g = int(e / ((long long)Q * k));
+  const long long rem = e - (long long)g * Q * k;
+  const int q = int(rem / k), j = int(rem - (long long)q * k);
+  const double md = d_all[e];
+  const long long mi = i_all[e];
+  // rank = number of entries, over all shard lists of this query, that order before (md, mi)
+  int rank = j;    // entries before it in its own (sorted) list
+  for (int g2 = 0; g2 < G; ++g2) {
+    if (g2 == g) continue;
+    const double* ld = d_all + ((size_t)g2 * Q + q) * k;
+    const long long* li = i_all + ((size_t)g2 * Q + q) * k;
+    int lo = 0, hi = k;                 // first position whose entry is NOT less than mine
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (pair_less(ld[mid], li[mid], md, mi)) lo = mid + 1; else hi = mid;
+    }
+    rank += lo;
+  }
+  if (rank < k) {
+    d[(size_t)q * k + rank] = mi < 0 ? INFINITY : md;
+    i[(size_t)q * k + rank] = mi < 0 ? -1ll : mi;
+  }
+}
+
+__global__ void __launch_bounds__(256) geo_topn_kernel(const double* __restrict__ qxy, const double* __restrict__ rxy,
+                                                       int Q, long long R, const long long* __restrict__ top_i, int k,
+                                                       double* __restrict__ top_g, long long* __restrict__ gt_i,
+                                                       double* __restrict__ gt_d) {
+  __shared__ double s_d[8];
+  __shared__ long long s_i[8];
+  const int q = blockIdx.x;
+  const double x = qxy[2 * q], y = qxy[2 * q + 1];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const long long r = top_i[(size_t)q * k + j];
+    double v = INFINITY;
+    if (r >= 0 && r < R) {
+      const double dx = x - rxy[2 * r], dy = y - rxy[2 * r + 1];
+      v = sqrt(dx * dx + dy * dy);
+    }
+    top_g[(size_t)q * k + j] = v;
+  }
+  double best = INFINITY;
+  long long bi = -1;
+  for (long long r = threadIdx.x; r < R; r += blockDim.x) {
+    const double dx = x - rxy[2 * r], dy = y - rxy[2 * r + 1];
+    const double v = dx * dx + dy * dy;
+    if (v < best) { best = v; bi = r; }      // strided scan keeps the lowest index within a thread
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov < best || (ov == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_d[warp] = best; s_i[warp] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (blockDim.x >> 5); ++w)
+      if (s_d[w] < best || (s_d[w] == best && s_i[w] >= 0 && (bi < 0 || s_i[w] < bi))) { best = s_d[w]; bi = s_i[w]; }
+    gt_i[q] = bi;                              // np.argmin: first minimum
+    gt_d[q] = sqrt(best);
+  }
+}
+
+__global__ void recall_zero_kernel(double* curves, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) curves[i] = 0.0;
+}
+__global__ void __launch_bounds__(256) recall_count_kernel(const double* __restrict__ top_g, int Q, int k,
+                                                           const double* __restrict__ thr, int nx,
+                                                           double* __restrict__ curves) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  double m = INFINITY;
+  for (int n = 0; n < k; ++n) {
+    m = fmin(m, top_g[(size_t)q * k + n]);       // top_n[q,n] = min(d[q,0..n])   (train.py:368-371)
+    for (int x = 0; x < nx; ++x)
+      if (m < thr[x]) atomicAdd(&curves[n * nx + x], 1.0);    // counts are small integers: exact in float64
+  }
+}
+__global__ void recall_scale_kernel(double* curves, int n, int Q) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) curves[i] = curves[i] / double(Q) * 100.0;       // float(sum(...)) / float(len) * 100  (roc.py:216)
+}
+
+// ---------------------------------------------------------------------------------------------
+// orchestration
+// ---------------------------------------------------------------------------------------------
+struct QueryWs {
+  __half* qh;
+  float* qmul;
+  double* qn2;
+  int* qexp;
+  float* cand_s;
+  uint32_t* cand_i;
+  int* cand_cnt;
+  uint32_t* sel_idx;
+  float* sel_T;
+  int* sel_n;
+  double* d2;
+  int* flag_list;
+  int* stats;
+  double* scan_d2;
+  SelKey* sel_scratch;
+  int scan_qb;
+};
+
+static int scan_batch(int64_t R) {
+  // queries per exact-scan launch: keep the [qb, R] float64 buffer <= 256 MB
+  long long qb = (256ll << 20) / (8ll * (R > 0 ? R : 1));
+  if (qb < 1) qb = 1;
+  if (qb > 64) qb = 64;
+  return int(qb);
+}
+static int scan_qt(int D) {
+  int qt = int((96 * 1024) / (size_t(D) * 4));
+  if (qt > kScanQT) qt = kScanQT;
+  if (qt < 1) qt = 1;
+  return qt;
+}
+
+static bool use_tensor_pass(int64_t R, int D, int Q, int k, int force_path) {
+  if (force_path == 1) return false;
+  if (k > kKeep || (D & 3) || R >= (1ll << 31) || R < 1024) return false;
+  if (force_path >= 2) return true;
+  return double(Q) * double(R) >= double(1 << 22) && R >= 4096;
+}
+
+static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* base, size_t bytes) {
+  Carver c(base, bytes);
+  const int Dp = pad64(D);
+  int mb, nt, NR, tpr;
+  knn_tc_tiling(Q, R, &mb, &nt, &NR, &tpr);
+  QueryWs tmp;
+  QueryWs* o = w ? w : &tmp;
+  o->stats = c.take<int>(8);
+  o->qh = c.take<__half>(size_t(Q) * Dp);
+  o->qmul = c.take<float>(Q);
+  o->qn2 = c.take<double>(Q);
+  o->qexp = c.take<int>(Q);
+  o->cand_s = c.take<float>(size_t(Q) * NR * kCandCap);
+  o->cand_i = c.take<uint32_t>(size_t(Q) * NR * kCandCap);
+  o->cand_cnt = c.take<int>(size_t(Q) * NR);
+  o->sel_idx = c.take<uint32_t>(size_t(Q) * kKeep);
+  o->sel_T = c.take<float>(Q);
+  o->sel_n = c.take<int>(Q);
+  o->d2 = c.take<double>(size_t(Q) * kKeep);
+  o->flag_list = c.take<int>(Q);
+  o->scan_qb = scan_batch(R);
+  o->scan_d2 = c.take<double>(size_t(o->scan_qb) * R);
+  o->sel_scratch = c.take<SelKey>(size_t(o->scan_qb) * kTieCap);
+  (void)k;
+  return c.off;
+}
+
+// exact scan + select for `nq` queries (all of them, or those listed in qsel)
+static int run_exact(const float* db, int64_t R, int D, const float* queries, const int* qsel, int nq, int k,
+                     int64_t idx_offset, double* dist, int64_t* idx, const QueryWs& w, cudaStream_t stream) {
+  const int qt = scan_qt(D);
+  const size_t scan_smem = size_t(qt) * D * sizeof(float);
+  static size_t scan_cfg = 0;
+  if (scan_smem > 48 * 1024 && scan_cfg < scan_smem) {
+    SCL_CUDA_TRY(cudaFuncSetAttribute(knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scan_smem)));
+    scan_cfg = scan_smem;
+  }
+  int kpow2 = 1;
+  const int kk = int(k < R ? k : R);
+  while (kpow2 < kk) kpow2 <<= 1;
+  const size_t sel_smem = size_t(kpow2) * sizeof(SelKey);
+  long long rows_per_cta = 8;
+  int scan_grid = int(std::min<long long>((R + rows_per_cta - 1) / rows_per_cta, (long long)num_sms() * 8));
+  for (int b0 = 0; b0 < nq; b0 += w.scan_qb) {
+    const int nb = std::min(w.scan_qb, nq - b0);
+    for (int s0 = 0; s0 < nb; s0 += qt) {
+      const int n = std::min(qt, nb - s0);
+      knn_scan_kernel<<<scan_grid, 256, scan_smem, stream>>>(db, R, D, queries, qsel, b0 + s0, n,
+                                                             w.scan_d2 + size_t(s0) * R);
+      SCL_LAUNCH_CHECK();
+    }
+    knn_select_kernel<<<nb, kSelThreads, sel_smem, stream>>>(w.scan_d2, R, k, qsel, b0, idx_offset, w.sel_scratch, dist,
+                                                             reinterpret_cast<long long*>(idx));
+    SCL_LAUNCH_CHECK();
+  }
+  return SCL_OK;
+}
+
+}  // namespace scl
+
+using namespace scl;
+
+extern "C" int scl_knn_shadow_bytes(int64_t R, int D, size_t* bytes) {
+  if (!bytes || R < 1 || D < 4 || (D & 3)) return SCL_ERR_BAD_ARG;
+  *bytes = shadow_data_off(R) + size_t(R) * pad64(D) * sizeof(__half);
+  return SCL_OK;
+}
+
+extern "C" int scl_knn_build(const float* db, int64_t R, int D, void* shadow, size_t shadow_bytes, scl_stream_t stream_) {
+  if (!db || !shadow || R < 1) return SCL_ERR_BAD_ARG;
+  if (D < 4 || (D & 3)) return SCL_ERR_BAD_SHAPE;
+  if (!aligned16(db) || (reinterpret_cast<uintptr_t>(shadow) & 255u)) return SCL_ERR_ALIGN;
+  size_t need = 0;
+  scl_knn_shadow_bytes(R, D, &need);
+  if (shadow_bytes < need) return SCL_ERR_WORKSPACE;
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  char* sb = static_cast<char*>(shadow);
+  ShadowHeader* h = reinterpret_cast<ShadowHeader*>(sb);
+  float* rn = reinterpret_cast<float*>(sb + shadow_norm_off());
+  __half* data = reinterpret_cast<__half*>(sb + shadow_data_off(R));
+  const int Dp = pad64(D);
+  knn_header_init_kernel<<<1, 1, 0, stream>>>(h, R, D, Dp);
+  SCL_LAUNCH_CHECK();
+  const int grid = num_sms() * 8;
+  knn_build_stats_kernel<<<grid, 256, 0, stream>>>(db, R, D, rn, h);
+  SCL_LAUNCH_CHECK();
+  knn_build_scale_kernel<<<1, 1, 0, stream>>>(h);
+  SCL_LAUNCH_CHECK();
+  knn_build_convert_kernel<<<grid, 256, 0, stream>>>(db, R, D, Dp, h, data);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+extern "C" int scl_knn_query_workspace_bytes(int64_t R, int D, int Q, int k, size_t* bytes) {
+  if (!bytes || R < 1 || Q < 1 || k < 1 || D < 4 || (D & 3)) return SCL_ERR_BAD_ARG;
+  *bytes = query_ws_layout(R, D, Q, k, nullptr, nullptr, 0);
+  return SCL_OK;
+}
+
+extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                             int64_t idx_offset, int force_path, double* dist, int64_t* idx, int32_t* stats,
+                             void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
+  if (!db || !queries || !dist || !idx || !workspace) return SCL_ERR_BAD_ARG;
+  if (R < 1 || Q < 1 || k < 1 || k > 1024 || D < 4 || (D & 3)) return SCL_ERR_BAD_SHAPE;
+  if (!aligned16(db) || !aligned16(queries) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return SCL_ERR_ALIGN;
+  int rc = check_device();
+  if (rc) return rc;
+  QueryWs w;
+  const size_t need = query_ws_layout(R, D, Q, k, &w, workspace, workspace_bytes);
+  if (workspace_bytes < need) return SCL_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool tensor = use_tensor_pass(R, D, Q, k, force_path);
+  if (tensor && !shadow) return SCL_ERR_BAD_ARG;
+  SCL_CUDA_TRY(cudaMemsetAsync(w.stats, 0, 8 * sizeof(int), stream));
+
+  if (!tensor) {
+    rc = run_exact(db, R, D, queries, nullptr, Q, k, idx_offset, dist, idx, w, stream);
+    if (rc) return rc;
+    if (stats) {
+      const int host_stats[4] = {Q, 0, Q, 1};
+      SCL_CUDA_TRY(cudaMemcpyAsync(stats, host_stats, sizeof(host_stats), cudaMemcpyHostToDevice, stream));
+      SCL_CUDA_TRY(cudaStreamSynchronize(stream));      // host_stats lives on this stack frame
+    }
+    return SCL_OK;
+  }
+
+  const char* sb = static_cast<const char*>(shadow);
+  const ShadowHeader* h = reinterpret_cast<const ShadowHeader*>(sb);
+  const float* rn = reinterpret_cast<const float*>(sb + shadow_norm_off());
+  const __half* dbh = reinterpret_cast<const __half*>(sb + shadow_data_off(R));
+  const int Dp = pad64(D);
+
+  knn_query_prep_kernel<<<Q, 256, 0, stream>>>(queries, Q, D, Dp, h, w.qh, w.qmul, w.qn2, w.qexp);
+  SCL_LAUNCH_CHECK();
+
+  TcArgs a = {};
+  a.rn = rn; a.qmul = w.qmul; a.Q = Q; a.R = int(R); a.Dp = Dp;
+  knn_tc_tiling(Q, R, &a.num_m_blocks, &a.num_n_tiles, &a.NR, &a.tiles_per_range);
+  a.cand_s = w.cand_s; a.cand_i = w.cand_i; a.cand_cnt = w.cand_cnt;
+  a.dbg_scores = nullptr;
+  const char* dbg = getenv("SCL_KNN_DEBUG_SCORES");     // test hook: address of a [Q,R] float buffer, in hex
+  if (dbg) a.dbg_scores = reinterpret_cast<float*>(strtoull(dbg, nullptr, 16));
+  rc = knn_tc_launch(a, w.qh, dbh, stream);
+  if (rc) return rc;
+
+  int n_pow2 = 1;
+  while (n_pow2 < a.NR * kKeep) n_pow2 <<= 1;
+  const size_t merge_smem = size_t(n_pow2) * sizeof(unsigned long long);
+  static size_t merge_cfg = 0;
+  if (merge_smem > 48 * 1024 && merge_cfg < merge_smem) {
+    SCL_CUDA_TRY(cudaFuncSetAttribute(knn_cand_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(merge_smem)));
+    merge_cfg = merge_smem;
+  }
+  knn_cand_merge_kernel<<<Q, 256, merge_smem, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, a.NR, n_pow2, w.sel_idx, w.sel_T,
+                                                        w.sel_n);
+  SCL_LAUNCH_CHECK();
+  const long long pairs = (long long)Q * kKeep;
+  knn_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, stream>>>(db, queries, D, w.sel_idx, pairs, w.d2);
+  SCL_LAUNCH_CHECK();
+  knn_finalize_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(w.sel_idx, w.d2, w.sel_T, w.sel_n, w.qn2, w.qexp, h, Q, k,
+                                                       idx_offset, force_path == 3 ? 1 : 0, dist,
+                                                       reinterpret_cast<long long*>(idx), w.flag_list, w.stats);
+  SCL_LAUNCH_CHECK();
+
+  // the number of uncertified queries decides how much exact work follows: one small device->host read
+  int hs[4] = {0, 0, 0, 0};
+  SCL_CUDA_TRY(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
+  SCL_CUDA_TRY(cudaStreamSynchronize(stream));
+  const int nflag = hs[2];
+  if (nflag > 0) {
+    rc = run_exact(db, R, D, queries, w.flag_list, nflag, k, idx_offset, dist, idx, w, stream);
+    if (rc) return rc;
+  }
+  if (stats) {
+    const int host_stats[4] = {Q, hs[1], nflag, 2};
+    SCL_CUDA_TRY(cudaMemcpyAsync(stats, host_stats, sizeof(host_stats), cudaMemcpyHostToDevice, stream));
+    SCL_CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  return SCL_OK;
+}
+
+extern "C" int scl_topk_merge(const double* d_all, const int64_t* i_all, int G, int Q, int k, double* d, int64_t* i,
+                              scl_stream_t stream) {
+  if (!d_all || !i_all || !d || !i || G < 1 || Q < 1 || k < 1) return SCL_ERR_BAD_ARG;
+  int rc = check_device();
+  if (rc) return rc;
+  const long long n = (long long)G * Q * k;
+  topk_merge_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_all, reinterpret_cast<const long long*>(i_all), G, Q, k, d, reinterpret_cast<long long*>(i));
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+extern "C" int scl_geo_topn(const double* query_xy, const double* ref_xy, int Q, int64_t R, const int64_t* top_i, int k,
+                            double* top_g_dists, int64_t* gt_i, double* gt_g_dist, scl_stream_t stream) {
+  if (!query_xy || !ref_xy || !top_i || !top_g_dists || !gt_i || !gt_g_dist || Q < 1 || R < 1 || k < 1)
+    return SCL_ERR_BAD_ARG;
+  int rc = check_device();
+  if (rc) return rc;
+  geo_topn_kernel<<<Q, 256, 0, static_cast<cudaStream_t>(stream)>>>(query_xy, ref_xy, Q, R,
+                                                                   reinterpret_cast<const long long*>(top_i), k, top_g_dists,
+                                                                   reinterpret_cast<long long*>(gt_i), gt_g_dist);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+extern "C" int scl_recall_curves(const double* top_g_dists, int Q, int k, const double* thresholds, int n_thresholds,
+                                 double* curves, scl_stream_t stream_) {
+  if (!top_g_dists || !thresholds || !curves || Q < 1 || k < 1 || n_thresholds < 1) return SCL_ERR_BAD_ARG;
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int n = k * n_thresholds;
+  recall_zero_kernel<<<(n + 255) / 256, 256, 0, stream>>>(curves, n);
+  SCL_LAUNCH_CHECK();
+  recall_count_kernel<<<(Q + 255) / 256, 256, 0, stream>>>(top_g_dists, Q, k, thresholds, n_thresholds, curves);
+  SCL_LAUNCH_CHECK();
+  recall_scale_kernel<<<(n + 255) / 256, 256, 0, stream>>>(curves, n, Q);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}

@@ -1,0 +1,38 @@
+// knn_internal.cuh -- structures shared by knn.cu (orchestration, exact kernels) and knn_tc.cu (tensor pass).
+#pragma once
+#include "common.cuh"
+
+namespace scl {
+
+constexpr int kKeep = 64;        // k': candidates kept per (query, database range) and rescored per query
+constexpr int kCandCap = 128;    // capacity of one candidate list (k' + slack between prunes)
+
+// Device-resident description of a database shard's shadow copy (first 256 bytes of the shadow buffer).
+struct ShadowHeader {
+  long long R;
+  int D, Dp;
+  unsigned int maxabs_bits;      // max |x| over the shard (float bits; non-negative floats order like uints)
+  int scale_exp;                 // fp16 copy holds x * 2^scale_exp
+  unsigned long long rmax2_bits; // max squared row norm (double bits)
+  int built;
+  int pad[55];
+};
+static_assert(sizeof(ShadowHeader) == 256, "header must stay 256 bytes");
+
+struct TcArgs {
+  const float* rn;       // [R] exact squared row norms (fp32-rounded)
+  const float* qmul;     // [Q] -2 * 2^-(scale_db + scale_q)
+  int Q;
+  int R;
+  int Dp;
+  int num_m_blocks, num_n_tiles, NR, tiles_per_range;
+  float* cand_s;         // [Q, NR, kCandCap]
+  uint32_t* cand_i;      // [Q, NR, kCandCap]
+  int* cand_cnt;         // [Q, NR]
+  float* dbg_scores;     // optional [Q, R]: raw fp16-pass scores (tests)
+};
+
+int knn_tc_launch(const TcArgs& a, const void* queries_fp16, const void* db_fp16, cudaStream_t stream);
+void knn_tc_tiling(int Q, int64_t R, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range);
+
+}  // namespace scl

@@ -1,0 +1,389 @@
+// netvlad.cu -- N1 NetVLAD aggregation head (forward + backward) and P1 PCA-whitening projection.
+//
+// N1 replaces  x = tf.nn.l2_normalize(x, axis=-1); x = layers.netVLAD(x, 64)   (/root/reference/model/nets.py:66-67)
+//   xh = x / max(|x|, 1e-6)                                   per spatial position
+//   a  = softmax_k(xh W)                                      soft assignment, W = 'assignment/kernel' [C,K]
+//   V[c,k] = sum_n a[n,k] (xh[n,c] + Cc[c,k])                 Cc = 'cluster_centers' (stored negated upstream)
+//   V[:,k] /= sqrt(sum_c V[c,k]^2 + 1e-12)                    intra-normalisation
+//   out = flatten_{c*K+k}(V) / sqrt(sum V^2 + 1e-12)
+// The [B,h,w,C,K] residual tensor of the upstream graph is never formed: V = X^T A + Cc * colsum(A).
+// P1 replaces train/train.py:650-651:  y = ((x - m) V^T) / sqrt(var).
+//
+// Contractions run on sgemm.cuh (FP32 FFMA) in this version; the row-normalisation, soft-max, and the two vector
+// norms are fused warp-shuffle kernels.
+#include <algorithm>
+
+#include "sgemm.cuh"
+
+namespace scl {
+
+struct NvWs {
+  float* inv;     // [B*HW]   1/|x|
+  float* a;       // [B*HW,K] soft assignments
+  float* V;       // [B,C,K]  un-normalised VLAD (after the centre term)
+  float* asum;    // [B,K]
+  float* nk;      // [B,K]    intra norms
+  float* nt;      // [B]      total norms
+  float* dV;      // [B,C,K]
+  float* da;      // [B*HW,K] (backward scratch: da then ds)
+  float* dasum;   // [B,K]
+};
+
+static size_t nv_ws_bytes(int B, int HW, int C, int K) {
+  size_t n = 0;
+  n += carve_bytes(size_t(B) * HW, 4);
+  n += 2 * carve_bytes(size_t(B) * HW * K, 4);
+  n += 2 * carve_bytes(size_t(B) * C * K, 4);
+  n += 3 * carve_bytes(size_t(B) * K, 4);
+  n += carve_bytes(B, 4);
+  return n;
+}
+static NvWs nv_carve(void* p, size_t bytes, int B, int HW, int C, int K) {
+  Carver c(p, bytes);
+  NvWs w;
+  w.inv = c.take<float>(size_t(B) * HW);
+  w.a = c.take<float>(size_t(B) * HW * K);
+  w.da = c.take<float>(size_t(B) * HW * K);
+  w.V = c.take<float>(size_t(B) * C * K);
+  w.dV = c.take<float>(size_t(B) * C * K);
+  w.asum = c.take<float>(size_t(B) * K);
+  w.nk = c.take<float>(size_t(B) * K);
+  w.dasum = c.take<float>(size_t(B) * K);
+  w.nt = c.take<float>(B);
+  return w;
+}
+
+// inv[p] = rsqrt(max(sum_c x[p,c]^2, 1e-12))  -- tf.nn.l2_normalize (nets.py:66).  One warp per position.
+__global__ void __launch_bounds__(256) nv_rownorm_kernel(const float* __restrict__ x, long long P, int C,
+                                                         float* __restrict__ inv) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  const float4* row = reinterpret_cast<const float4*>(x + size_t(p) * C);
+  float s = 0.0f;
+  for (int c = lane; c < (C >> 2); c += 32) {
+    const float4 v = __ldg(row + c);
+    s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) inv[p] = rsqrtf(fmaxf(s, 1e-12f));
+}
+
+// in-place softmax over K = 64 columns; one warp per position (2 values per lane)
+__global__ void __launch_bounds__(256) nv_softmax_kernel(float* __restrict__ a, long long P) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  float* row = a + size_t(p) * 64;
+  float v0 = row[lane], v1 = row[lane + 32];
+  const float m = warp_max(fmaxf(v0, v1));
+  v0 = expf(v0 - m);
+  v1 = expf(v1 - m);
+  const float s = warp_sum(v0 + v1);
+  row[lane] = v0 / s;
+  row[lane + 32] = v1 / s;
+}
+
+// asum[b,k] = sum_n a[b,n,k].  One CTA (256 threads) per image: 4 row groups x 64 columns.
+__global__ void __launch_bounds__(256) nv_colsum_kernel(const float* __restrict__ a, int HW, float* __restrict__ asum) {
+  __shared__ float s[4][64];
+  const int b = blockIdx.x, k = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const float* A = a + size_t(b) * HW * 64;
+  float acc = 0.0f;
+  for (int n = g; n < HW; n += 4) acc += A[size_t(n) * 64 + k];
+  s[g][k] = acc;
+  __syncthreads();
+  if (g == 0) asum[b * 64 + k] = (s[0][k] + s[1][k]) + (s[2][k] + s[3][k]);
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = 0.0f;
+  for (int w = 0; w < 8; ++w) r += sh[w];
+  return r;
+}
+
+// V += Cc * asum; intra-norm per cluster; flatten; l2 norm.  One CTA per image, K = 64.
+__global__ void __launch_bounds__(256) nv_norm_fwd_kernel(float* __restrict__ V, const float* __restrict__ centers,
+                                                          const float* __restrict__ asum, int C, float* __restrict__ nk,
+                                                          float* __restrict__ nt, float* __restrict__ out) {
+  __shared__ float s_col[4][64];
+  __shared__ float s_nk[64];
+  __shared__ float s_red[8];
+  const int b = blockIdx.x, k = threadIdx.x & 63, g = threadIdx.x >> 6;
+  float* Vb = V + size_t(b) * C * 64;
+  const float as = asum[b * 64 + k];
+  float ss = 0.0f;
+  for (int c = g; c < C; c += 4) {
+    const float v = Vb[size_t(c) * 64 + k] + centers[size_t(c) * 64 + k] * as;
+    Vb[size_t(c) * 64 + k] = v;
+    ss = fmaf(v, v, ss);
+  }
+  s_col[g][k] = ss;
+  __syncthreads();
+  if (g == 0) {
+    const float n = sqrtf((s_col[0][k] + s_col[1][k]) + (s_col[2][k] + s_col[3][k]) + 1e-12f);
+    s_nk[k] = n;
+    nk[b * 64 + k] = n;
+  }
+  __syncthreads();
+  const float ink = 1.0f / s_nk[k];
+  float tot = 0.0f;
+  for (int c = g; c < C; c += 4) {
+    const float v = Vb[size_t(c) * 64 + k] * ink;
+    tot = fmaf(v, v, tot);
+  }
+  tot = block_sum_256(tot, s_red);
+  const float n_t = sqrtf(tot + 1e-12f);
+  if (threadIdx.x == 0) nt[b] = n_t;
+  const float sc = ink / n_t;
+  float* ob = out + size_t(b) * C * 64;
+  for (int c = g; c < C; c += 4) ob[size_t(c) * 64 + k] = Vb[size_t(c) * 64 + k] * sc;
+}
+
+// backward of the two norms: dV from dout.  One CTA per image.
+//   out = V1 / nt, V1 = V / nk:   dV1 = (dout - out (out.dout)) / nt ;  dV = (dV1 - V1 (V1.dV1)_c) / nk
+__global__ void __launch_bounds__(256) nv_norm_bwd_kernel(const float* __restrict__ V, const float* __restrict__ dout,
+                                                          const float* __restrict__ nk, const float* __restrict__ nt,
+                                                          int C, float* __restrict__ dV) {
+  __shared__ float s_col[4][64];
+  __shared__ float s_dot[64];
+  __shared__ float s_red[8];
+  const int b = blockIdx.x, k = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const float* Vb = V + size_t(b) * C * 64;
+  const float* db = dout + size_t(b) * C * 64;
+  float* dvb = dV + size_t(b) * C * 64;
+  const float ink = 1.0f / nk[b * 64 + k], intt = 1.0f / nt[b];
+  float dot = 0.0f;
+  for (int c = g; c < C; c += 4) dot = fmaf(Vb[size_t(c) * 64 + k] * ink * intt, db[size_t(c) * 64 + k], dot);
+  dot = block_sum_256(dot, s_red);                 // out . dout
+  float cd = 0.0f;
+  for (int c = g; c < C; c += 4) {
+    const float v1 = Vb[size_t(c) * 64 + k] * ink;
+    const float dv1 = (db[size_t(c) * 64 + k] - v1 * intt * dot) * intt;
+    cd = fmaf(v1, dv1, cd);
+  }
+  s_col[g][k] = cd;
+  __syncthreads();
+  if (g == 0) s_dot[k] = (s_col[0][k] + s_col[1][k]) + (s_col[2][k] + s_col[3][k]);
+  __syncthreads();
+  const float cdk = s_dot[k];
+  for (int c = g; c < C; c += 4) {
+    const float v1 = Vb[size_t(c) * 64 + k] * ink;
+    const float dv1 = (db[size_t(c) * 64 + k] - v1 * intt * dot) * intt;
+    dvb[size_t(c) * 64 + k] = (dv1 - v1 * cdk) * ink;
+  }
+}
+
+// dcenters[c,k] = sum_b dV[b,c,k] asum[b,k]
+__global__ void __launch_bounds__(256) nv_dcenters_kernel(const float* __restrict__ dV, const float* __restrict__ asum,
+                                                          int B, int C, float* __restrict__ dcenters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 64) return;
+  const int k = i & 63;
+  float acc = 0.0f;
+  for (int b = 0; b < B; ++b) acc = fmaf(dV[size_t(b) * C * 64 + i], asum[b * 64 + k], acc);
+  dcenters[i] = acc;
+}
+
+// dasum[b,k] = sum_c dV[b,c,k] Cc[c,k]
+__global__ void __launch_bounds__(256) nv_dasum_kernel(const float* __restrict__ dV, const float* __restrict__ centers,
+                                                       int C, float* __restrict__ dasum) {
+  __shared__ float s[4][64];
+  const int b = blockIdx.x, k = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const float* dvb = dV + size_t(b) * C * 64;
+  float acc = 0.0f;
+  for (int c = g; c < C; c += 4) acc = fmaf(dvb[size_t(c) * 64 + k], centers[size_t(c) * 64 + k], acc);
+  s[g][k] = acc;
+  __syncthreads();
+  if (g == 0) dasum[b * 64 + k] = (s[0][k] + s[1][k]) + (s[2][k] + s[3][k]);
+}
+
+// ds = a * ((da + dasum) - sum_k a (da + dasum)); in place on da.  One warp per position.
+__global__ void __launch_bounds__(256) nv_softmax_bwd_kernel(const float* __restrict__ a, float* __restrict__ da,
+                                                             const float* __restrict__ dasum, long long P, int HW) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  const int b = int(p / HW);
+  const float a0 = a[size_t(p) * 64 + lane], a1 = a[size_t(p) * 64 + lane + 32];
+  const float g0 = da[size_t(p) * 64 + lane] + dasum[b * 64 + lane];
+  const float g1 = da[size_t(p) * 64 + lane + 32] + dasum[b * 64 + lane + 32];
+  const float dot = warp_sum(a0 * g0 + a1 * g1);
+  da[size_t(p) * 64 + lane] = a0 * (g0 - dot);
+  da[size_t(p) * 64 + lane + 32] = a1 * (g1 - dot);
+}
+
+// dx = inv * (dxh - xh (xh . dxh)), xh = x * inv; in place on dx (which holds dxh).  One warp per position.
+__global__ void __launch_bounds__(256) nv_l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ inv,
+                                                            long long P, int C, float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  const float iv = inv[p];
+  const bool clamped = iv >= 1e6f * 0.999f;       // sum x^2 below 1e-12: the normalisation is a pure scale
+  const float4* xr = reinterpret_cast<const float4*>(x + size_t(p) * C);
+  float4* dr = reinterpret_cast<float4*>(dx + size_t(p) * C);
+  float dot = 0.0f;
+  for (int c = lane; c < (C >> 2); c += 32) {
+    const float4 xv = __ldg(xr + c), dv = dr[c];
+    dot = fmaf(xv.x * iv, dv.x, dot); dot = fmaf(xv.y * iv, dv.y, dot);
+    dot = fmaf(xv.z * iv, dv.z, dot); dot = fmaf(xv.w * iv, dv.w, dot);
+  }
+  dot = warp_sum(dot);
+  if (clamped) dot = 0.0f;
+  for (int c = lane; c < (C >> 2); c += 32) {
+    const float4 xv = __ldg(xr + c);
+    float4 dv = dr[c];
+    dv.x = iv * (dv.x - xv.x * iv * dot); dv.y = iv * (dv.y - xv.y * iv * dot);
+    dv.z = iv * (dv.z - xv.z * iv * dot); dv.w = iv * (dv.w - xv.w * iv * dot);
+    dr[c] = dv;
+  }
+}
+
+static int nv_check(int B, int HW, int C, int K) {
+  if (B < 1 || HW < 1 || C < 4 || (C & 3)) return SCL_ERR_BAD_SHAPE;
+  if (K != 64) return SCL_ERR_UNSUPPORTED;     // the reference only ever calls netVLAD(x, 64)
+  return SCL_OK;
+}
+
+}  // namespace scl
+
+using namespace scl;
+
+extern "C" int scl_netvlad_workspace_bytes(int B, int HW, int C, int K, size_t* bytes) {
+  if (!bytes) return SCL_ERR_BAD_ARG;
+  int rc = nv_check(B, HW, C, K);
+  if (rc) return rc;
+  *bytes = nv_ws_bytes(B, HW, C, K);
+  return SCL_OK;
+}
+
+extern "C" int scl_netvlad_fwd(const float* x, const float* assign_w, const float* centers, int B, int HW, int C, int K,
+                               float* out, void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
+  if (!x || !assign_w || !centers || !out || !workspace) return SCL_ERR_BAD_ARG;
+  int rc = nv_check(B, HW, C, K);
+  if (rc) return rc;
+  if (!aligned16(x) || !aligned16(out) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return SCL_ERR_ALIGN;
+  if (workspace_bytes < nv_ws_bytes(B, HW, C, K)) return SCL_ERR_WORKSPACE;
+  rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NvWs w = nv_carve(workspace, workspace_bytes, B, HW, C, K);
+  const long long P = (long long)B * HW;
+  nv_rownorm_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(x, P, C, w.inv);
+  SCL_LAUNCH_CHECK();
+  // logits = (X W) * inv[row]
+  GemmArgs g = gemm_args(x, assign_w, w.a, int(P), K, C, C, K, K, 0, 0);
+  g.row_scale = w.inv;
+  rc = gemm_launch(g, stream);
+  if (rc) return rc;
+  nv_softmax_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(w.a, P);
+  SCL_LAUNCH_CHECK();
+  nv_colsum_kernel<<<B, 256, 0, stream>>>(w.a, HW, w.asum);
+  SCL_LAUNCH_CHECK();
+  // V[b] = (X[b] * inv)^T A[b]     M = C, N = K, contraction over the HW positions
+  GemmArgs h = gemm_args(x, w.a, w.V, C, K, HW, C, K, K, 1, 0);
+  h.batch = B;
+  h.sA = (long long)HW * C; h.sB = (long long)HW * K; h.sC = (long long)C * K;
+  h.a_mul_k = w.inv; h.a_mul_k_stride = HW;
+  rc = gemm_launch(h, stream);
+  if (rc) return rc;
+  nv_norm_fwd_kernel<<<B, 256, 0, stream>>>(w.V, centers, w.asum, C, w.nk, w.nt, out);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+extern "C" int scl_netvlad_bwd(const float* x, const float* assign_w, const float* centers, const float* dout, int B,
+                               int HW, int C, int K, float* dx, float* dassign_w, float* dcenters, void* workspace,
+                               size_t workspace_bytes, scl_stream_t stream_) {
+  if (!x || !assign_w || !centers || !dout || !workspace) return SCL_ERR_BAD_ARG;
+  int rc = nv_check(B, HW, C, K);
+  if (rc) return rc;
+  if (workspace_bytes < nv_ws_bytes(B, HW, C, K)) return SCL_ERR_WORKSPACE;
+  rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NvWs w = nv_carve(workspace, workspace_bytes, B, HW, C, K);
+  const long long P = (long long)B * HW;
+  nv_norm_bwd_kernel<<<B, 256, 0, stream>>>(w.V, dout, w.nk, w.nt, C, w.dV);
+  SCL_LAUNCH_CHECK();
+  if (dcenters) {
+    nv_dcenters_kernel<<<(C * 64 + 255) / 256, 256, 0, stream>>>(w.dV, w.asum, B, C, dcenters);
+    SCL_LAUNCH_CHECK();
+  }
+  nv_dasum_kernel<<<B, 256, 0, stream>>>(w.dV, centers, C, w.dasum);
+  SCL_LAUNCH_CHECK();
+  // da[b] = (X[b] dV[b]) * inv[row]      M = HW, N = K, contraction over C
+  GemmArgs g = gemm_args(x, w.dV, w.da, HW, K, C, C, K, K, 0, 0);
+  g.batch = B;
+  g.sA = (long long)HW * C; g.sB = (long long)C * K; g.sC = (long long)HW * K;
+  g.row_scale = w.inv; g.row_scale_stride = HW;
+  rc = gemm_launch(g, stream);
+  if (rc) return rc;
+  nv_softmax_bwd_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(w.a, w.da, w.dasum, P, HW);
+  SCL_LAUNCH_CHECK();
+  if (dassign_w) {
+    // dW = (X * inv)^T dS      M = C, N = K, contraction over all B*HW positions (split-K with atomics)
+    SCL_CUDA_TRY(cudaMemsetAsync(dassign_w, 0, size_t(C) * K * sizeof(float), stream));
+    GemmArgs d = gemm_args(x, w.da, dassign_w, C, K, int(P), C, K, K, 1, 0);
+    d.a_mul_k = w.inv;
+    long long chunks = (P + kGemmBK - 1) / kGemmBK;
+    d.split_k = int(std::min<long long>(chunks, 2ll * num_sms() / ((C + 127) / 128)));
+    if (d.split_k < 1) d.split_k = 1;
+    rc = gemm_launch(d, stream);
+    if (rc) return rc;
+  }
+  if (dx) {
+    if (!aligned16(dx)) return SCL_ERR_ALIGN;
+    // dxh[b] = A[b] dV[b]^T (aggregation path)   M = HW, N = C, contraction over K
+    GemmArgs e = gemm_args(w.a, w.dV, dx, HW, C, K, K, K, C, 0, 1);
+    e.batch = B;
+    e.sA = (long long)HW * K; e.sB = (long long)C * K; e.sC = (long long)HW * C;
+    rc = gemm_launch(e, stream);
+    if (rc) return rc;
+    // dxh += dS W^T (assignment path)
+    GemmArgs f = gemm_args(w.da, assign_w, dx, int(P), C, K, K, K, C, 0, 1);
+    f.accumulate = 1;
+    rc = gemm_launch(f, stream);
+    if (rc) return rc;
+    nv_l2norm_bwd_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(x, w.inv, P, C, dx);
+    SCL_LAUNCH_CHECK();
+  }
+  return SCL_OK;
+}
+
+extern "C" int scl_pca_fwd(const float* x, const float* v, const float* m, const float* var, int B, int Din, int Dout,
+                           float* y, scl_stream_t stream_) {
+  if (!x || !v || !m || !var || !y) return SCL_ERR_BAD_ARG;
+  if (B < 1 || Din < 1 || Dout < 1) return SCL_ERR_BAD_SHAPE;
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GemmArgs g = gemm_args(x, v, y, B, Dout, Din, Din, Din, Dout, 0, 1);      // (x - m) V^T, then / sqrt(var)
+  g.a_sub_k = m;
+  g.col_isqrt = var;
+  const int ctas = ((B + 127) / 128) * ((Dout + 127) / 128);
+  const int chunks = (Din + kGemmBK - 1) / kGemmBK;
+  int split = (2 * num_sms() + ctas - 1) / ctas;
+  if (split > chunks / 8) split = chunks / 8;
+  if (split < 1) split = 1;
+  g.split_k = split;
+  if (split > 1) SCL_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(B) * Dout * sizeof(float), stream));
+  return gemm_launch(g, stream);
+}
+
+extern "C" int scl_pca_bwd(const float* dy, const float* v, const float* var, int B, int Din, int Dout, float* dx,
+                           scl_stream_t stream_) {
+  if (!dy || !v || !var || !dx) return SCL_ERR_BAD_ARG;
+  if (B < 1 || Din < 1 || Dout < 1) return SCL_ERR_BAD_SHAPE;
+  int rc = check_device();
+  if (rc) return rc;
+  GemmArgs g = gemm_args(dy, v, dx, B, Din, Dout, Dout, Din, Din, 0, 0);    // (dy / sqrt(var)) V
+  g.a_isqrt_k = var;
+  return gemm_launch(g, static_cast<cudaStream_t>(stream_));
+}

@@ -1,0 +1,107 @@
+"""NetVLAD aggregation head and PCA-whitening projection, by the reference's names.
+
+Host-side mirror of
+  x = tf.nn.l2_normalize(x, axis=-1); x = layers.netVLAD(x, 64)      /root/reference/model/nets.py:66-67
+  x_tf = tf.matmul(full_out - m, v, adjoint_b=True); output = x_tf / tf.sqrt(var)   train/train.py:646-652
+Forward and backward run in libscl_b200.so (csrc/netvlad.cu); torch owns memory, streams and the autograd tape.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .losses import _f32, _p, _stream, _ws
+
+
+class _NetVladFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, assign_w, centers):
+        B = x.shape[0]
+        Cc = x.shape[-1]
+        K = assign_w.shape[-1]
+        x3 = _f32(x.detach()).reshape(B, -1, Cc)
+        w = _f32(assign_w.detach()).reshape(Cc, K)
+        c = _f32(centers.detach()).reshape(Cc, K)
+        HW = x3.shape[1]
+        L = lib()
+        nbytes = C.c_size_t()
+        check(L.scl_netvlad_workspace_bytes(B, HW, Cc, K, C.byref(nbytes)), "scl_netvlad_workspace_bytes")
+        ws = _ws(nbytes.value, x3.device)
+        out = torch.empty((B, Cc * K), dtype=torch.float32, device=x3.device)
+        check(L.scl_netvlad_fwd(_p(x3), _p(w), _p(c), B, HW, Cc, K, _p(out), _p(ws), ws.numel(), _stream()),
+              "scl_netvlad_fwd")
+        ctx.save_for_backward(x3, w, c, ws)
+        ctx.dims = (B, HW, Cc, K, x.shape, assign_w.shape, centers.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x3, w, c, ws = ctx.saved_tensors
+        B, HW, Cc, K, xs, ws_shape, cs = ctx.dims
+        dout = _f32(dout)
+        need_x, need_w, need_c = ctx.needs_input_grad
+        dx = torch.empty_like(x3) if need_x else None
+        dw = torch.empty_like(w) if need_w else None
+        dc = torch.empty_like(c) if need_c else None
+        check(lib().scl_netvlad_bwd(_p(x3), _p(w), _p(c), _p(dout), B, HW, Cc, K, _p(dx), _p(dw), _p(dc), _p(ws),
+                                    ws.numel(), _stream()), "scl_netvlad_bwd")
+        return (None if dx is None else dx.reshape(xs), None if dw is None else dw.reshape(ws_shape),
+                None if dc is None else dc.reshape(cs))
+
+
+def netVLAD(inputs, assignment_kernel, cluster_centers, num_clusters=64):
+    """``layers.netVLAD(tf.nn.l2_normalize(inputs, -1), num_clusters)`` (model/nets.py:66-67).
+
+    inputs [B,h,w,C] (NHWC conv5_3 map) or [B,HW,C]; assignment_kernel [1,1,C,K] or [C,K] ('assignment/kernel');
+    cluster_centers [1,1,1,C,K] or [C,K] ('cluster_centers').  TF variables become explicit tensors.
+    Returns [B, C*K] (index c*K+k), intra-normalised and L2-normalised."""
+    if assignment_kernel.shape[-1] != num_clusters:
+        raise ValueError("assignment kernel does not match num_clusters")
+    t = [a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+         for a in (inputs, assignment_kernel, cluster_centers)]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = [a if a.is_cuda else a.to(dev) for a in t]
+    out = _NetVladFn.apply(*t)
+    return out.cpu().numpy() if isinstance(inputs, np.ndarray) else out
+
+
+class _PcaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, v, m, var):
+        x2, v2, m1, var1 = _f32(x.detach()), _f32(v.detach()), _f32(m.detach()), _f32(var.detach())
+        B, Din = x2.shape
+        Dout = v2.shape[0]
+        y = torch.empty((B, Dout), dtype=torch.float32, device=x2.device)
+        check(lib().scl_pca_fwd(_p(x2), _p(v2), _p(m1), _p(var1), B, Din, Dout, _p(y), _stream()), "scl_pca_fwd")
+        ctx.save_for_backward(v2, var1)
+        ctx.dims = (B, Din, Dout)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        v2, var1 = ctx.saved_tensors
+        B, Din, Dout = ctx.dims
+        dy = _f32(dy)
+        dx = torch.empty((B, Din), dtype=torch.float32, device=dy.device)
+        check(lib().scl_pca_bwd(_p(dy), _p(v2), _p(var1), B, Din, Dout, _p(dx), _stream()), "scl_pca_bwd")
+        return dx, None, None, None          # v, m, var are fed placeholders, not trained (train.py:647-649)
+
+
+def pca_project(full_out, v, m, var):
+    """train/train.py:650-651: ``matmul(full_out - m, v, adjoint_b=True) / sqrt(var)``.
+    full_out [B,Din], v [Dout,Din], m [Din], var [Dout] -> [B,Dout]."""
+    t = [a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)) for a in (full_out, v, m, var)]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = [a if a.is_cuda else a.to(dev) for a in t]
+    out = _PcaFn.apply(*t)
+    return out.cpu().numpy() if isinstance(full_out, np.ndarray) else out
+
+
+def pca_from_sklearn(pca):
+    """(v, m, var) of a fitted ``sklearn.decomposition.PCA(whiten=True)`` (evaluation/top-n.py:74-75):
+    pca.transform(x) == pca_project(x, components_, mean_, explained_variance_)."""
+    return (np.asarray(pca.components_, dtype=np.float32), np.asarray(pca.mean_, dtype=np.float32),
+            np.asarray(pca.explained_variance_, dtype=np.float32))

@@ -1,0 +1,199 @@
+"""Exact brute-force top-N retrieval, geo bookkeeping and recall@N on B200, by the reference's call shapes.
+
+Host-side mirror of /root/reference/evaluation/top-n.py:69-119 (and train/train.py:1181-1185, 363-386;
+evaluation/roc.py:200-216).  ``KDTree`` below is a drop-in for the one call the reference makes on
+``sklearn.neighbors.KDTree``:  ``KDTree(ref_f).query(query_f, k=N, return_distance=True, sort_results=True)``.
+The neighbour search runs in libscl_b200.so (csrc/knn.cu, csrc/knn_tc.cu): an fp16 tcgen05 candidate pass, an exact
+float64 rescore and a per-query exactness certificate with an exact-scan fallback -- results are the exact float64
+kNN ordered by (distance, index).  With ``torch.distributed`` initialised, ``ShardedKDTree`` splits the database rows
+over the ranks and merges per-shard lists after one NCCL all-gather.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+from .losses import _dev, _f32, _p, _stream, _ws
+
+
+def _f64(x, dev):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+    return x.to(dev, dtype=torch.float64).contiguous()
+
+
+class KDTree:
+    """Exact Euclidean kNN index over the rows of ``X`` (the database shard stays resident in HBM).
+
+    Only the part of sklearn's KDTree API that the reference uses is provided: construction from an
+    [R,D] float array and ``query``.  ``index_offset`` is added to returned indices (shards)."""
+
+    def __init__(self, X, index_offset: int = 0):
+        self.db = _f32(X)
+        if self.db.dim() != 2:
+            raise ValueError("X must be [n_samples, n_features]")
+        self.R, self.D = self.db.shape
+        if self.D % 4:
+            raise ValueError("feature dimension must be a multiple of 4")
+        self.index_offset = int(index_offset)
+        L = lib()
+        nbytes = C.c_size_t()
+        check(L.scl_knn_shadow_bytes(self.R, self.D, C.byref(nbytes)), "scl_knn_shadow_bytes")
+        self.shadow = _ws(nbytes.value, self.db.device)
+        check(L.scl_knn_build(_p(self.db), self.R, self.D, _p(self.shadow), self.shadow.numel(), _stream()),
+              "scl_knn_build")
+        self.last_stats = None
+
+    def query_device(self, queries, k=1, force_path=0):
+        """Device tensors in, device tensors out: (dist [Q,k] float64, idx [Q,k] int64)."""
+        q = _f32(queries)
+        if q.dim() == 1:
+            q = q[None]
+        Q = q.shape[0]
+        if q.shape[1] != self.D:
+            raise ValueError("query dimension mismatch")
+        L = lib()
+        nbytes = C.c_size_t()
+        check(L.scl_knn_query_workspace_bytes(self.R, self.D, Q, k, C.byref(nbytes)), "scl_knn_query_workspace_bytes")
+        ws = _ws(nbytes.value, q.device)
+        dist = torch.empty((Q, k), dtype=torch.float64, device=q.device)
+        idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+        stats = torch.zeros(4, dtype=torch.int32, device=q.device)
+        check(L.scl_knn_query(_p(self.db), _p(self.shadow), self.R, self.D, _p(q), Q, k, self.index_offset,
+                              int(force_path), _p(dist), _p(idx), _p(stats), _p(ws), ws.numel(), _stream()),
+              "scl_knn_query")
+        self.last_stats = stats
+        return dist, idx
+
+    def query(self, X, k=1, return_distance=True, sort_results=True, force_path=0):
+        """``KDTree.query`` as called at evaluation/top-n.py:106.  Results are always sorted ascending."""
+        dist, idx = self.query_device(X, k, force_path)
+        if isinstance(X, np.ndarray) or (isinstance(X, torch.Tensor) and not X.is_cuda):
+            idx_h = idx.cpu().numpy()
+            return (dist.cpu().numpy(), idx_h) if return_distance else idx_h
+        return (dist, idx) if return_distance else idx
+
+    def stats(self):
+        """{n_queries, n_certified, n_fallback, path} of the last query (path 1 = exact scan, 2 = tensor pass)."""
+        s = self.last_stats.cpu().tolist()
+        return {"n_queries": s[0], "n_certified": s[1], "n_fallback": s[2], "path": s[3]}
+
+
+def topk_merge(d_all, i_all):
+    """Merge G sorted per-shard lists: d_all [G,Q,k] float64, i_all [G,Q,k] int64 -> ([Q,k], [Q,k])."""
+    G, Q, k = d_all.shape
+    d = torch.empty((Q, k), dtype=torch.float64, device=d_all.device)
+    i = torch.empty((Q, k), dtype=torch.int64, device=d_all.device)
+    check(lib().scl_topk_merge(_p(d_all.contiguous()), _p(i_all.contiguous()), G, Q, k, _p(d), _p(i), _stream()),
+          "scl_topk_merge")
+    return d, i
+
+
+class ShardedKDTree:
+    """Database rows split contiguously over the ranks of ``group``; queries replicated.
+
+    Each rank answers against its shard (global indices = local + offset); one all-gather of the [Q,k] lists
+    (NCCL over NVLink) followed by the merge kernel gives every rank the exact global top-k."""
+
+    def __init__(self, X_local, index_offset, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local = KDTree(X_local, index_offset=index_offset)
+
+    def query_device(self, queries, k=1, force_path=0):
+        import torch.distributed as dist
+        d, i = self.local.query_device(queries, k, force_path)
+        if self.world == 1:
+            return d, i
+        Q, kk = d.shape
+        # concatenated layout [G*Q, k] (what both NCCL and gloo accept), viewed as [G, Q, k] for the merge
+        d_all = torch.empty((self.world * Q, kk), dtype=d.dtype, device=d.device)
+        i_all = torch.empty((self.world * Q, kk), dtype=i.dtype, device=i.device)
+        dist.all_gather_into_tensor(d_all, d.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(i_all, i.contiguous(), group=self.group)
+        return topk_merge(d_all.view(self.world, Q, kk), i_all.view(self.world, Q, kk))
+
+    def query(self, X, k=1, return_distance=True, sort_results=True):
+        d, i = self.query_device(X, k)
+        if isinstance(X, np.ndarray):
+            return (d.cpu().numpy(), i.cpu().numpy()) if return_distance else i.cpu().numpy()
+        return (d, i) if return_distance else i
+
+
+def shard_bounds(R, world, rank):
+    """Contiguous row split R/G per rank."""
+    per = (R + world - 1) // world
+    lo = min(R, rank * per)
+    return lo, min(R, lo + per)
+
+
+# ----------------------------------------------------------------------------------------------
+# R2 / R3
+# ----------------------------------------------------------------------------------------------
+def geo_topn(query_xy, ref_xy, top_i):
+    """top-n.py:69,110-113 without the [Q,R] distance matrix: (top_g_dists [Q,k], gt_i [Q], gt_g_dist [Q])."""
+    dev = _dev()
+    qxy, rxy = _f64(query_xy, dev), _f64(ref_xy, dev)
+    ti = top_i if isinstance(top_i, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(top_i, dtype=np.int64))
+    ti = ti.to(dev, dtype=torch.int64).contiguous()
+    Q, k = ti.shape
+    R = rxy.shape[0]
+    tg = torch.empty((Q, k), dtype=torch.float64, device=dev)
+    gi = torch.empty(Q, dtype=torch.int64, device=dev)
+    gd = torch.empty(Q, dtype=torch.float64, device=dev)
+    check(lib().scl_geo_topn(_p(qxy), _p(rxy), Q, R, _p(ti), k, _p(tg), _p(gi), _p(gd), _stream()), "scl_geo_topn")
+    return tg, gi, gd
+
+
+def subsample_refs(ref_xy, l):
+    """top-n.py:91-94 greedy subsampling (sequential by construction; host side like the reference)."""
+    ref_xy = np.asarray(ref_xy)
+    ref_idx = [0]
+    last = ref_xy[0]
+    l2 = l ** 2
+    for i in range(len(ref_xy)):
+        d = ref_xy[i] - last
+        if d[0] * d[0] + d[1] * d[1] >= l2:
+            ref_idx.append(i)
+            last = ref_xy[i]
+    return ref_idx
+
+
+def top_n(ref_f, query_f, ref_xy, query_xy, N=25, l=0.0):
+    """Body of get_top_n for one (dimension, l) cell (top-n.py:91-119) on already PCA-projected features.
+    Returns the pickle payload [top_i, top_g_dists, top_f_dists, gt_i, gt_g_dist, ref_idx] (NumPy / lists)."""
+    ref_idx = subsample_refs(ref_xy, l)                                        # :91-94
+    if len(ref_idx) < N:                                                       # :96-97
+        return None
+    ref_idx_np = np.asarray(ref_idx, dtype=np.int64)
+    ref_f = np.asarray(ref_f)
+    sub_f = ref_f[ref_idx_np]                                                  # :99
+    tree = KDTree(sub_f)                                                       # :103
+    top_f_dists, top_i = tree.query(np.asarray(query_f), k=N, return_distance=True, sort_results=True)   # :106
+    sub_xy = np.asarray(ref_xy, dtype=np.float64)[ref_idx_np]
+    tg, gi, gd = geo_topn(np.asarray(query_xy, dtype=np.float64), sub_xy, top_i)                          # :110-113
+    top_i_orig = ref_idx_np[top_i]                                             # :116
+    gt_i = ref_idx_np[gi.cpu().numpy()]                                        # :117
+    return [top_i_orig.tolist(), tg.cpu().numpy().tolist(), top_f_dists, gt_i.tolist(), gd.cpu().numpy(), ref_idx]
+
+
+def recall_curves(top_g_dists, thresholds):
+    """curves[n, x] = % of queries with min_{j<=n} top_g_dists[q,j] < thresholds[x]
+    (train.py:368-375; row 0 is roc.py:213-216's top-1 curve)."""
+    dev = _dev()
+    tg = _f64(np.asarray(top_g_dists, dtype=np.float64) if not isinstance(top_g_dists, torch.Tensor) else top_g_dists, dev)
+    th = _f64(np.asarray(thresholds, dtype=np.float64), dev)
+    Q, k = tg.shape
+    out = torch.empty((k, th.numel()), dtype=torch.float64, device=dev)
+    check(lib().scl_recall_curves(_p(tg), Q, k, _p(th), th.numel(), _p(out), _stream()), "scl_recall_curves")
+    return out.cpu().numpy()
+
+
+def recall_at_n(top_g_dists, rad=25.0, num=25):
+    """train.py:373-375: X = linspace(0, rad, 25); returns (X, Y[n, x])."""
+    X = np.linspace(0, rad, num=num)
+    return X, recall_curves(top_g_dists, X)

@@ -1,0 +1,80 @@
+"""CPU, world_size 2 over gloo: the sharded-retrieval host protocol (contiguous row shards, global index offsets,
+one all-gather of the per-shard [Q,k] lists, merge by (distance, index)) returns the exact global top-k.
+
+The two device-side pieces (local kNN, merge kernel) are replaced by oracle stand-ins injected from here; what is
+exercised is the product's distributed plumbing in soft_contrastive_learning_b200.retrieval."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _OracleLocal:
+    def __init__(self, X, index_offset=0):
+        self.X, self.off = np.asarray(X), index_offset
+
+    def query_device(self, q, k=1, force_path=0):
+        from oracle import retrieval as orr
+        d, i = orr.knn_bruteforce_exact(self.X, np.asarray(q), k)
+        if d.shape[1] < k:      # shard smaller than k: pad like the device path (inf, -1)
+            pad = k - d.shape[1]
+            d = np.concatenate([d, np.full((d.shape[0], pad), np.inf)], 1)
+            i = np.concatenate([i, np.full((i.shape[0], pad), -1 - self.off, dtype=np.int64)], 1)
+        return torch.from_numpy(d), torch.from_numpy(i + self.off)
+
+
+def _numpy_merge(d_all, i_all):
+    G, Q, k = d_all.shape
+    d = d_all.permute(1, 0, 2).reshape(Q, G * k).numpy()
+    i = i_all.permute(1, 0, 2).reshape(Q, G * k).numpy()
+    od = np.empty((Q, k))
+    oi = np.empty((Q, k), dtype=np.int64)
+    for q in range(Q):
+        key_i = np.where(i[q] < 0, np.iinfo(np.int64).max, i[q])
+        order = np.lexsort((key_i, d[q]))[:k]
+        od[q], oi[q] = d[q][order], i[q][order]
+    return torch.from_numpy(od), torch.from_numpy(oi)
+
+
+def _worker(rank, world, port, R, D, Q, k, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from soft_contrastive_learning_b200 import retrieval, synth
+        db, qry, *_ = synth.retrieval_problem(R=R, Q=Q, D=D, seed=5)
+        lo, hi = retrieval.shard_bounds(R, world, rank)
+        retrieval.KDTree = _OracleLocal            # test doubles for the two CUDA pieces
+        retrieval.topk_merge = _numpy_merge
+        tree = retrieval.ShardedKDTree(db[lo:hi], index_offset=lo)
+        d, i = tree.query_device(qry, k)
+        if rank == 0:
+            np.savez(out, d=d.numpy(), i=i.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("R,k", [(257, 5), (40, 25)])
+def test_sharded_protocol_world2(tmp_path, R, k):
+    D, Q = 16, 9
+    out = str(tmp_path / "res.npz")
+    mp.spawn(_worker, args=(2, _free_port(), R, D, Q, k, out), nprocs=2, join=True)
+    from oracle import retrieval as orr
+    from soft_contrastive_learning_b200 import synth
+    db, qry, *_ = synth.retrieval_problem(R=R, Q=Q, D=D, seed=5)
+    ref_d, ref_i = orr.knn_bruteforce_exact(db, qry, k)
+    got = np.load(out)
+    assert np.array_equal(got["i"], ref_i)
+    assert np.allclose(got["d"], ref_d, rtol=1e-12)
