@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the descriptor-space hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload retrieval|wms]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Primary line (metric A): top-25 queries/s against a 1M x 4096 fp32 database (BASELINE config 4: 10 000 queries per
+step).  With N GPUs the 1M rows are split contiguously over the ranks (strong scaling), queries are replicated, the
+per-shard lists are all-gathered over NCCL and merged; `value` = queries / (max-over-ranks device time).
+Secondary (metric B, N=1 only): fused wms forward+backward tuples/s (S=25, D=4096).
+
+One JSON line on stdout (rank 0).  `value` is timed with inputs resident in HBM; `e2e` is the same call fed from
+pinned HOST buffers with the host<->device copies inside the timed region.  `roofline` describes the dominant
+kernel (tcgen05 distance GEMM) with its own device time measured by CUDA events on the launching stream.
+`cpu_baseline` / `--impl reference` time the reference's own CPU call -- sklearn KDTree.query exactly as
+evaluation/top-n.py:103-106 -- on a bounded sample and scale it linearly in the number of rows (a 4096-d KD-tree
+degenerates to a brute-force scan, so linear scaling in R is generous to it); the wms baseline is the oracle port.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+R_FULL, D_FULL, K_TOP = 1_000_000, 4096, 25
+Q_STEP = 10_000
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "tf_burst": j["bf16_tflops"], "tf_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]      # upper half = samples taken under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baselines
+# ------------------------------------------------------------------------------------------------
+def kdtree_reference(steps, warmup, R_s=10_000, Q_s=32, D=D_FULL, k=K_TOP):
+    """The reference's own call (evaluation/top-n.py:103-106) on a bounded sample, scaled linearly to R_FULL rows."""
+    from sklearn.neighbors import KDTree
+    rng = np.random.default_rng(42)
+    ref = rng.standard_normal((R_s, D), dtype=np.float32)
+    qry = ref[rng.integers(0, R_s, Q_s)] + 0.5 * rng.standard_normal((Q_s, D), dtype=np.float32)
+    t0 = time.perf_counter()
+    tree = KDTree(ref)
+    build_s = time.perf_counter() - t0
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        tree.query(qry, k=k, return_distance=True, sort_results=True)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    qps_sample = Q_s / t
+    return {"value": qps_sample * R_s / R_FULL, "unit": "queries/s", "cores": 1, "kind": "reference",
+            "sample": f"sklearn KDTree(ref[{R_s}x{D}]).query(q[{Q_s}], k={k}, sort_results=True): {qps_sample:.2f} q/s measured, "
+                      f"scaled by {R_s}/{R_FULL} rows (linear in R); tree build {build_s:.1f} s not counted; single-threaded by construction",
+            "ms_per_step": t * 1e3}
+
+
+def wms_cpu_port(T=32, S=25, D=D_FULL, reps=3):
+    """Oracle port (float64 torch-CPU autograd transcription of model/losses.py:5-60) on all host threads."""
+    import torch
+    from oracle import losses as ol
+    from soft_contrastive_learning_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    emb, dist, _ = synth.wms_batch(T=T, P=12, N=12, D=D, seed=42)
+    e64, d64 = emb.astype(np.float64), torch.as_tensor(dist.astype(np.float64))
+    ol.value_and_grad(lambda e: ol.wms_loss_tuples(d64, e, 0.8, 15.0), [e64])
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ol.value_and_grad(lambda e: ol.wms_loss_tuples(d64, e, 0.8, 15.0), [e64])
+    t = (time.perf_counter() - t0) / reps
+    return {"value": T / t, "unit": "tuples/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"oracle (torch-CPU float64 autograd transcription of losses.py:5-60) fwd+bwd on {T} tuples x {S} x {D}, mean of {reps}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if args.workload == "wms":
+        cb = wms_cpu_port(reps=max(1, args.steps))
+        line = {"impl": "reference", "metric": "wms loss fwd+bwd tuples/s", "value": cb["value"], "unit": "tuples/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 32 / cb["value"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "wms tuple mode T=32 S=25 D=4096 (BASELINE config 1)"}, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "tuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    else:
+        cb = kdtree_reference(args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "top-25 queries/s vs 1Mx4096 db", "value": cb["value"], "unit": "queries/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb.pop("ms_per_step"),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "top-25 retrieval, 1Mx4096 fp32 db (BASELINE config 4), bounded CPU sample scaled to 1M rows"},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def timed(torch, fn, steps, warmup, dist_mod=None):
+    for _ in range(warmup):
+        fn()
+    if dist_mod is not None:
+        dist_mod.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist_mod is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist_mod.all_reduce(t, op=dist_mod.ReduceOp.MAX)
+        ms = float(t.item())
+        dist_mod.barrier()
+    return ms / steps
+
+
+def bench_retrieval(args, torch, dist_mod, rank, world, pk):
+    from soft_contrastive_learning_b200 import _lib, retrieval
+    L = _lib.lib()
+    R, D, Q, k = args.rows, D_FULL, args.queries, K_TOP
+    lo, hi = retrieval.shard_bounds(R, world, rank)
+    g = torch.Generator(device="cuda").manual_seed(42 + rank)
+    db = torch.empty((hi - lo, D), dtype=torch.float32, device="cuda")
+    chunk = 65536
+    for r0 in range(0, hi - lo, chunk):          # chunked: randn's temporaries stay small
+        r1 = min(hi - lo, r0 + chunk)
+        db[r0:r1] = torch.randn((r1 - r0, D), generator=g, device="cuda")
+    # queries = perturbed database rows (planted neighbours), identical on every rank
+    gq = torch.Generator(device="cuda").manual_seed(7)
+    src = torch.randint(0, R, (Q,), generator=gq, device="cuda")
+    noise = 0.5 * torch.randn((Q, D), generator=gq, device="cuda")
+    mine = (src >= lo) & (src < hi)
+    qry = torch.zeros((Q, D), dtype=torch.float32, device="cuda")
+    qry[mine] = db[(src[mine] - lo)] + noise[mine]
+    if dist_mod is not None:
+        dist_mod.all_reduce(qry)
+    del noise
+
+    # index build from HOST memory (H2D of the shard + shadow build), timed once
+    t_build_h2d = None
+    if args.time_build and world == 1:
+        host = torch.empty((hi - lo, D), dtype=torch.float32, pin_memory=True)
+        host.copy_(db)
+        torch.cuda.synchronize()
+        del db
+        torch.cuda.empty_cache()
+        t0 = time.perf_counter()
+        db = host.to("cuda", non_blocking=True)
+        tree = retrieval.KDTree(db)
+        torch.cuda.synchronize()
+        t_build_h2d = time.perf_counter() - t0
+        del host
+    else:
+        tree = retrieval.KDTree(db)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if dist_mod is not None:
+        index = retrieval.ShardedKDTree.__new__(retrieval.ShardedKDTree)
+        index.group, index.world, index.local = None, world, tree
+    else:
+        index = tree
+
+    out = {}
+
+    def step_dev():
+        out["d"], out["i"] = index.query_device(qry, k)
+
+    # correctness guard inside the bench: planted neighbour must be rank 1
+    step_dev()
+    torch.cuda.synchronize()
+    assert bool((out["i"][:, 0] == src).all()), "planted neighbours not recovered"
+    stats = tree.stats()
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    L.scl_knn_timing(1, None, None)
+    sampler.start()
+    ms = timed(torch, step_dev, args.steps, args.warmup, dist_mod)
+    clocks = sampler.stop()
+    tc_ms, tc_calls = C.c_double(), C.c_int()
+    L.scl_knn_timing(0, C.byref(tc_ms), C.byref(tc_calls))
+    tc_avg_ms = tc_ms.value / max(1, tc_calls.value)
+
+    # end to end: pinned host queries in, host results out, every step
+    q_host = torch.empty((Q, D), dtype=torch.float32, pin_memory=True)
+    q_host.copy_(qry)
+    d_host = torch.empty((Q, k), dtype=torch.float64, pin_memory=True)
+    i_host = torch.empty((Q, k), dtype=torch.int64, pin_memory=True)
+
+    def step_e2e():
+        qd = q_host.to("cuda", non_blocking=True)
+        d, i = index.query_device(qd, k)
+        d_host.copy_(d, non_blocking=True)
+        i_host.copy_(i, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e = timed(torch, step_e2e, args.steps, args.warmup, dist_mod)
+    assert np.array_equal(i_host.numpy()[:, 0], src.cpu().numpy())
+
+    flops = 2.0 * Q * (hi - lo) * D
+    achieved = flops / (tc_avg_ms * 1e-3) / 1e12 if tc_avg_ms > 0 else 0.0
+    nf = stats["n_fallback"]
+    launches_per_step = 5 + (0 if nf == 0 else (-(-nf // 6) + -(-nf // 16))) + (1 if world > 1 else 0)
+    line = {
+        "metric": "top-25 queries/s vs 1Mx4096 db", "value": Q / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f16 x f16 -> f32 (tcgen05 candidate pass) + f64 exact rescore", "data": "synthetic",
+        "config": {"workload": f"top-{k} exact retrieval, {Q} queries/step vs {R}x{D} fp32 db (BASELINE config 4), "
+                               f"db row-sharded over {world} GPU(s), NCCL all-gather + merge",
+                   "rows_per_gpu": hi - lo, "l2": "inputs larger than L2 (db shard fp32+fp16 >> 126 MB); no flush",
+                   "exactness": stats, "index_build_from_host_s": t_build_h2d},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tf_sustained"], "frac_of_burst_peak": achieved / pk["tf_burst"],
+                     "peak_source": f"{pk['source']} cuBLAS bf16 sustained (kernel runs ~{tc_avg_ms:.0f} ms back to back under the power cap)",
+                     "kernel": "knn_tc_kernel", "kernel_ms": tc_avg_ms, "kernel_share_of_step": tc_avg_ms / ms,
+                     "algorithmic_flops_per_launch": flops, "traffic": None},
+        "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4,
+                "d2h_bytes_per_step": Q * k * 16, "ms_per_step": ms_e2e},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+    return line
+
+
+def bench_wms(args, torch, pk, T=4096):
+    from soft_contrastive_learning_b200 import losses, synth
+    S, D = 25, D_FULL
+    emb_s, dist_s, _ = synth.wms_batch(T=64, P=12, N=12, D=D, seed=42)        # 64 distinct tuples, tiled to T
+    reps = T // 64
+    emb = torch.tensor(emb_s, device="cuda").repeat(reps, 1, 1).contiguous()
+    dist = torch.tensor(dist_s, device="cuda").repeat(reps, 1, 1).contiguous()
+    emb += 1e-3 * torch.randn_like(emb)
+    params = losses._ms_params(0.8, 15.0)
+
+    def step():
+        losses._wms_tuple_raw(emb, dist, params, need_grad=True)
+
+    ms = timed(torch, step, max(args.steps, 10), max(args.warmup, 3))
+    bytes_alg = T * (2 * S * D * 4 + S * S * 4)
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    # config 1 exactly (T=32): latency of one fused launch
+    e32, d32 = emb[:32].contiguous(), dist[:32].contiguous()
+    ms32 = timed(torch, lambda: losses._wms_tuple_raw(e32, d32, params, need_grad=True), 50, 10)
+    # end to end from pinned host buffers
+    eh = torch.empty(emb.shape, dtype=torch.float32, pin_memory=True)
+    eh.copy_(emb)
+    dh = torch.empty(dist.shape, dtype=torch.float32, pin_memory=True)
+    dh.copy_(dist)
+    gh = torch.empty(emb.shape, dtype=torch.float32, pin_memory=True)
+    lh = torch.empty(1, dtype=torch.float32, pin_memory=True)
+
+    def step_e2e():
+        e = eh.to("cuda", non_blocking=True)
+        d = dh.to("cuda", non_blocking=True)
+        loss, grad, _, _ = losses._wms_tuple_raw(e, d, params, need_grad=True)
+        gh.copy_(grad, non_blocking=True)
+        lh.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e = timed(torch, step_e2e, max(3, args.steps), 3)
+    cb = wms_cpu_port()
+    return {"metric": "wms loss fwd+bwd tuples/s", "value": T / (ms * 1e-3), "unit": "tuples/s", "ms_per_step": ms,
+            "dtype": "f32", "config": {"workload": f"wms tuple mode, T={T} S={S} D={D} fp32 (config 1 shape x{T // 32}; inputs 3.4 GB > L2)",
+                                       "config1_T32_us_per_launch": ms32 * 1e3, "config1_T32_tuples_per_s": 32 / (ms32 * 1e-3)},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                         "peak_source": pk["source"], "kernel": "wms_tuple_kernel<5>",
+                         "algorithmic_bytes_per_tuple": 2 * S * D * 4 + S * S * 4, "traffic": None},
+            "e2e": {"value": T / (ms_e2e * 1e-3), "unit": "tuples/s", "h2d_bytes_per_step": int(emb.numel() * 4 + dist.numel() * 4),
+                    "d2h_bytes_per_step": int(emb.numel() * 4 + 4)},
+            "cpu_baseline": cb, "gpu_launches": max(args.steps, 10)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="retrieval", choices=["retrieval", "wms"])
+    ap.add_argument("--rows", type=int, default=R_FULL)
+    ap.add_argument("--queries", type=int, default=Q_STEP)
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--time-build", action="store_true", default=True)
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist_mod = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pk = peaks()
+    if args.workload == "wms":
+        line = bench_wms(args, torch, pk)
+        line.update({"n_gpus": 1, "steps": max(args.steps, 10), "warmup": max(args.warmup, 3), "higher_is_better": True,
+                     "scaling": "weak", "vs_baseline": None, "data": "synthetic"})
+    else:
+        line = bench_retrieval(args, torch, dist_mod, rank, world, pk)
+        if rank == 0 and world == 1:
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = kdtree_reference(steps=1, warmup=0)
+                line["cpu_baseline"].pop("ms_per_step", None)
+            if not args.no_secondary:
+                torch.cuda.empty_cache()
+                line["secondary"] = [bench_wms(args, torch, pk)]
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist_mod is not None:
+        dist_mod.barrier()
+        dist_mod.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -9,7 +9,7 @@
  *  - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host; tensors are
  *    row-major, contiguous, 16-byte aligned; outputs are pre-allocated by the caller;
  *  - scalar results (losses) are written to device memory: no entry point synchronises the stream
- *    except where stated (scl_knn_query_host);
+ *    except where stated (scl_knn_query);
  *  - no global mutable state: workspace and stream are per call, so concurrent calls from several host
  *    threads are safe when they use different workspaces (train.py runs up to three threads per session);
  *  - return value 0 on success, a negative scl_status otherwise; never throws, never exits;
@@ -169,13 +169,18 @@ int scl_pca_bwd(const float* dy, const float* v, const float* var, int B, int Di
  *                          stats (optional, device i32[4]): {n_queries, n_certified, n_fallback, path}
  *   force_path: 0 auto, 1 exact scan only, 2 tensor pass (+fallback), 3 tensor pass with every query
  *               forced through the fallback as well (test hook).
- * Requires D % 4 == 0, k <= 1024 (tensor pass used when k <= 64 and the problem is large enough). */
+ * Requires D % 4 == 0, k <= 1024 (tensor pass used when k <= 32 and the problem is large enough). */
 int scl_knn_shadow_bytes(int64_t R, int D, size_t* bytes);
 int scl_knn_build(const float* db, int64_t R, int D, void* shadow, size_t shadow_bytes, scl_stream_t stream);
 int scl_knn_query_workspace_bytes(int64_t R, int D, int Q, int k, size_t* bytes);
 int scl_knn_query(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
                   int64_t idx_offset, int force_path, double* dist, int64_t* idx, int32_t* stats,
                   void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* Measurement hook (bench.py): returns the accumulated device time (CUDA events on the launching stream) and the
+ * number of launches of the tensor-pass kernel since the last reset, then, if enable >= 0, resets the counters and
+ * switches the timing on (1) or off (0).  Pass enable = -1 to read without resetting. */
+int scl_knn_timing(int enable, double* tensor_pass_ms_sum, int* tensor_pass_calls);
 
 /* Merge of G per-shard sorted top-k lists (after an all-gather): d_all [G,Q,k] f64, i_all [G,Q,k] i64
  * -> d [Q,k], i [Q,k], ordered by (distance, index).  SURVEY.md section 8(e). */

@@ -42,13 +42,18 @@ def l2_normalize(x, dim):
 # W1: wms_loss  (model/losses.py:5-60)
 # --------------------------------------------------------------------------------------
 def wms_masks(distances, d_alpha, d_beta, wfunction="exp"):
-    """Soft positive / negative weights from GPS distances (losses.py:11-19)."""
+    """Soft positive / negative weights from GPS distances (losses.py:11-19), evaluated in the dtype of
+    ``distances``.  ``wms_loss`` calls this in FLOAT32, like the reference (see there)."""
     if wfunction == "lin":      # losses.py:11-13
         mask_pos = torch.where(distances < d_beta, 1.0 - distances / d_beta, torch.zeros_like(distances))
         mask_neg = torch.where(distances < d_beta, distances / d_beta, torch.ones_like(distances))
     elif wfunction == "tanh":   # losses.py:14-16
-        mask_pos = 1.0 - torch.tanh(distances / d_beta)
-        mask_neg = torch.tanh(distances / d_beta)
+        # float32 tanh saturates to exactly 1.0 near x ~ 9 and faithful implementations disagree on where (any x > 8.66
+        # may round either way), which flips `mask_pos > 0`.  The oracle pins the correctly rounded value: tanh in
+        # float64, rounded once to the mask dtype.  (TF-1.10's Eigen tanh may saturate elsewhere: unpinnable here.)
+        t = torch.tanh((distances / d_beta).to(torch.float64)).to(distances.dtype)
+        mask_pos = 1.0 - t
+        mask_neg = t
     else:                       # 'exp' default, losses.py:17-19
         mask_pos = 1.0 / (1.0 + torch.exp(d_alpha * (distances - d_beta)))
         mask_neg = 1.0 / (1.0 + torch.exp(d_alpha * (d_beta - distances)))
@@ -91,12 +96,16 @@ def wms_loss(distances, embeddings, d_alpha, d_beta, alpha=2.0, beta=50.0, lamb=
     model/losses.py:5-60.  Call site train/train.py:852 passes d_alpha=ALPHA, d_beta=BETA only.
     """
     embeddings = _keep(embeddings)
-    distances = _t(distances, embeddings.dtype)
     embeddings = l2_normalize(embeddings, 1)                                  # :7
     batch_size = embeddings.shape[0]                                          # :9
-    mask_pos, mask_neg = wms_masks(distances, d_alpha, d_beta, wfunction)     # :11-19
-    # :22 -- the masks are cast to float32 in the reference before subtracting the identity
-    mask_pos = mask_pos - torch.eye(batch_size, dtype=mask_pos.dtype)
+    # The masks are FLOAT32 in the reference: the distances placeholder is float32 (train.py:684-686) and :22
+    # casts to float32 before subtracting the identity.  This is not a rounding detail: tf.exp overflows to inf in
+    # float32 beyond ~126 m, which makes mask_pos exactly 0 there, and the later `mask_pos > 0` tests (:50) then
+    # drop those pairs from the positive sum -- in float64 the same pairs would each contribute e^{alpha*lamb}.
+    d32 = _t(distances, torch.float32)
+    mask_pos, mask_neg = wms_masks(d32, d_alpha, d_beta, wfunction)           # :11-19, float32
+    mask_pos = mask_pos - torch.eye(batch_size, dtype=torch.float32)          # :22, float32
+    mask_pos, mask_neg = mask_pos.to(embeddings.dtype), mask_neg.to(embeddings.dtype)
     sim_mat = embeddings @ embeddings.T                                       # :25
     return _ms_core(sim_mat, mask_pos, mask_neg, alpha, beta, lamb, eps, ms_mining, sumfunction, return_masks)
 

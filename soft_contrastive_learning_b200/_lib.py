@@ -65,6 +65,7 @@ PROTOTYPES = {
     "scl_knn_query_workspace_bytes": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, _SIZE_P]),
     "scl_knn_query": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int64, C.c_int, c_ptr,
                                 c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "scl_knn_timing": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "scl_topk_merge": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
     "scl_geo_topn": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int64, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "scl_recall_curves": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr]),

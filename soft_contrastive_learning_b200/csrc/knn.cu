@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "knn_internal.cuh"
@@ -535,6 +536,10 @@ __global__ void recall_scale_kernel(double* curves, int n, int Q) {
 // ---------------------------------------------------------------------------------------------
 // orchestration
 // ---------------------------------------------------------------------------------------------
+static std::atomic<int> g_knn_timing{0};
+static std::atomic<double> g_knn_tc_ms_sum{0.0};
+static std::atomic<int> g_knn_tc_calls{0};
+
 struct QueryWs {
   __half* qh;
   float* qmul;
@@ -570,7 +575,7 @@ static int scan_qt(int D) {
 
 static bool use_tensor_pass(int64_t R, int D, int Q, int k, int force_path) {
   if (force_path == 1) return false;
-  if (k > kKeep || (D & 3) || R >= (1ll << 31) || R < 1024) return false;
+  if (k > kKeep / 2 || (D & 3) || R >= (1ll << 31) || R < 1024) return false;   // k' = 64 must leave slack above k
   if (force_path >= 2) return true;
   return double(Q) * double(R) >= double(1 << 22) && R >= 4096;
 }
@@ -719,8 +724,16 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
   a.dbg_scores = nullptr;
   const char* dbg = getenv("SCL_KNN_DEBUG_SCORES");     // test hook: address of a [Q,R] float buffer, in hex
   if (dbg) a.dbg_scores = reinterpret_cast<float*>(strtoull(dbg, nullptr, 16));
+  // optional device timing of the tensor pass alone (bench.py's roofline line): events on the launching stream
+  static thread_local cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  const bool timing = g_knn_timing.load(std::memory_order_relaxed) != 0;
+  if (timing) {
+    if (!ev0) { SCL_CUDA_TRY(cudaEventCreate(&ev0)); SCL_CUDA_TRY(cudaEventCreate(&ev1)); }
+    SCL_CUDA_TRY(cudaEventRecord(ev0, stream));
+  }
   rc = knn_tc_launch(a, w.qh, dbh, stream);
   if (rc) return rc;
+  if (timing) SCL_CUDA_TRY(cudaEventRecord(ev1, stream));
 
   int n_pow2 = 1;
   while (n_pow2 < a.NR * kKeep) n_pow2 <<= 1;
@@ -745,6 +758,12 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
   int hs[4] = {0, 0, 0, 0};
   SCL_CUDA_TRY(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
   SCL_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (timing) {
+    float ms = 0.0f;
+    SCL_CUDA_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
+    g_knn_tc_ms_sum.store(g_knn_tc_ms_sum.load() + double(ms));
+    g_knn_tc_calls.fetch_add(1);
+  }
   const int nflag = hs[2];
   if (nflag > 0) {
     rc = run_exact(db, R, D, queries, w.flag_list, nflag, k, idx_offset, dist, idx, w, stream);
@@ -754,6 +773,17 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
     const int host_stats[4] = {Q, hs[1], nflag, 2};
     SCL_CUDA_TRY(cudaMemcpyAsync(stats, host_stats, sizeof(host_stats), cudaMemcpyHostToDevice, stream));
     SCL_CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  return SCL_OK;
+}
+
+extern "C" int scl_knn_timing(int enable, double* tensor_pass_ms_sum, int* tensor_pass_calls) {
+  if (tensor_pass_ms_sum) *tensor_pass_ms_sum = g_knn_tc_ms_sum.load();
+  if (tensor_pass_calls) *tensor_pass_calls = g_knn_tc_calls.load();
+  if (enable >= 0) {
+    g_knn_timing.store(enable);
+    g_knn_tc_ms_sum.store(0.0);
+    g_knn_tc_calls.store(0);
   }
   return SCL_OK;
 }

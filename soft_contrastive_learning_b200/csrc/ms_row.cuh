@@ -15,7 +15,9 @@ __device__ __forceinline__ void wms_masks(float d, float d_alpha, float d_beta, 
     wp = d < d_beta ? 1.0f - r : 0.0f;
     wn = d < d_beta ? r : 1.0f;
   } else if (wfunction == SCL_WF_TANH) {
-    float t = tanhf(d / d_beta);
+    // correctly rounded float32 tanh (float64 evaluation, one rounding): tanhf's last-ulp freedom near saturation would
+    // flip the `mask_pos > 0` test of losses.py:50 for every pair beyond ~8.7 * d_beta
+    float t = float(tanh(double(d / d_beta)));
     wp = 1.0f - t;
     wn = t;
   } else {

@@ -42,7 +42,10 @@ def _w(x):
 
 def _make_tf():
     tf = types.ModuleType("tensorflow")
-    tf.float32 = np.float64          # run everything in float64: this is the oracle's precision
+    # dtypes are honoured: what the reference declares float32 (the GPS masks, losses.py:22) runs in float32 --
+    # tf.exp overflowing to inf there is part of the loss's behaviour -- while descriptors fed as float64 keep the
+    # similarity / log-sum-exp arithmetic in float64 (NumPy promotes mixed operands)
+    tf.float32 = np.float32
     tf.float64 = np.float64
     tf.bool = np.bool_
 
@@ -51,7 +54,7 @@ def _make_tf():
 
     tf.constant = lambda v, dtype=None: _w(np.array(v, dtype=np.float64))
     tf.cast = lambda x, dtype=None: _w(np.asarray(x).astype(dtype if dtype is not None else np.float64))
-    tf.eye = lambda n, dtype=None: _w(np.eye(int(n)))
+    tf.eye = lambda n, dtype=None: _w(np.eye(int(n), dtype=dtype if dtype is not None else np.float32))
     tf.zeros = lambda shape, dtype=None: _w(np.zeros([int(s) for s in shape]))
     tf.ones_like = lambda x: _w(np.ones_like(x))
     tf.zeros_like = lambda x: _w(np.zeros_like(x))
@@ -65,7 +68,8 @@ def _make_tf():
     tf.subtract = lambda a, b: _w(np.subtract(a, b))
     tf.exp = lambda x: _w(np.exp(x))
     tf.log = lambda x: _w(np.log(x))
-    tf.tanh = lambda x: _w(np.tanh(x))
+    # correctly rounded in the operand's dtype (see oracle/losses.py wms_masks)
+    tf.tanh = lambda x: _w(np.tanh(np.asarray(x, dtype=np.float64)).astype(np.asarray(x).dtype))
     tf.sqrt = lambda x: _w(np.sqrt(x))
     tf.maximum = lambda a, b: _w(np.maximum(a, b))
     tf.minimum = lambda a, b: _w(np.minimum(a, b))
@@ -202,6 +206,6 @@ def load_reference_losses(path="/root/reference/model/losses.py"):
     return mod, pn
 
 
-def A(x):
-    """Wrap an array so reference code can call .get_shape() on it."""
-    return _w(np.asarray(x, dtype=np.float64))
+def A(x, dtype=np.float64):
+    """Wrap an array so reference code can call .get_shape() on it (descriptors float64, GPS distances float32)."""
+    return _w(np.asarray(x, dtype=dtype))

@@ -1,0 +1,266 @@
+"""GPU parity: CUDA losses (through the C ABI) vs the float64 oracle and the committed golden vectors.
+
+Tolerance (BASELINE.json north_star): loss and gradients within 1e-5 relative of the reference math in fp32.
+Gradients are compared relative to the gradient's max magnitude (element-wise relative error is meaningless for
+entries that cancel to ~0); thresholds: loss 1e-5, gradient 2e-5, masks identical."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as ol
+from soft_contrastive_learning_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-5
+GRAD_TOL = 2e-5
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-12)
+
+
+def grad_err(g, ref):
+    return np.abs(np.asarray(g, dtype=np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30)
+
+
+WMS_VARIANTS = {
+    "exp_ms_mine": dict(wfunction="exp", sumfunction="ms", ms_mining=True),
+    "exp_ms_nomine": dict(wfunction="exp", sumfunction="ms", ms_mining=False),
+    "lin_ms_mine": dict(wfunction="lin", sumfunction="ms", ms_mining=True),
+    "tanh_ms_mine": dict(wfunction="tanh", sumfunction="ms", ms_mining=True),
+    "exp_plain_mine": dict(wfunction="exp", sumfunction="plain", ms_mining=True),
+}
+
+
+def _kept_bits(kept, S):
+    k = kept.cpu().numpy().astype(np.uint32)        # [T,S,2]
+    bits = ((k[..., None] >> np.arange(S, dtype=np.uint32)) & 1).astype(bool)      # [T,S,2,S]
+    return bits[:, :, 0, :], bits[:, :, 1, :]
+
+
+@pytest.mark.parametrize("tag", list(WMS_VARIANTS))
+def test_wms_golden_tuple_kernel(cuda_lib, golden, tag):
+    from soft_contrastive_learning_b200 import losses
+    g = golden("wms_flat_S25_D64")
+    loss, grad, kept = losses.wms_loss_value_and_grad(g["dist"], g["emb"], 0.8, 15.0, return_kept=True,
+                                                       **WMS_VARIANTS[tag])
+    assert rel(loss, float(g["loss_" + tag])) < LOSS_TOL
+    assert grad_err(grad, g["grad_" + tag]) < GRAD_TOL
+    kp, kn = _kept_bits(kept, 25)
+    assert np.array_equal(kp[0], g["keptpos_" + tag]) and np.array_equal(kn[0], g["keptneg_" + tag])
+
+
+def test_wms_golden_tuples_T4(cuda_lib, golden):
+    from soft_contrastive_learning_b200 import losses
+    g = golden("wms_tuples_T4_S25_D256")
+    loss, grad = losses.wms_loss_value_and_grad(g["dist"], g["emb"], 0.8, 15.0)
+    assert rel(loss, float(g["loss"])) < LOSS_TOL
+    assert grad_err(grad, g["grad"]) < GRAD_TOL
+
+
+def _oracle_wms(emb, dist, **kw):
+    return ol.value_and_grad(lambda e: ol.wms_loss_tuples(torch.as_tensor(dist.astype(np.float64)), e, 0.8, 15.0, **kw),
+                             [emb.astype(np.float64)])
+
+
+@pytest.mark.parametrize("T,P,N,D", [(32, 12, 12, 4096),      # BASELINE config 1
+                                     (3, 15, 16, 1024),       # S = 32 (config 3 tuple shape)
+                                     (2, 12, 12, 32768),      # the published model's 32768-d descriptors: chunked path
+                                     (5, 3, 4, 64), (2, 14, 14, 512)])
+def test_wms_tuple_vs_oracle(cuda_lib, T, P, N, D):
+    from soft_contrastive_learning_b200 import losses
+    emb, dist, _ = synth.wms_batch(T=T, P=P, N=N, D=D, seed=42)
+    loss, grad, kept = losses.wms_loss_value_and_grad(dist, emb, 0.8, 15.0, return_kept=True)
+    ref, (rg,) = _oracle_wms(emb, dist)
+    assert rel(loss, ref) < LOSS_TOL, (loss, ref)
+    assert grad_err(grad, rg) < GRAD_TOL
+    # identical mining decisions, pair by pair
+    S = 1 + P + N
+    kp, kn = _kept_bits(kept, S)
+    for t in range(T):
+        _, mp, mn = ol.wms_loss(dist[t].astype(np.float64), emb[t].astype(np.float64), 0.8, 15.0, return_masks=True)
+        assert np.array_equal(kp[t], mp.numpy()) and np.array_equal(kn[t], mn.numpy())
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "4", "8"])
+def test_wms_cluster_sizes_agree(cuda_lib, cluster, monkeypatch):
+    from soft_contrastive_learning_b200 import losses
+    monkeypatch.setenv("SCL_WMS_CLUSTER", cluster)
+    emb, dist, _ = synth.wms_batch(T=6, P=12, N=12, D=2048, seed=3)
+    loss, grad = losses.wms_loss_value_and_grad(dist, emb, 0.8, 15.0)
+    ref, (rg,) = _oracle_wms(emb, dist)
+    assert rel(loss, ref) < LOSS_TOL and grad_err(grad, rg) < GRAD_TOL
+
+
+def test_wms_autograd_wrapper_and_2d_call(cuda_lib):
+    from soft_contrastive_learning_b200 import losses
+    emb, dist, _ = synth.wms_batch(T=1, P=12, N=12, D=256, seed=9)
+    e = torch.tensor(emb[0], device="cuda", requires_grad=True)
+    d3 = torch.tensor(dist, device="cuda")               # [1,S,S], as train.py:684-686 feeds it
+    l3 = losses.wms_loss(d3, e, d_alpha=0.8, d_beta=15.0)
+    (3.0 * l3).backward()
+    ref, (rg,) = ol.value_and_grad(lambda x: ol.wms_loss(torch.as_tensor(dist[0].astype(np.float64)), x, 0.8, 15.0),
+                                   [emb[0].astype(np.float64)])
+    assert rel(float(l3), ref) < LOSS_TOL
+    assert grad_err(e.grad.cpu().numpy() / 3.0, rg) < GRAD_TOL
+    l2 = losses.wms_loss(d3[0], e.detach(), 0.8, 15.0)   # the 2-D form of losses.py:5
+    assert float(l2) == float(l3)
+
+
+def test_wms_is_deterministic(cuda_lib):
+    from soft_contrastive_learning_b200 import losses
+    emb, dist, _ = synth.wms_batch(T=16, P=12, N=12, D=1024, seed=5)
+    a = losses.wms_loss_value_and_grad(dist, emb, 0.8, 15.0)
+    b = losses.wms_loss_value_and_grad(dist, emb, 0.8, 15.0)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+def test_wms_zero_row_edge_case(cuda_lib):
+    """An all-zero descriptor hits the 1e-12 clamp of tf.nn.l2_normalize; loss and gradient stay finite and match."""
+    from soft_contrastive_learning_b200 import losses
+    emb, dist, _ = synth.wms_batch(T=2, P=4, N=4, D=64, seed=1)
+    emb[0, 3] = 0.0
+    loss, grad = losses.wms_loss_value_and_grad(dist, emb, 0.8, 15.0)
+    ref, (rg,) = _oracle_wms(emb, dist)
+    assert np.isfinite(loss) and np.isfinite(grad).all()
+    assert rel(loss, ref) < LOSS_TOL
+
+
+# ---------------- flat mode ----------------
+@pytest.mark.parametrize("tag,mining", [("mine", True), ("nomine", False)])
+def test_ms_golden_flat(cuda_lib, golden, tag, mining):
+    from soft_contrastive_learning_b200 import losses
+    g = golden("ms_T3_P4_N5_D48")
+    loss, grad = losses.ms_loss_value_and_grad(g["labels"], g["emb"], ms_mining=mining)
+    assert rel(loss, float(g["loss_" + tag])) < LOSS_TOL
+    assert grad_err(grad, g["grad_" + tag]) < GRAD_TOL
+
+
+def test_flat_wms_and_ms_batch(cuda_lib):
+    """Config 3 shape scaled to what the float64 oracle finishes in seconds: B = 8 tuples x 32 = 256, D = 1024."""
+    from soft_contrastive_learning_b200 import losses
+    T, P, N, D = 8, 15, 16, 1024
+    rng = np.random.default_rng(42)
+    xy = synth.tuple_xy(rng, T, P, N).reshape(-1, 2)
+    emb = synth.tuple_descriptors(rng, T, P, N, D).reshape(T * 32, D)
+    dist = np.sqrt(((xy[:, None] - xy[None]) ** 2).sum(-1)).astype(np.float32)
+    loss, grad, kept = losses.wms_loss_value_and_grad(dist, emb, 0.8, 15.0, return_kept=True)
+    ref, (rg,) = ol.value_and_grad(lambda e: ol.wms_loss(torch.as_tensor(dist.astype(np.float64)), e, 0.8, 15.0),
+                                   [emb.astype(np.float64)])
+    assert rel(loss, ref) < LOSS_TOL and grad_err(grad, rg) < GRAD_TOL
+    _, mp, mn = ol.wms_loss(dist.astype(np.float64), emb.astype(np.float64), 0.8, 15.0, return_masks=True)
+    k = kept.cpu().numpy().astype(bool)
+    assert (k[0] != mp.numpy()).sum() + (k[1] != mn.numpy()).sum() <= 2      # fp32 vs fp64 at a mining threshold
+    labels = losses.ms_labels(T, P, N)
+    loss, grad = losses.ms_loss_value_and_grad(labels, emb)
+    ref, (rg,) = ol.value_and_grad(lambda e: ol.ms_loss(labels, e), [emb.astype(np.float64)])
+    assert rel(loss, ref) < LOSS_TOL and grad_err(grad, rg) < GRAD_TOL
+
+
+# ---------------- triplet family ----------------
+TUPLE_CASES = ["triplet", "lazy_triplet", "quadruplet", "lazy_quadruplet", "evil_triplet", "evil_quadruplet",
+               "huber_distance_triplet", "huber_distance_lazy_triplet", "distance_triplet"]
+
+
+def _run_named(losses, tag, emb_t, sq, P, N, m1, m2, lam, dmax, fmax):
+    q, p, n, o = (emb_t[:, 0:1], emb_t[:, 1:1 + P], emb_t[:, 1 + P:1 + P + N], emb_t[:, 1 + P + N:])
+    if tag == "triplet":
+        return losses.triplet_loss(q, p, n, m1)
+    if tag == "lazy_triplet":
+        return losses.lazy_triplet_loss(q, p, n, m1)
+    if tag == "quadruplet":
+        return losses.quadruplet_loss(q, p, n, o, m1, m2)
+    if tag == "lazy_quadruplet":
+        return losses.lazy_quadruplet_loss(q, p, n, o, m1, m2)
+    if tag == "evil_triplet":
+        return losses.evil_triplet_loss(q, p, n, m1)
+    if tag == "evil_quadruplet":
+        return losses.evil_quadruplet_loss(q, p, n, o, m1, m2)
+    trip = "lazy_triplet_loss" if "lazy" in tag else "triplet_loss"
+    dl = "huber_distance_loss" if "huber" in tag else "distance_loss"
+    return losses.distance_triplet_loss(q, p, n, m1, lam, sq, dmax, fmax, trip, dl)
+
+
+@pytest.mark.parametrize("tag", TUPLE_CASES)
+def test_tuple_losses_golden(cuda_lib, golden, tag):
+    from soft_contrastive_learning_b200 import losses
+    g = golden("tuple_losses_T3_P4_N6_D40")
+    P, N = int(g["P"]), int(g["N"])
+    quad = "quadruplet" in tag
+    emb = g["emb"] if quad else g["emb"][:, :1 + P + N]
+    e = torch.tensor(emb, device="cuda", requires_grad=True)
+    loss = _run_named(losses, tag, e, g["sq_d_dists"], P, N, float(g["m1"]), float(g["m2"]), float(g["lam"]),
+                      float(g["d_max_squared"]), float(g["f_max_squared"]))
+    loss.backward()
+    assert rel(float(loss), float(g["loss_" + tag])) < LOSS_TOL
+    ref_grad = g["grad_" + tag] if quad else g["grad_" + tag][:, :1 + P + N]
+    assert grad_err(e.grad.cpu().numpy(), ref_grad) < GRAD_TOL
+
+
+@pytest.mark.parametrize("name", ["triplet_loss", "lazy_quadruplet_loss", "quadruplet_loss"])
+def test_tuple_losses_config3_shape(cuda_lib, name):
+    """T=32, S=32, D=4096 (config 3).  Descriptors scaled so hinges are partly active."""
+    from soft_contrastive_learning_b200 import losses
+    T, P, D = 32, 15, 4096
+    quad = "quadruplet" in name
+    N = 15 if quad else 16
+    rng = np.random.default_rng(7)
+    emb = (0.011 * synth.tuple_descriptors(rng, T, P, N, D, other=quad, pos_noise=1.35)).astype(np.float32)
+    loss, grad = losses.tuple_loss_value_and_grad(name, emb.reshape(T * 32, D), T, P, N, m1=0.1, m2=0.2)
+    fn = getattr(ol, name)
+
+    def f(e):
+        parts = ol.split_tuple(e, P, N, other=quad)
+        return fn(*parts, 0.1, 0.2) if quad else fn(*parts, 0.1)
+    ref, (rg,) = ol.value_and_grad(f, [emb.astype(np.float64)])
+    assert ref > 0
+    assert rel(loss, ref) < LOSS_TOL and grad_err(grad.reshape(emb.shape), rg) < GRAD_TOL
+
+
+def test_logratio_golden_and_tuples(cuda_lib, golden):
+    from soft_contrastive_learning_b200 import losses
+    g = golden("logratio_P5_N5_D32")
+    e = torch.tensor(g["emb"], device="cuda", requires_grad=True)
+    loss = losses.logratio_loss(e[:, :1], e[:, 1:6], e[:, 6:], g["sq_pos"], g["sq_neg"])
+    loss.backward()
+    assert rel(float(loss), float(g["loss"])) < LOSS_TOL
+    assert grad_err(e.grad.cpu().numpy(), g["grad"]) < GRAD_TOL
+    # tuple mode and the non-strict (all-pairs) variant against the oracle
+    rng = np.random.default_rng(4)
+    T, P, N, D = 6, 12, 12, 512
+    xy = synth.tuple_xy(rng, T, P, N)
+    emb = synth.tuple_descriptors(rng, T, P, N, D)
+    sp, sn = synth.logratio_sq_dists(xy, P, N)
+    loss, grad = losses.logratio_loss_value_and_grad(emb.reshape(T * 25, D), T, P, N, sp.astype(np.float32),
+                                                     sn.astype(np.float32))
+    ref, (rg,) = ol.value_and_grad(
+        lambda x: ol.logratio_loss_tuples(*ol.split_tuple(x, P, N), torch.as_tensor(sp.astype(np.float32).astype(np.float64)),
+                                          torch.as_tensor(sn.astype(np.float32).astype(np.float64))),
+        [emb.astype(np.float64)])
+    assert rel(loss, ref) < LOSS_TOL and grad_err(grad.reshape(emb.shape), rg) < GRAD_TOL
+
+
+def test_pairwise_sqdist(cuda_lib, golden):
+    from soft_contrastive_learning_b200 import losses
+    g = golden("pairwise_sqdist")
+    out = losses._pairwise_squared_distances(g["selfcheck_in"].astype(np.float32))
+    assert np.array_equal(out, g["selfcheck_out"].astype(np.float32))          # the reference's own self-check tensor
+    out = losses._pairwise_squared_distances(g["x"])
+    assert np.allclose(out, g["d"], rtol=1e-5, atol=1e-4)
+
+
+def test_get_loss_by_name(cuda_lib):
+    from soft_contrastive_learning_b200 import losses
+    emb, dist, xy = synth.wms_batch(T=2, P=12, N=12, D=128, seed=8)
+    out = torch.tensor(emb.reshape(50, 128), device="cuda", requires_grad=True)
+    cfg = dict(TUPLES_PER_BATCH=2)
+    l = losses.get_loss("wms")(out, torch.tensor(dist, device="cuda"), cfg)
+    l.backward()
+    ref, _ = _oracle_wms(emb, dist)
+    assert rel(float(l), ref) < LOSS_TOL and out.grad.abs().sum() > 0
+    sq = synth.anchor_sq_dists(xy, 12).astype(np.float32)
+    l2 = losses.get_loss("huber_distance_triplet")(out.detach(), sq, cfg)
+    q, p, n = ol.split_tuple(torch.as_tensor(emb.astype(np.float64)), 12, 12)
+    ref2 = float(ol.distance_triplet_loss(q, p, n, 0.1, 0.5, torch.as_tensor(sq.astype(np.float64)), 225.0, 2.0))
+    assert rel(float(l2), ref2) < LOSS_TOL

@@ -1,0 +1,60 @@
+"""GPU parity: NetVLAD head and PCA projection (forward and backward) vs the float64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import netvlad as onv
+from soft_contrastive_learning_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def relmax(a, b):
+    return np.abs(np.asarray(a, dtype=np.float64) - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 3, 4), (3, 11, 15), (2, 30, 40)])
+def test_netvlad_forward_backward(cuda_lib, B, H, W):
+    from soft_contrastive_learning_b200 import netvlad
+    x, aw, cc, *_ = synth.netvlad_problem(B=B, H=H, W=W, seed=42)
+    rng = np.random.default_rng(0)
+    dout = rng.standard_normal((B, 512 * 64)).astype(np.float32)
+    xt = torch.tensor(x, device="cuda", requires_grad=True)
+    wt = torch.tensor(aw, device="cuda", requires_grad=True)
+    ct = torch.tensor(cc, device="cuda", requires_grad=True)
+    out = netvlad.netVLAD(xt, wt.reshape(1, 1, 512, 64), ct.reshape(1, 1, 1, 512, 64))
+    (out * torch.tensor(dout, device="cuda")).sum().backward()
+    xo = torch.tensor(x.astype(np.float64), requires_grad=True)
+    wo = torch.tensor(aw.astype(np.float64), requires_grad=True)
+    co = torch.tensor(cc.astype(np.float64), requires_grad=True)
+    ro = onv.netvlad_head(xo, wo, co)
+    (ro * torch.tensor(dout.astype(np.float64))).sum().backward()
+    assert relmax(out.detach().cpu().numpy(), ro.detach().numpy()) < 1e-5
+    assert relmax(xt.grad.cpu().numpy(), xo.grad.numpy()) < 5e-5
+    assert relmax(wt.grad.cpu().numpy(), wo.grad.numpy()) < 5e-5
+    assert relmax(ct.grad.cpu().numpy(), co.grad.numpy()) < 5e-5
+    assert np.allclose((out.detach().cpu().numpy() ** 2).sum(1), 1.0, atol=1e-5)
+
+
+def test_pca_forward_backward_and_sklearn(cuda_lib):
+    from sklearn.decomposition import PCA
+    from soft_contrastive_learning_b200 import netvlad
+    x, aw, cc, V, m, var = synth.netvlad_problem(B=4, H=2, W=2, Dout=256, seed=1)
+    rng = np.random.default_rng(1)
+    feats = rng.standard_normal((4, 32768)).astype(np.float32) * 0.01
+    ft = torch.tensor(feats, device="cuda", requires_grad=True)
+    y = netvlad.pca_project(ft, torch.tensor(V, device="cuda"), torch.tensor(m, device="cuda"),
+                            torch.tensor(var, device="cuda"))
+    dy = rng.standard_normal(y.shape).astype(np.float32)
+    (y * torch.tensor(dy, device="cuda")).sum().backward()
+    fo = torch.tensor(feats.astype(np.float64), requires_grad=True)
+    yo = onv.pca_project(fo, V.astype(np.float64), m.astype(np.float64), var.astype(np.float64))
+    (yo * torch.tensor(dy.astype(np.float64))).sum().backward()
+    assert relmax(y.detach().cpu().numpy(), yo.detach().numpy()) < 1e-5
+    assert relmax(ft.grad.cpu().numpy(), fo.grad.numpy()) < 1e-5
+    # evaluation twin: sklearn PCA(whiten=True).transform (top-n.py:74-77)
+    X = (rng.standard_normal((300, 64)) @ rng.standard_normal((64, 64))).astype(np.float32)
+    pca = PCA(whiten=True, n_components=16).fit(X)
+    v2, m2, var2 = netvlad.pca_from_sklearn(pca)
+    got = netvlad.pca_project(X[:32], v2, m2, var2)
+    assert np.allclose(got, pca.transform(X[:32]), rtol=2e-4, atol=2e-4)

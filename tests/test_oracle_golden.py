@@ -21,7 +21,8 @@ def test_wms_flat_golden(golden, tag):
     g = golden("wms_flat_S25_D64")
     e, d = g["emb"].astype(np.float64), g["dist"].astype(np.float64)
     v, (gr,) = ol.value_and_grad(lambda x: ol.wms_loss(torch.as_tensor(d), x, 0.8, 15.0, **WMS_VARIANTS[tag]), [e])
-    assert abs(v - float(g["loss_" + tag])) <= 1e-12 * max(1.0, abs(v))
+    # the golden value came out of the reference source over NumPy; its float32 exp differs from torch's by an ulp
+    assert abs(v - float(g["loss_" + tag])) <= 1e-6 * max(1.0, abs(v))
     assert np.allclose(gr, g["grad_" + tag], rtol=1e-10, atol=1e-14)
     _, mp, mn = ol.wms_loss(d, e, 0.8, 15.0, return_masks=True, **WMS_VARIANTS[tag])
     assert np.array_equal(mp.numpy(), g["keptpos_" + tag]) and np.array_equal(mn.numpy(), g["keptneg_" + tag])
@@ -31,11 +32,11 @@ def test_wms_tuple_mode_is_mean_of_reference_tuples(golden):
     g = golden("wms_tuples_T4_S25_D256")
     e, d = g["emb"].astype(np.float64), g["dist"].astype(np.float64)
     v = float(ol.wms_loss_tuples(torch.as_tensor(d), torch.as_tensor(e), 0.8, 15.0))
-    assert abs(v - float(g["loss"])) < 1e-12
-    assert abs(v - g["per_tuple"].mean()) < 1e-12
+    assert abs(v - float(g["loss"])) < 1e-6
+    assert abs(v - g["per_tuple"].mean()) < 1e-6
     # T=1 tuple mode == the flat 2-D call
     v1 = float(ol.wms_loss_tuples(torch.as_tensor(d[:1]), torch.as_tensor(e[:1]), 0.8, 15.0))
-    assert abs(v1 - g["per_tuple"][0]) < 1e-12
+    assert abs(v1 - g["per_tuple"][0]) < 1e-6
 
 
 @pytest.mark.parametrize("tag,mining", [("mine", True), ("nomine", False)])
@@ -170,3 +171,14 @@ def test_recall_oracle():
     assert np.allclose(Y[2], [0, 100, 100])
     X1, Y1 = orr.recall_curve_top1(d, t=10.0, num=3)
     assert np.allclose(Y1, Y[0])
+
+
+def test_wms_masks_are_float32_like_the_reference(golden):
+    """mask_pos > 0 (losses.py:50) hinges on float32 overflow of tf.exp: pairs beyond ~126 m get mask_pos == 0 exactly."""
+    d = torch.tensor([[0.0, 10.0, 100.0, 130.0, 500.0]])
+    mp32, _ = ol.wms_masks(d.to(torch.float32), 0.8, 15.0)
+    mp64, _ = ol.wms_masks(d.to(torch.float64), 0.8, 15.0)
+    assert (mp32[0, :3] > 0).all() and (mp32[0, 3:] == 0).all()
+    assert (mp64 > 0).all()            # which is why a float64 transcription of the masks would be a different loss
+    g = golden("wms_flat_S25_D64")
+    assert int(g["keptpos_exp_ms_nomine"].sum()) < 25 * 24
