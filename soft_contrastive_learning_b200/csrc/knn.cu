@@ -164,7 +164,8 @@ __device__ __forceinline__ void bitonic_sort_smem(K* keys, int n_pow2) {
 
 __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __restrict__ cand_s,
                                                              const uint32_t* __restrict__ cand_i,
-                                                             const int* __restrict__ cand_cnt, int NR, int n_pow2,
+                                                             const int* __restrict__ cand_cnt,
+                                                             const unsigned int* __restrict__ q_thr, int NR, int n_pow2,
                                                              uint32_t* __restrict__ sel_idx, float* __restrict__ sel_T,
                                                              int* __restrict__ sel_n) {
   extern __shared__ unsigned long long mkeys[];
@@ -186,7 +187,13 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   }
   if (threadIdx.x == 0) {
     sel_n[q] = total;
-    sel_T[q] = total >= kKeep ? key64_score(mkeys[kKeep - 1]) : INFINITY;
+    // Everything that is NOT among the kKeep selected entries scored >= T:
+    //   entries left in the lists score >= the kKeep-th smallest of the union;
+    //   anything a range rejected or pruned scored >= the threshold in force, which was >= the final published one.
+    const unsigned int pub = q_thr[q];
+    const float t_pub = pub == 0xffffffffu ? INFINITY : key64_score((unsigned long long)pub << 32);
+    const float t_sel = total >= kKeep ? key64_score(mkeys[kKeep - 1]) : INFINITY;
+    sel_T[q] = fminf(t_sel, t_pub);
   }
 }
 
@@ -276,8 +283,8 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __res
   for (int o = 16; o > 0; o >>= 1) kth = fmin(kth, __shfl_xor_sync(0xffffffffu, kth, o));
   if (lane == 0) {
     bool ok;
-    if ((long long)sel_n[q] >= h->R) {
-      ok = true;                                   // every row of the shard was rescored
+    if (sel_n[q] <= kKeep && (long long)sel_n[q] >= h->R) {
+      ok = true;                                   // every row of the shard is a candidate and was rescored
     } else {
       const double eps = knn_eps(sqrt(qn2[q]), qexp[q], h);
       ok = kth < double(sel_T[q]) + qn2[q] - eps;
@@ -548,6 +555,7 @@ struct QueryWs {
   float* cand_s;
   uint32_t* cand_i;
   int* cand_cnt;
+  unsigned int* q_thr;
   uint32_t* sel_idx;
   float* sel_T;
   int* sel_n;
@@ -583,8 +591,8 @@ static bool use_tensor_pass(int64_t R, int D, int Q, int k, int force_path) {
 static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* base, size_t bytes) {
   Carver c(base, bytes);
   const int Dp = pad64(D);
-  int mb, nt, NR, tpr;
-  knn_tc_tiling(Q, R, &mb, &nt, &NR, &tpr);
+  int mb, nt, NR, tpr, gm;
+  knn_tc_tiling(Q, R, &mb, &nt, &NR, &tpr, &gm);
   QueryWs tmp;
   QueryWs* o = w ? w : &tmp;
   o->stats = c.take<int>(8);
@@ -595,6 +603,7 @@ static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* 
   o->cand_s = c.take<float>(size_t(Q) * NR * kCandCap);
   o->cand_i = c.take<uint32_t>(size_t(Q) * NR * kCandCap);
   o->cand_cnt = c.take<int>(size_t(Q) * NR);
+  o->q_thr = c.take<unsigned int>(Q);
   o->sel_idx = c.take<uint32_t>(size_t(Q) * kKeep);
   o->sel_T = c.take<float>(Q);
   o->sel_n = c.take<int>(Q);
@@ -719,8 +728,9 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
 
   TcArgs a = {};
   a.rn = rn; a.qmul = w.qmul; a.Q = Q; a.R = int(R); a.Dp = Dp;
-  knn_tc_tiling(Q, R, &a.num_m_blocks, &a.num_n_tiles, &a.NR, &a.tiles_per_range);
-  a.cand_s = w.cand_s; a.cand_i = w.cand_i; a.cand_cnt = w.cand_cnt;
+  knn_tc_tiling(Q, R, &a.num_m_blocks, &a.num_n_tiles, &a.NR, &a.tiles_per_range, &a.group_m);
+  a.cand_s = w.cand_s; a.cand_i = w.cand_i; a.cand_cnt = w.cand_cnt; a.q_thr = w.q_thr;
+  SCL_CUDA_TRY(cudaMemsetAsync(w.q_thr, 0xff, size_t(Q) * sizeof(unsigned int), stream));
   a.dbg_scores = nullptr;
   const char* dbg = getenv("SCL_KNN_DEBUG_SCORES");     // test hook: address of a [Q,R] float buffer, in hex
   if (dbg) a.dbg_scores = reinterpret_cast<float*>(strtoull(dbg, nullptr, 16));
@@ -743,7 +753,7 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
     SCL_CUDA_TRY(cudaFuncSetAttribute(knn_cand_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(merge_smem)));
     merge_cfg = merge_smem;
   }
-  knn_cand_merge_kernel<<<Q, 256, merge_smem, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, a.NR, n_pow2, w.sel_idx, w.sel_T,
+  knn_cand_merge_kernel<<<Q, 256, merge_smem, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, w.q_thr, a.NR, n_pow2, w.sel_idx, w.sel_T,
                                                         w.sel_n);
   SCL_LAUNCH_CHECK();
   const long long pairs = (long long)Q * kKeep;

@@ -26,13 +26,16 @@ struct TcArgs {
   int R;
   int Dp;
   int num_m_blocks, num_n_tiles, NR, tiles_per_range;
+  int group_m;           // query-axis work units processed concurrently (bounds the L2 working set of A)
   float* cand_s;         // [Q, NR, kCandCap]
   uint32_t* cand_i;      // [Q, NR, kCandCap]
   int* cand_cnt;         // [Q, NR]
+  unsigned int* q_thr;   // [Q] best (smallest) pruning threshold any range has published for the query, as an
+                         //     order-preserving uint (0xffffffff = none yet); shared by all ranges of the query
   float* dbg_scores;     // optional [Q, R]: raw fp16-pass scores (tests)
 };
 
 int knn_tc_launch(const TcArgs& a, const void* queries_fp16, const void* db_fp16, cudaStream_t stream);
-void knn_tc_tiling(int Q, int64_t R, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range);
+void knn_tc_tiling(int Q, int64_t R, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range, int* group_m);
 
 }  // namespace scl

@@ -21,32 +21,59 @@ namespace scl {
 
 using namespace tc;
 
-constexpr int kBM = 128, kBN = 256, kBK = 64;          // CTA tile; kBK fp16 = 128 bytes = one swizzle row
-constexpr int kStages = 4;
+constexpr int kBM = 128, kBN = 256, kBK = 64;          // per-CTA accumulator tile; kBK fp16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kTcThreads = 192;
-constexpr uint32_t kABytes = kBM * kBK * 2, kBBytes = kBN * kBK * 2;
-constexpr uint32_t kStageBytes = kABytes + kBBytes;     // 48 KB
+constexpr int kMaxStages = 6;
+constexpr uint32_t kABytes = kBM * kBK * 2;             // 16 KB: this CTA's 128 query rows
 constexpr uint32_t kTmemCols = 512;                     // 2 accumulators x 256 fp32 columns
 
+// kPair = false: one CTA per 128x256 tile (cta_group::1), the CTA loads the whole 256-row B tile.
+// kPair = true : a CTA pair computes a 256x256 tile (cta_group::2, UMMA M = 256); each CTA loads its own 128 query
+//                rows and HALF of the B tile, the tensor cores read the other half from the peer's shared memory.
+//                One third less L2->SM traffic per flop and two more pipeline stages.
+// kNSub = 2   : the CTA keeps TWO 256-column accumulators (all 512 TMEM columns) alive for one K sweep, so each
+//                query chunk fetched from L2 is used against 512 database rows instead of 256: another quarter less
+//                L2->SM traffic per flop.  The accumulators are then single-buffered; with K = 4096 a tile computes for
+//                ~60 us and drains in ~2 us, and TMA keeps prefetching the next tile's stages meanwhile.
+template <bool kPair, int kNSub>
+struct TcCfg {
+  static constexpr uint32_t kBRows = kPair ? kBN / 2 : kBN;            // rows per B sub-tile held by this CTA
+  static constexpr uint32_t kBBytes = kBRows * kBK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kNSub * kBBytes;   // 32 / 48 KB
+  static constexpr int kStages = (kStageBytes == 32768) ? 6 : 4;
+  static constexpr uint32_t kTxBytes = kPair ? 2 * kStageBytes : kStageBytes;
+  static constexpr int kTileN = kBN * kNSub;                           // database rows per CTA tile
+  static constexpr int kBufs = kNSub == 1 ? 2 : 1;                     // TMEM accumulator buffers
+};
+
 struct TcSmemTail {
-  float rn[2][kBN];
+  float rn[2][2 * kBN];
   unsigned long long prune_keys[4][kCandCap];
   float prune_thr[4];
-  uint64_t full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
+  uint64_t full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
-constexpr size_t kTcSmemBytes = 1024 + size_t(kStages) * kStageBytes + sizeof(TcSmemTail);
+template <bool kPair, int kNSub>
+constexpr size_t tc_smem_bytes() {
+  return 1024 + size_t(TcCfg<kPair, kNSub>::kStages) * TcCfg<kPair, kNSub>::kStageBytes + sizeof(TcSmemTail);
+}
 
-__device__ __forceinline__ unsigned long long cand_key(float s, uint32_t idx) {
+__device__ __forceinline__ uint32_t f2ord(float s) {      // order-preserving map float -> uint
   uint32_t u = __float_as_uint(s);
-  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);       // order-preserving map float -> uint
-  return (static_cast<unsigned long long>(u) << 32) | idx;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ unsigned long long cand_key(float s, uint32_t idx) {
+  return (static_cast<unsigned long long>(f2ord(s)) << 32) | idx;
 }
 
 // Warp-cooperative prune of the candidate list of lane `L`'s row to its kKeep best entries (sorted ascending).
 __device__ __forceinline__ void prune_row(int L, int lane, float* __restrict__ cs, uint32_t* __restrict__ ci,
-                                          size_t base, int& cnt, float& thr, unsigned long long* keys, float* thr_slot) {
+                                          size_t base, int& cnt, float& thr, unsigned long long* keys, float* thr_slot,
+                                          unsigned int* q_thr_of_lane) {
   const int n = __shfl_sync(0xffffffffu, cnt, L);
   const unsigned long long b64 = static_cast<unsigned long long>(base);
   const size_t bL = static_cast<size_t>(__shfl_sync(0xffffffffu, b64, L));
@@ -81,16 +108,41 @@ __device__ __forceinline__ void prune_row(int L, int lane, float* __restrict__ c
   if (lane == L) {
     cnt = kKeep;
     thr = *thr_slot;
+    // publish: every range of this query may now reject anything that scores >= the 64th best seen here
+    atomicMin(q_thr_of_lane, f2ord(thr));
   }
   __syncwarp();
 }
 
+// Work item -> (database range, query unit).  Items are ordered group-major: a group of `group_m` query units runs
+// against every range before the next group starts, so the CTAs that are resident at the same time share a small set
+// of query blocks (kept hot in L2) and each database range is streamed from HBM once per group, by CTAs in lockstep.
+__device__ __forceinline__ void decode_item(int item, int m_units, int NR, int group_m, int& range, int& mu) {
+  const int per_group = group_m * NR;
+  const int groups = (m_units + group_m - 1) / group_m;
+  int g = item / per_group;
+  if (g > groups - 1) g = groups - 1;
+  const int rem = item - g * per_group;
+  const int gsz = min(group_m, m_units - g * group_m);
+  range = rem / gsz;
+  mu = g * group_m + (rem - range * gsz);
+}
+
+template <bool kPair, int kNSub>
 __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB, TcArgs a) {
+  using Cfg = TcCfg<kPair, kNSub>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr uint32_t kStageBytes = Cfg::kStageBytes;
+  constexpr int kTileN = Cfg::kTileN;
+  constexpr uint32_t kBufs = Cfg::kBufs;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(smem + size_t(kStages) * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;       // 0 = leader of the pair
+  const int worker = kPair ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int num_workers = kPair ? int(gridDim.x >> 1) : int(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -101,68 +153,94 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tail->tmem_full[b], 1);
-      mbar_init(&tail->tmem_empty[b], 4);     // one arrival per epilogue warp
+      mbar_init(&tail->tmem_empty[b], kPair ? 8 : 4);     // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tail->tmem_base, kTmemCols);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_2sm(&tail->tmem_base, kTmemCols); else tmem_alloc(&tail->tmem_base, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();       // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
   const int num_k = a.Dp / kBK;
-  const int num_items = a.num_m_blocks * a.NR;
+  const int m_units = kPair ? (a.num_m_blocks + 1) / 2 : a.num_m_blocks;   // query blocks (pairs of blocks) per range
+  const int num_items = m_units * a.NR;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int range = item / a.num_m_blocks, mb = item - range * a.num_m_blocks;
+      for (int item = worker; item < num_items; item += num_workers) {
+        int range, mu;
+        decode_item(item, m_units, a.NR, a.group_m, range, mu);
+        const int mb = kPair ? 2 * mu + int(crank) : mu;
         const int t0 = range * a.tiles_per_range, t1 = min(a.num_n_tiles, t0 + a.tiles_per_range);
         for (int t = t0; t < t1; ++t) {
           for (int kc = 0; kc < num_k; ++kc) {
             mbar_wait(&tail->empty[stage], phase ^ 1);
             uint8_t* sa = smem + size_t(stage) * kStageBytes;
-            mbar_arrive_expect_tx(&tail->full[stage], kStageBytes);
-            tma_load_2d(sa, &tmA, &tail->full[stage], kc * kBK, mb * kBM);
-            tma_load_2d(sa + kABytes, &tmB, &tail->full[stage], kc * kBK, t * kBN);
+            if (kPair) {
+              // both CTAs report their bytes to the LEADER's barrier; only the leader arms it (with both shares)
+              const uint32_t lead_bar = mapa_u32(smem_u32(&tail->full[stage]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&tail->full[stage], Cfg::kTxBytes);
+              tma_load_2d_2sm(sa, &tmA, lead_bar, kc * kBK, mb * kBM);
+#pragma unroll
+              for (int sub = 0; sub < kNSub; ++sub)
+                tma_load_2d_2sm(sa + kABytes + sub * Cfg::kBBytes, &tmB, lead_bar, kc * kBK,
+                                t * kTileN + sub * kBN + int(crank) * int(Cfg::kBRows));
+            } else {
+              mbar_arrive_expect_tx(&tail->full[stage], Cfg::kTxBytes);
+              tma_load_2d(sa, &tmA, &tail->full[stage], kc * kBK, mb * kBM);
+#pragma unroll
+              for (int sub = 0; sub < kNSub; ++sub)
+                tma_load_2d(sa + kABytes + sub * Cfg::kBBytes, &tmB, &tail->full[stage], kc * kBK, t * kTileN + sub * kBN);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kFmtF16, kBM, kBN);
+    // ===================== MMA issuer (leader CTA of a pair only) =====================
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc(kFmtF16, kPair ? 2 * kBM : kBM, kBN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_count = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int range = item / a.num_m_blocks;
+      for (int item = worker; item < num_items; item += num_workers) {
+        int range, mu;
+        decode_item(item, m_units, a.NR, a.group_m, range, mu);
         const int t0 = range * a.tiles_per_range, t1 = min(a.num_n_tiles, t0 + a.tiles_per_range);
         for (int t = t0; t < t1; ++t, ++tile_count) {
-          const uint32_t buf = tile_count & 1, use = tile_count >> 1;
-          mbar_wait(&tail->tmem_empty[buf], (use & 1) ^ 1);       // epilogue drained this accumulator
+          const uint32_t buf = tile_count % kBufs, use = tile_count / kBufs;
+          mbar_wait(&tail->tmem_empty[buf], (use & 1) ^ 1);       // epilogue(s) drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kBN;
           for (int kc = 0; kc < num_k; ++kc) {
             mbar_wait(&tail->full[stage], phase);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + size_t(stage) * kStageBytes);
-            const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + kABytes);
+            const uint64_t da = smem_desc_sw128(sa);
 #pragma unroll
-            for (int k = 0; k < kBK / kUmmaK; ++k) {
-              // advance 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-              mma_f16_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            for (int sub = 0; sub < kNSub; ++sub) {
+              const uint64_t db = smem_desc_sw128(sa + kABytes + sub * Cfg::kBBytes);
+#pragma unroll
+              for (int k = 0; k < kBK / kUmmaK; ++k) {
+                // advance 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                if (kPair) mma_f16_ss_2sm(d_tmem + sub * kBN, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+                else mma_f16_ss(d_tmem + sub * kBN, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+              }
             }
-            mma_commit(&tail->empty[stage]);                      // frees the smem slot when these MMAs retire
+            // frees the smem slot (in both CTAs) when these MMAs retire
+            if (kPair) mma_commit_2sm(&tail->empty[stage], 0b11); else mma_commit(&tail->empty[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          mma_commit(&tail->tmem_full[buf]);                      // accumulator complete
+          if (kPair) mma_commit_2sm(&tail->tmem_full[buf], 0b11); else mma_commit(&tail->tmem_full[buf]);
         }
       }
     }
@@ -174,47 +252,71 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
     unsigned long long* keys = tail->prune_keys[ew];
     float* thr_slot = &tail->prune_thr[ew];
     uint32_t tile_count = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int range = item / a.num_m_blocks, mb = item - range * a.num_m_blocks;
+    for (int item = worker; item < num_items; item += num_workers) {
+      int range, mu;
+      decode_item(item, m_units, a.NR, a.group_m, range, mu);
+      const int mb = kPair ? 2 * mu + int(crank) : mu;
       const int t0 = range * a.tiles_per_range, t1 = min(a.num_n_tiles, t0 + a.tiles_per_range);
       const int q = mb * kBM + lq * 32 + lane;
       const bool valid = q < a.Q;
       const float qmul = valid ? a.qmul[q] : 0.0f;
       const size_t base = (size_t(valid ? q : 0) * a.NR + range) * kCandCap;
+      unsigned int* my_thr = a.q_thr + (valid ? q : 0);
       float thr = INFINITY;
       int cnt = 0;
       for (int t = t0; t < t1; ++t, ++tile_count) {
-        const uint32_t buf = tile_count & 1, use = tile_count >> 1;
-        const int n0 = t * kBN;
-        // stage the |r|^2 of this tile's 256 rows (rows beyond the shard score +inf)
-        {
-          const int r0 = n0 + et, r1 = n0 + 128 + et;
-          tail->rn[buf][et] = r0 < a.R ? __ldg(a.rn + r0) : INFINITY;
-          tail->rn[buf][128 + et] = r1 < a.R ? __ldg(a.rn + r1) : INFINITY;
+        const uint32_t buf = tile_count % kBufs, use = tile_count / kBufs;
+        const uint32_t rbuf = tile_count & 1;      // the |r|^2 staging is always double-buffered
+        const int n0 = t * kTileN;
+        // stage the |r|^2 of this tile's rows (rows beyond the shard score +inf)
+#pragma unroll
+        for (int u = 0; u < kTileN / 128; ++u) {
+          const int r = n0 + u * 128 + et;
+          tail->rn[rbuf][u * 128 + et] = r < a.R ? __ldg(a.rn + r) : INFINITY;
+        }
+        // thresholds published by other ranges of the same query (other CTAs) tighten this row's filter too
+        if (valid) {
+          const unsigned int pub = __ldcg(my_thr);
+          if (pub != 0xffffffffu) thr = fminf(thr, ord2f(pub));
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(&tail->tmem_full[buf], use & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16) + buf * kBN;
 #pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
+        for (int c = 0; c < kTileN / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          const float* rn = &tail->rn[buf][c * 32];
+          // scores of this row against 32 database rows; the common case (nothing beats the threshold) is branch-free
+          float sc[32];
+          {
+            const float4* rn4 = reinterpret_cast<const float4*>(&tail->rn[rbuf][c * 32]);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 r = rn4[j4];
+              sc[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), qmul, r.x);
+              sc[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), qmul, r.y);
+              sc[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), qmul, r.z);
+              sc[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), qmul, r.w);
+            }
+          }
           if (a.dbg_scores != nullptr && valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = n0 + c * 32 + j;
-              if (n < a.R) a.dbg_scores[size_t(q) * a.R + n] = fmaf(__uint_as_float(v[j]), qmul, rn[j]);
+              if (n < a.R) a.dbg_scores[size_t(q) * a.R + n] = sc[j];
             }
           }
-          if (valid) {
+          uint32_t hit = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) hit |= (sc[j] < thr) ? (1u << j) : 0u;
+          if (!valid) hit = 0;
+          if (hit != 0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float s = fmaf(__uint_as_float(v[j]), qmul, rn[j]);
-              if (s < thr) {
-                a.cand_s[base + cnt] = s;
+              if ((hit >> j) & 1u) {
+                a.cand_s[base + cnt] = sc[j];
                 a.cand_i[base + cnt] = uint32_t(n0 + c * 32 + j);
                 ++cnt;
               }
@@ -224,19 +326,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
           unsigned need = __ballot_sync(0xffffffffu, cnt > kCandCap - 32);
           while (need) {
             const int L = __ffs(need) - 1;
-            prune_row(L, lane, a.cand_s, a.cand_i, base, cnt, thr, keys, thr_slot);
+            prune_row(L, lane, a.cand_s, a.cand_i, base, cnt, thr, keys, thr_slot, my_thr);
             need &= need - 1;
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->tmem_empty[buf]);
+        if (lane == 0) {
+          // the accumulator of BOTH CTAs must be drained before the leader's MMA warp may overwrite it
+          if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tmem_empty[buf]), 0));
+          else mbar_arrive(&tail->tmem_empty[buf]);
+        }
       }
       // end of the item: bring every list down to <= k' entries and publish its length
       unsigned need = __ballot_sync(0xffffffffu, cnt > kKeep);
       while (need) {
         const int L = __ffs(need) - 1;
-        prune_row(L, lane, a.cand_s, a.cand_i, base, cnt, thr, keys, thr_slot);
+        prune_row(L, lane, a.cand_s, a.cand_i, base, cnt, thr, keys, thr_slot, my_thr);
         need &= need - 1;
       }
       if (valid) a.cand_cnt[size_t(q) * a.NR + range] = cnt;
@@ -245,9 +351,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();       // the leader's MMAs read the peer's shared memory: nobody leaves early
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -285,40 +392,75 @@ int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, size_t elem_bytes,
   return SCL_OK;
 }
 
+static int tc_variant() {
+  // 1 = single-CTA 128x256 tiles, 2 = CTA pairs 256x256, 3 = CTA pairs 256x512 (default)
+  const char* env = getenv("SCL_KNN_TC_VARIANT");
+  if (env && atoi(env) >= 1 && atoi(env) <= 3) return atoi(env);
+  return 3;
+}
+static int tc_tile_n(int variant) { return variant == 3 ? 2 * kBN : kBN; }
+
+template <bool kPair, int kNSub>
+static int tc_launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
+  auto kern = knn_tc_kernel<kPair, kNSub>;
+  static bool configured = false;
+  if (!configured) {
+    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tc_smem_bytes<kPair, kNSub>())));
+    configured = true;
+  }
+  const int sms = num_sms();
+  const int m_units = kPair ? (a.num_m_blocks + 1) / 2 : a.num_m_blocks;
+  const int items = m_units * a.NR;
+  const int workers_max = kPair ? sms / 2 : sms;
+  const int workers = items < workers_max ? items : workers_max;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(kPair ? 2 * workers : workers));
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = tc_smem_bytes<kPair, kNSub>();
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SCL_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a));
+  return SCL_OK;
+}
+
 int knn_tc_launch(const TcArgs& a, const void* qh, const void* dbh, cudaStream_t stream) {
+  const int variant = tc_variant();
   CUtensorMap tmA, tmB;
   int rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, qh, uint64_t(a.Dp), uint64_t(a.Q),
                         uint64_t(a.Dp) * 2, kBK, kBM);
   if (rc) return rc;
   rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, dbh, uint64_t(a.Dp), uint64_t(a.R), uint64_t(a.Dp) * 2,
-                    kBK, kBN);
+                    kBK, variant == 1 ? kBN : kBN / 2);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(knn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)));
-    configured = true;
-  }
-  const int items = a.num_m_blocks * a.NR;
-  const int grid = items < num_sms() ? items : num_sms();
-  knn_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(tmA, tmB, a);
-  SCL_LAUNCH_CHECK();
-  return SCL_OK;
+  if (variant == 1) return tc_launch_variant<false, 1>(tmA, tmB, a, stream);
+  if (variant == 2) return tc_launch_variant<true, 1>(tmA, tmB, a, stream);
+  return tc_launch_variant<true, 2>(tmA, tmB, a, stream);
 }
 
-void knn_tc_tiling(int Q, int64_t R, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range) {
+void knn_tc_tiling(int Q, int64_t R, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range, int* group_m) {
   const int mb = (Q + kBM - 1) / kBM;
-  const int nt = int((R + kBN - 1) / kBN);
-  const int sms = num_sms();
+  const int variant = tc_variant();
+  const int tile_n = tc_tile_n(variant);
+  const int nt = int((R + tile_n - 1) / tile_n);
+  const bool pair = variant >= 2;
+  const int sms = pair ? num_sms() / 2 : num_sms();      // workers: CTA pairs or single CTAs
+  const int mu = pair ? (mb + 1) / 2 : mb;               // work units along the query axis
   // choose the number of database ranges so that (query blocks x ranges) fills whole waves of SMs
   int best = 1;
   double best_eff = -1.0;
   const int max_nr = nt < 64 ? nt : 64;
   for (int nr = 1; nr <= max_nr; ++nr) {
-    const long long items = 1ll * mb * nr;
+    const long long items = 1ll * mu * nr;
     const long long waves = (items + sms - 1) / sms;
     const int tpr = (nt + nr - 1) / nr;
     // time ~ waves * tiles_per_range; efficiency relative to perfect balance
-    const double eff = double(1ll * mb * nt) / (double(waves) * sms * tpr);
+    const double eff = double(1ll * mu * nt) / (double(waves) * sms * tpr);
     if (eff > best_eff + 0.005) { best_eff = eff; best = nr; }
   }
   const char* env = getenv("SCL_KNN_RANGES");
@@ -327,6 +469,13 @@ void knn_tc_tiling(int Q, int64_t R, int* num_m_blocks, int* num_n_tiles, int* N
   *num_n_tiles = nt;
   *NR = best;
   *tiles_per_range = (nt + best - 1) / best;
+  // 16 query blocks (16 MB of fp16 at D = 4096) per group: small enough to stay L2-resident next to the database
+  // streams, large enough that each range is re-streamed from HBM only ceil(mb / 16) times
+  int gm = pair ? 8 : 16;
+  const char* genv = getenv("SCL_KNN_GROUP_M");
+  if (genv && atoi(genv) >= 1) gm = atoi(genv);
+  if (gm > mu) gm = mu;
+  *group_m = gm;
 }
 
 }  // namespace scl

@@ -53,7 +53,14 @@ def test_ties_are_ordered_by_index(cuda_lib):
         assert (i[:, :3] == np.arange(7)[:, None] + np.array([0, 50, 100])[None]).all()
 
 
-def test_tensor_pass_raw_scores_match_fp16_gemm(cuda_lib):
+@pytest.fixture(params=["1", "2", "3"], ids=["cta_group1", "cta_pair", "cta_pair_wide"])
+def tc_variant(request, monkeypatch):
+    """Both tensor-pass kernels: single-CTA 128x256 tiles and cta_group::2 CTA pairs (256x256)."""
+    monkeypatch.setenv("SCL_KNN_TC_VARIANT", request.param)
+    return request.param
+
+
+def test_tensor_pass_raw_scores_match_fp16_gemm(cuda_lib, tc_variant):
     """The tcgen05 GEMM itself: scores |r|^2 - 2 q.r from the fp16 pass vs the same fp16-rounded operands in float64."""
     from soft_contrastive_learning_b200 import retrieval
     R, Q, D = 4096 + 300, 150, 192
@@ -69,9 +76,6 @@ def test_tensor_pass_raw_scores_match_fp16_gemm(cuda_lib):
     got = dbg.cpu().numpy().astype(np.float64)
     assert not np.isnan(got).any(), "some tiles were never written"
 
-    def fp16_scaled(x):
-        e = 13 - np.floor(np.log2(np.abs(x).max(axis=-1 if x.ndim == 1 else None, keepdims=False)))
-        return e
     e_db = 13 - int(np.floor(np.log2(np.abs(db).max())))
     dbh = (db * 2.0 ** e_db).astype(np.float16).astype(np.float64) * 2.0 ** -e_db
     e_q = 13 - np.floor(np.log2(np.abs(qry).max(axis=1)))
@@ -84,7 +88,7 @@ def test_tensor_pass_raw_scores_match_fp16_gemm(cuda_lib):
 
 @pytest.mark.parametrize("R,Q,D,k", [(20000, 300, 256, 25), (9000, 129, 4096, 25), (50000, 64, 128, 5),
                                      (4097, 257, 64, 32)])
-def test_tensor_pass_is_exact(cuda_lib, R, Q, D, k):
+def test_tensor_pass_is_exact(cuda_lib, tc_variant, R, Q, D, k):
     from soft_contrastive_learning_b200 import retrieval
     db, qry, *_ = synth.retrieval_problem(R=R, Q=Q, D=D, seed=5)
     tree = retrieval.KDTree(db)
