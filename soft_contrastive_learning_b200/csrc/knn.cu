@@ -162,38 +162,76 @@ __device__ __forceinline__ void bitonic_sort_smem(K* keys, int n_pow2) {
   __syncthreads();
 }
 
+// rigorous bound on |fp16-pass score - exact score| for query q against ANY row of the shard (see DESIGN.md)
+__device__ double knn_eps(double qnorm, int eq, const ShadowHeader* h) {
+  const double u = ldexp(1.0, -11), a = ldexp(1.0, -25);
+  const double rmax = sqrt(__longlong_as_double((long long)h->rmax2_bits));
+  const double Qn = ldexp(qnorm, eq), Rn = ldexp(rmax, h->scale_exp);
+  const double sD = sqrt(double(h->Dp));
+  const double Qt = Qn * (1.0 + u) + a * sD, Rt = Rn * (1.0 + u) + a * sD;        // norms of the rounded vectors
+  double e = u * (2.0 + u) * Qn * Rn + a * (1.0 + u) * sD * (Qn + Rn) + double(h->Dp) * a * a;   // input rounding
+  e += (double(h->Dp) / 16.0 + 1.0) * ldexp(1.0, -21) * Qt * Rt;                // tensor-core fp32 accumulation
+  const double e_dot = ldexp(e, -(eq + h->scale_exp));
+  const double smax = rmax * rmax + 2.0 * qnorm * rmax + 2.0 * e_dot;
+  return 2.0 * e_dot + ldexp(1.0, -23) * (rmax * rmax + smax);                    // + norm and fma rounding
+}
+
 __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __restrict__ cand_s,
                                                              const uint32_t* __restrict__ cand_i,
                                                              const int* __restrict__ cand_cnt,
-                                                             const unsigned int* __restrict__ q_thr, int NR, int n_pow2,
+                                                             const unsigned int* __restrict__ q_thr, int NR, int k,
+                                                             const double* __restrict__ qn2, const int* __restrict__ qexp,
+                                                             const ShadowHeader* __restrict__ h,
                                                              uint32_t* __restrict__ sel_idx, float* __restrict__ sel_T,
                                                              int* __restrict__ sel_n) {
   extern __shared__ unsigned long long mkeys[];
+  __shared__ int s_off[65];
+  __shared__ int s_need;
   const int q = blockIdx.x;
-  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) mkeys[i] = ~0ull;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int r = 0; r < NR; ++r) { s_off[r] = acc; acc += cand_cnt[size_t(q) * NR + r]; }
+    s_off[NR] = acc;
+    s_need = 0;
+  }
   __syncthreads();
-  // slot layout: range r occupies [r*kKeep, (r+1)*kKeep)
-  int total = 0;
+  // the lists are short once the shared threshold has tightened: sort only what is there (compact, padded to 2^n)
+  const int total = s_off[NR];
+  int n_pow2 = kKeep;
+  while (n_pow2 < total) n_pow2 <<= 1;
+  for (int i = total + threadIdx.x; i < n_pow2; i += blockDim.x) mkeys[i] = ~0ull;
   for (int r = 0; r < NR; ++r) {
-    const int c = cand_cnt[size_t(q) * NR + r];
-    total += c;
+    const int o = s_off[r], c = s_off[r + 1] - o;
     const size_t base = (size_t(q) * NR + r) * kCandCap;
-    for (int e = threadIdx.x; e < c; e += blockDim.x) mkeys[r * kKeep + e] = cand_key64(cand_s[base + e], cand_i[base + e]);
+    for (int e = threadIdx.x; e < c; e += blockDim.x) mkeys[o + e] = cand_key64(cand_s[base + e], cand_i[base + e]);
   }
   bitonic_sort_smem(mkeys, n_pow2);
-  if (threadIdx.x < kKeep) {
-    const unsigned long long k = mkeys[threadIdx.x];
-    sel_idx[size_t(q) * kKeep + threadIdx.x] = (threadIdx.x < total) ? uint32_t(k & 0xffffffffu) : 0xffffffffu;
+  // Everything that is NOT among the selected entries scored >= T:
+  //   entries left in the lists score >= the kKeep-th smallest of the union;
+  //   anything a range rejected or pruned scored >= the threshold in force, which was >= the final published one.
+  // Of the kKeep best, only candidates within 2*eps of the k-th best fp16 score can belong to the exact top-k
+  // (a candidate c beyond that has exact_c >= s_c - eps > s_k + eps >= the exact score of each of the k best), so the
+  // rest is not rescored and T is lowered to that cutoff.
+  const unsigned int pub = q_thr[q];
+  const float t_pub = pub == 0xffffffffu ? INFINITY : key64_score((unsigned long long)pub << 32);
+  const float t_sel = total >= kKeep ? key64_score(mkeys[kKeep - 1]) : INFINITY;
+  float T = fminf(t_sel, t_pub);
+  int n_sel = total < kKeep ? total : kKeep;
+  if (total > k && (long long)total < h->R) {
+    const double eps = knn_eps(sqrt(qn2[q]), qexp[q], h);
+    const double cut = double(key64_score(mkeys[k - 1])) + 2.0 * eps;
+    if (threadIdx.x < n_sel && double(key64_score(mkeys[threadIdx.x])) <= cut) atomicAdd(&s_need, 1);
+    __syncthreads();
+    if (s_need < n_sel) {
+      n_sel = s_need;                                  // keys are sorted: the needed ones are a prefix
+      T = fminf(T, __double2float_rd(cut));
+    }
   }
+  if (threadIdx.x < kKeep)
+    sel_idx[size_t(q) * kKeep + threadIdx.x] = (threadIdx.x < n_sel) ? uint32_t(mkeys[threadIdx.x] & 0xffffffffu) : 0xffffffffu;
   if (threadIdx.x == 0) {
     sel_n[q] = total;
-    // Everything that is NOT among the kKeep selected entries scored >= T:
-    //   entries left in the lists score >= the kKeep-th smallest of the union;
-    //   anything a range rejected or pruned scored >= the threshold in force, which was >= the final published one.
-    const unsigned int pub = q_thr[q];
-    const float t_pub = pub == 0xffffffffu ? INFINITY : key64_score((unsigned long long)pub << 32);
-    const float t_sel = total >= kKeep ? key64_score(mkeys[kKeep - 1]) : INFINITY;
-    sel_T[q] = fminf(t_sel, t_pub);
+    sel_T[q] = T;
   }
 }
 
@@ -225,20 +263,6 @@ __global__ void __launch_bounds__(256) knn_rescore_kernel(const float* __restric
   }
   acc = warp_sum(acc);
   if (lane == 0) d2[p] = acc;
-}
-
-// rigorous bound on |fp16-pass score - exact score| for query q against ANY row of the shard (see DESIGN.md)
-__device__ double knn_eps(double qnorm, int eq, const ShadowHeader* h) {
-  const double u = ldexp(1.0, -11), a = ldexp(1.0, -25);
-  const double rmax = sqrt(__longlong_as_double((long long)h->rmax2_bits));
-  const double Qn = ldexp(qnorm, eq), Rn = ldexp(rmax, h->scale_exp);
-  const double sD = sqrt(double(h->Dp));
-  const double Qt = Qn * (1.0 + u) + a * sD, Rt = Rn * (1.0 + u) + a * sD;        // norms of the rounded vectors
-  double e = u * (2.0 + u) * Qn * Rn + a * (1.0 + u) * sD * (Qn + Rn) + double(h->Dp) * a * a;   // input rounding
-  e += (double(h->Dp) / 16.0 + 1.0) * ldexp(1.0, -21) * Qt * Rt;                // tensor-core fp32 accumulation
-  const double e_dot = ldexp(e, -(eq + h->scale_exp));
-  const double smax = rmax * rmax + 2.0 * qnorm * rmax + 2.0 * e_dot;
-  return 2.0 * e_dot + ldexp(1.0, -23) * (rmax * rmax + smax);                    // + norm and fma rounding
 }
 
 // order the kKeep rescored candidates of one query by (d^2, idx), emit the top-k, certify.  One warp per query.
@@ -556,6 +580,7 @@ struct QueryWs {
   uint32_t* cand_i;
   int* cand_cnt;
   unsigned int* q_thr;
+  unsigned int* sync_ctr;
   uint32_t* sel_idx;
   float* sel_T;
   int* sel_n;
@@ -592,7 +617,7 @@ static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* 
   Carver c(base, bytes);
   const int Dp = pad64(D);
   int mb, nt, NR, tpr, gm;
-  knn_tc_tiling(Q, R, &mb, &nt, &NR, &tpr, &gm);
+  knn_tc_tiling(Q, R, Dp, &mb, &nt, &NR, &tpr, &gm);
   QueryWs tmp;
   QueryWs* o = w ? w : &tmp;
   o->stats = c.take<int>(8);
@@ -604,6 +629,7 @@ static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* 
   o->cand_i = c.take<uint32_t>(size_t(Q) * NR * kCandCap);
   o->cand_cnt = c.take<int>(size_t(Q) * NR);
   o->q_thr = c.take<unsigned int>(Q);
+  o->sync_ctr = c.take<unsigned int>(kSyncMax);
   o->sel_idx = c.take<uint32_t>(size_t(Q) * kKeep);
   o->sel_T = c.take<float>(Q);
   o->sel_n = c.take<int>(Q);
@@ -728,9 +754,11 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
 
   TcArgs a = {};
   a.rn = rn; a.qmul = w.qmul; a.Q = Q; a.R = int(R); a.Dp = Dp;
-  knn_tc_tiling(Q, R, &a.num_m_blocks, &a.num_n_tiles, &a.NR, &a.tiles_per_range, &a.group_m);
+  knn_tc_tiling(Q, R, Dp, &a.num_m_blocks, &a.num_n_tiles, &a.NR, &a.tiles_per_range, &a.group_m);
   a.cand_s = w.cand_s; a.cand_i = w.cand_i; a.cand_cnt = w.cand_cnt; a.q_thr = w.q_thr;
   SCL_CUDA_TRY(cudaMemsetAsync(w.q_thr, 0xff, size_t(Q) * sizeof(unsigned int), stream));
+  a.sync_ctr = w.sync_ctr;
+  SCL_CUDA_TRY(cudaMemsetAsync(w.sync_ctr, 0, size_t(kSyncMax) * sizeof(unsigned int), stream));
   a.dbg_scores = nullptr;
   const char* dbg = getenv("SCL_KNN_DEBUG_SCORES");     // test hook: address of a [Q,R] float buffer, in hex
   if (dbg) a.dbg_scores = reinterpret_cast<float*>(strtoull(dbg, nullptr, 16));
@@ -746,15 +774,15 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
   if (timing) SCL_CUDA_TRY(cudaEventRecord(ev1, stream));
 
   int n_pow2 = 1;
-  while (n_pow2 < a.NR * kKeep) n_pow2 <<= 1;
+  while (n_pow2 < a.NR * kCandCap) n_pow2 <<= 1;          // worst case: every list full
   const size_t merge_smem = size_t(n_pow2) * sizeof(unsigned long long);
   static size_t merge_cfg = 0;
   if (merge_smem > 48 * 1024 && merge_cfg < merge_smem) {
     SCL_CUDA_TRY(cudaFuncSetAttribute(knn_cand_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(merge_smem)));
     merge_cfg = merge_smem;
   }
-  knn_cand_merge_kernel<<<Q, 256, merge_smem, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, w.q_thr, a.NR, n_pow2, w.sel_idx, w.sel_T,
-                                                        w.sel_n);
+  knn_cand_merge_kernel<<<Q, 256, merge_smem, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, w.q_thr, a.NR, k, w.qn2, w.qexp, h,
+                                                        w.sel_idx, w.sel_T, w.sel_n);
   SCL_LAUNCH_CHECK();
   const long long pairs = (long long)Q * kKeep;
   knn_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, stream>>>(db, queries, D, w.sel_idx, pairs, w.d2);

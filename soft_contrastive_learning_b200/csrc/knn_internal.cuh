@@ -33,9 +33,17 @@ struct TcArgs {
   unsigned int* q_thr;   // [Q] best (smallest) pruning threshold any range has published for the query, as an
                          //     order-preserving uint (0xffffffff = none yet); shared by all ranges of the query
   float* dbg_scores;     // optional [Q, R]: raw fp16-pass scores (tests)
+  // Sliding-window pacing of the TMA producers (performance only, never needed for correctness): producer w bumps
+  // sync_ctr[p] once it has issued the loads of its p-th sync point (a fraction of a tile) and does not start point p
+  // before every worker has passed point p - sync_window.  Keeps the workers that stream the same database range (and
+  // the same query blocks) within a fraction of a tile of each other, so the shared operand is fetched from HBM once
+  // and found in L2 by everybody else.  nullptr / sync_total == 0 disables it.
+  unsigned int* sync_ctr;   // [kSyncMax], zeroed before the launch
+  int sync_total, sync_window, sync_subs;
 };
+constexpr int kSyncMax = 1 << 16;
 
 int knn_tc_launch(const TcArgs& a, const void* queries_fp16, const void* db_fp16, cudaStream_t stream);
-void knn_tc_tiling(int Q, int64_t R, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range, int* group_m);
+void knn_tc_tiling(int Q, int64_t R, int Dp, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range, int* group_m);
 
 }  // namespace scl

@@ -175,35 +175,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = worker; item < num_items; item += num_workers) {
+      // pacing (see TcArgs::sync_ctr): only the leader CTA of a pair takes part, its peer follows through the ring
+      const bool pace = a.sync_total > 0 && crank == 0;
+      const int subs = a.sync_subs;
+      int round = 0;
+      int sp_next = 0;                                   // first sync point this worker has not bumped yet
+      for (int item = worker; item < num_items; item += num_workers, ++round) {
         int range, mu;
         decode_item(item, m_units, a.NR, a.group_m, range, mu);
         const int mb = kPair ? 2 * mu + int(crank) : mu;
         const int t0 = range * a.tiles_per_range, t1 = min(a.num_n_tiles, t0 + a.tiles_per_range);
         for (int t = t0; t < t1; ++t) {
-          for (int kc = 0; kc < num_k; ++kc) {
-            mbar_wait(&tail->empty[stage], phase ^ 1);
-            uint8_t* sa = smem + size_t(stage) * kStageBytes;
-            if (kPair) {
-              // both CTAs report their bytes to the LEADER's barrier; only the leader arms it (with both shares)
-              const uint32_t lead_bar = mapa_u32(smem_u32(&tail->full[stage]), 0);
-              if (crank == 0) mbar_arrive_expect_tx(&tail->full[stage], Cfg::kTxBytes);
-              tma_load_2d_2sm(sa, &tmA, lead_bar, kc * kBK, mb * kBM);
-#pragma unroll
-              for (int sub = 0; sub < kNSub; ++sub)
-                tma_load_2d_2sm(sa + kABytes + sub * Cfg::kBBytes, &tmB, lead_bar, kc * kBK,
-                                t * kTileN + sub * kBN + int(crank) * int(Cfg::kBRows));
-            } else {
-              mbar_arrive_expect_tx(&tail->full[stage], Cfg::kTxBytes);
-              tma_load_2d(sa, &tmA, &tail->full[stage], kc * kBK, mb * kBM);
-#pragma unroll
-              for (int sub = 0; sub < kNSub; ++sub)
-                tma_load_2d(sa + kABytes + sub * Cfg::kBBytes, &tmB, &tail->full[stage], kc * kBK, t * kTileN + sub * kBN);
+          for (int sub = 0; sub < subs; ++sub) {
+            const int kc0 = sub * num_k / subs, kc1 = (sub + 1) * num_k / subs;
+            const int sp = (round * a.tiles_per_range + (t - t0)) * subs + sub;
+            if (pace) {
+              while (sp_next < sp) atomicAdd(a.sync_ctr + sp_next++, 1u);      // points of a short range
+              if (sp >= a.sync_window) {
+                const volatile unsigned int* c = a.sync_ctr + (sp - a.sync_window);
+                if (*c < unsigned(num_workers)) {
+                  const long long w0 = clock64();
+                  while (*c < unsigned(num_workers) && clock64() - w0 < 400000) __nanosleep(256);
+                }
+              }
             }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            for (int kc = kc0; kc < kc1; ++kc) {
+              mbar_wait(&tail->empty[stage], phase ^ 1);
+              uint8_t* sa = smem + size_t(stage) * kStageBytes;
+              if (kPair) {
+                // both CTAs report their bytes to the LEADER's barrier; only the leader arms it (with both shares)
+                const uint32_t lead_bar = mapa_u32(smem_u32(&tail->full[stage]), 0);
+                if (crank == 0) mbar_arrive_expect_tx(&tail->full[stage], Cfg::kTxBytes);
+                tma_load_2d_2sm(sa, &tmA, lead_bar, kc * kBK, mb * kBM);
+#pragma unroll
+                for (int sub2 = 0; sub2 < kNSub; ++sub2)
+                  tma_load_2d_2sm(sa + kABytes + sub2 * Cfg::kBBytes, &tmB, lead_bar, kc * kBK,
+                                  t * kTileN + sub2 * kBN + int(crank) * int(Cfg::kBRows));
+              } else {
+                mbar_arrive_expect_tx(&tail->full[stage], Cfg::kTxBytes);
+                tma_load_2d(sa, &tmA, &tail->full[stage], kc * kBK, mb * kBM);
+#pragma unroll
+                for (int sub2 = 0; sub2 < kNSub; ++sub2)
+                  tma_load_2d(sa + kABytes + sub2 * Cfg::kBBytes, &tmB, &tail->full[stage], kc * kBK,
+                              t * kTileN + sub2 * kBN);
+              }
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            if (pace) { atomicAdd(a.sync_ctr + sp, 1u); sp_next = sp + 1; }
           }
         }
       }
+      // this worker is done: it counts as "passed" for every remaining point, so nobody waits for it
+      if (pace) while (sp_next < a.sync_total) atomicAdd(a.sync_ctr + sp_next++, 1u);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA of a pair only) =====================
@@ -393,10 +416,11 @@ int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, size_t elem_bytes,
 }
 
 static int tc_variant() {
-  // 1 = single-CTA 128x256 tiles, 2 = CTA pairs 256x256, 3 = CTA pairs 256x512 (default)
+  // 1 = single-CTA 128x256 tiles, 2 = CTA pairs 256x256 with double-buffered accumulators (default: the epilogue
+  // of tile i overlaps the MMAs of tile i+1), 3 = CTA pairs 256x512 (a quarter less L2->SM traffic, no overlap)
   const char* env = getenv("SCL_KNN_TC_VARIANT");
   if (env && atoi(env) >= 1 && atoi(env) <= 3) return atoi(env);
-  return 3;
+  return 2;
 }
 static int tc_tile_n(int variant) { return variant == 3 ? 2 * kBN : kBN; }
 
@@ -413,6 +437,25 @@ static int tc_launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   const int items = m_units * a.NR;
   const int workers_max = kPair ? sms / 2 : sms;
   const int workers = items < workers_max ? items : workers_max;
+  TcArgs args = a;
+  {
+    // pacing of the producers: `subs` sync points per tile, window in sync points (SCL_KNN_SYNC=0 switches it off)
+    const char* es = getenv("SCL_KNN_SYNC");
+    const char* ew = getenv("SCL_KNN_SYNC_WINDOW");
+    const char* eb = getenv("SCL_KNN_SYNC_SUBS");
+    const int num_k = a.Dp / kBK;
+    int subs = eb ? atoi(eb) : 4;
+    if (subs < 1) subs = 1;
+    if (subs > num_k) subs = num_k;
+    int window = ew ? atoi(ew) : subs;
+    if (window < 1) window = 1;
+    const long long rounds = (items + workers - 1) / workers;
+    const long long total = rounds * a.tiles_per_range * subs;
+    const bool on = !(es && atoi(es) == 0) && a.sync_ctr != nullptr && workers > 1 && total <= kSyncMax;
+    args.sync_subs = subs;
+    args.sync_window = window;
+    args.sync_total = on ? int(total) : 0;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(kPair ? 2 * workers : workers));
   cfg.blockDim = dim3(kTcThreads);
@@ -425,7 +468,7 @@ static int tc_launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SCL_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a));
+  SCL_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, args));
   return SCL_OK;
 }
 
@@ -443,7 +486,7 @@ int knn_tc_launch(const TcArgs& a, const void* qh, const void* dbh, cudaStream_t
   return tc_launch_variant<true, 2>(tmA, tmB, a, stream);
 }
 
-void knn_tc_tiling(int Q, int64_t R, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range, int* group_m) {
+void knn_tc_tiling(int Q, int64_t R, int Dp, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range, int* group_m) {
   const int mb = (Q + kBM - 1) / kBM;
   const int variant = tc_variant();
   const int tile_n = tc_tile_n(variant);
@@ -469,12 +512,16 @@ void knn_tc_tiling(int Q, int64_t R, int* num_m_blocks, int* num_n_tiles, int* N
   *num_n_tiles = nt;
   *NR = best;
   *tiles_per_range = (nt + best - 1) / best;
-  // 16 query blocks (16 MB of fp16 at D = 4096) per group: small enough to stay L2-resident next to the database
-  // streams, large enough that each range is re-streamed from HBM only ceil(mb / 16) times
-  int gm = pair ? 8 : 16;
+  // query-axis work units per group: ~40 MB of fp16 query blocks (20 CTA-pair units at D = 4096) stay L2-resident next
+  // to the database streams, and each range is streamed from HBM only ceil(units / group) times (measured on B200:
+  // group 20 -> 1267 TFLOP/s, 8 -> 1160, 40 -> 1119)
+  const long long unit_bytes = (pair ? 2ll : 1ll) * kBM * Dp * 2;
+  int gm = int((40ll << 20) / (unit_bytes > 0 ? unit_bytes : 1));
+  if (gm < 2) gm = 2;
   const char* genv = getenv("SCL_KNN_GROUP_M");
   if (genv && atoi(genv) >= 1) gm = atoi(genv);
   if (gm > mu) gm = mu;
+  gm = (mu + (mu + gm - 1) / gm - 1) / ((mu + gm - 1) / gm);      // equal-sized groups
   *group_m = gm;
 }
 

@@ -1,4 +1,6 @@
-// wms_tuple.cu -- W1 tuple mode: fused forward + analytic backward of the weighted multi-similarity loss.
+// wms_tuple.cu -- W1 tuple mode, C-ABI entry point and the CHUNKED kernel for tuples whose column slice does not
+// fit in shared memory (D = 32768); everything else runs wms_tuple_resident.cu.  Fused forward + analytic backward
+// of the weighted multi-similarity loss.
 //
 // Replaces wms_loss (/root/reference/model/losses.py:5-60, call train/train.py:852) and the TF autodiff of
 // it (train.py:874-878) for T independent tuples of S <= 32 descriptors.
@@ -51,7 +53,7 @@ __constant__ unsigned char c_tile_a[kNumTiles] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 
 __constant__ unsigned char c_tile_b[kNumTiles] = {0, 1, 2, 3, 4, 1, 2, 3, 4, 2, 3, 4, 3, 4, 4};
 
 template <int TS>
-__global__ void __launch_bounds__(kWmsThreads, (TS <= 6 ? 2 : 1)) wms_tuple_kernel(
+__global__ void __launch_bounds__(kWmsThreads, (TS <= 6 ? 2 : 1)) wms_tuple_chunked_kernel(
     const float* __restrict__ emb, const float* __restrict__ dist, int T, int S, int D, int Ds, int Dc,
     scl_ms_params p, float* __restrict__ per_tuple, float* __restrict__ demb, uint32_t* __restrict__ kept,
     float* __restrict__ loss_out, unsigned int* __restrict__ done_counter) {
@@ -293,10 +295,10 @@ static int wms_plan(int S, int D, WmsPlan* pl) {
 }
 
 template <int TS>
-static int wms_launch(const WmsPlan& pl, const float* emb, const float* dist, int T, int S, int D,
+static int wms_launch_chunked(const WmsPlan& pl, const float* emb, const float* dist, int T, int S, int D,
                       const scl_ms_params& p, float* per_tuple, float* demb, uint32_t* kept, float* loss,
                       unsigned int* counter, cudaStream_t stream) {
-  auto kern = wms_tuple_kernel<TS>;
+  auto kern = wms_tuple_chunked_kernel<TS>;
   static std::atomic<size_t> configured{0};   // idempotent attribute, set only when it has to grow
   if (configured.load(std::memory_order_relaxed) < pl.smem) {
     SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
@@ -318,6 +320,9 @@ static int wms_launch(const WmsPlan& pl, const float* emb, const float* dist, in
                                   counter));
   return SCL_OK;
 }
+
+int wms_resident_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
+                        float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream);
 
 }  // namespace scl
 
@@ -346,9 +351,11 @@ extern "C" int scl_wms_tuple_fwd_bwd(const float* emb, const float* dist, int T,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   unsigned int* counter = static_cast<unsigned int*>(workspace);
   SCL_CUDA_TRY(cudaMemsetAsync(counter, 0, 16, stream));
+  rc = scl::wms_resident_launch(emb, dist, T, S, D, *p, loss, per_tuple, demb, kept, counter, stream);
+  if (rc != SCL_ERR_UNSUPPORTED) return rc;
   switch (pl.ts) {
-    case 5: return scl::wms_launch<5>(pl, emb, dist, T, S, D, *p, per_tuple, demb, kept, loss, counter, stream);
-    case 6: return scl::wms_launch<6>(pl, emb, dist, T, S, D, *p, per_tuple, demb, kept, loss, counter, stream);
-    default: return scl::wms_launch<7>(pl, emb, dist, T, S, D, *p, per_tuple, demb, kept, loss, counter, stream);
+    case 5: return scl::wms_launch_chunked<5>(pl, emb, dist, T, S, D, *p, per_tuple, demb, kept, loss, counter, stream);
+    case 6: return scl::wms_launch_chunked<6>(pl, emb, dist, T, S, D, *p, per_tuple, demb, kept, loss, counter, stream);
+    default: return scl::wms_launch_chunked<7>(pl, emb, dist, T, S, D, *p, per_tuple, demb, kept, loss, counter, stream);
   }
 }
