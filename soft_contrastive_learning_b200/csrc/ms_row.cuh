@@ -63,7 +63,7 @@ __device__ __forceinline__ float ms_row_loss(float A, float B, const scl_ms_para
 }
 __device__ __forceinline__ float ms_elem_grad(float wp, float wn, bool keptp, bool keptn, float ep, float en, float A,
                                               float B, const scl_ms_params& p) {
-  if (p.sumfunction == SCL_SUM_MS) return -wp * ep / (1.0f + A) + wn * en / (1.0f + B);
+  if (p.sumfunction == SCL_SUM_MS) return -wp * __fdividef(ep, 1.0f + A) + wn * __fdividef(en, 1.0f + B);   // gradient only: 2 ulp
   return (keptn ? wn : 0.0f) - (keptp ? wp : 0.0f);
 }
 

@@ -321,6 +321,8 @@ static int wms_launch_chunked(const WmsPlan& pl, const float* emb, const float* 
   return SCL_OK;
 }
 
+int wms_stream_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
+                      float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream);
 int wms_resident_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
                         float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream);
 
@@ -351,6 +353,9 @@ extern "C" int scl_wms_tuple_fwd_bwd(const float* emb, const float* dist, int T,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   unsigned int* counter = static_cast<unsigned int*>(workspace);
   SCL_CUDA_TRY(cudaMemsetAsync(counter, 0, 16, stream));
+  // large batches: streaming kernel (one tuple per CTA); small ones: a cluster per tuple (resident slice if it fits)
+  rc = scl::wms_stream_launch(emb, dist, T, S, D, *p, loss, per_tuple, demb, kept, counter, stream);
+  if (rc != SCL_ERR_UNSUPPORTED) return rc;
   rc = scl::wms_resident_launch(emb, dist, T, S, D, *p, loss, per_tuple, demb, kept, counter, stream);
   if (rc != SCL_ERR_UNSUPPORTED) return rc;
   switch (pl.ts) {

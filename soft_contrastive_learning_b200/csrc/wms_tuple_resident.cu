@@ -42,11 +42,10 @@ struct RSmem {
   static constexpr int NP = kRTiles * TS * TS;
   static constexpr int HR = (SG + 1) / 2;
   static constexpr int HRP = (HR + 3) / 4 * 4;
-  static constexpr int GF = int(al4(size_t(SG) * (SG + 1)));          // Gram, then Mt behind it
-  static constexpr int MT = SG * 2 * HRP;
-  static constexpr int RED = (kRRed * NP > GF + MT) ? kRRed * NP : GF + MT;
+  static constexpr int MT = SG * 2 * HRP;                              // transposed M (overlays the slots)
+  static constexpr int RED = (kRRed * NP > 2 * SG * SG) ? kRRed * NP : 2 * SG * SG;   // reduction, then Gw and Sraw
   static __host__ __device__ size_t slots_floats(int C) {
-    size_t a = size_t(C) * NP, b = 2 * size_t(SG) * SG;
+    size_t a = size_t(C) * NP, b = MT;
     return al4(a > b ? a : b);
   }
   static __host__ __device__ size_t bytes(int Ds, int C) {
@@ -93,13 +92,10 @@ __global__ void __launch_bounds__(kRThreads, (TS == 5 ? 2 : 1)) wms_tuple_kernel
   const int ncols4 = Ds >> 2;
 
   float* Es = smem;
-  float* red = Es + size_t(SG) * pitch;          // cross-warp reduction, later Gf and Mt
-  float* slots = red + al4(L::RED);              // cluster exchange, later Gw and Sraw
+  float* red = Es + size_t(SG) * pitch;          // cross-warp reduction, later Gw and Sraw
+  float* slots = red + al4(L::RED);              // cluster exchange, later Mt
   float* misc = slots + L::slots_floats(C);
-  float* invn = misc;
-  float* nflag = invn + SG;
-  float* rowloss = nflag + SG;
-  float* cvec = rowloss + SG;
+  float* rowloss = misc;
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc + al4(4 * SG));
 
   if (tid == 0) {
@@ -112,7 +108,7 @@ __global__ void __launch_bounds__(kRThreads, (TS == 5 ? 2 : 1)) wms_tuple_kernel
   __syncthreads();
   // every CTA of the cluster must be resident before anyone writes into a peer's shared memory: arrive now,
   // wait just before the push
-  if (C > 1) cluster_arrive();
+  if (C > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
   // ---------------- 1. slice -> shared memory ----------------
   const float* E_t = emb + (size_t(t) * S) * D + size_t(crank) * Ds;
@@ -218,85 +214,119 @@ __global__ void __launch_bounds__(kRThreads, (TS == 5 ? 2 : 1)) wms_tuple_kernel
     }
   }
   if (C > 1) cluster.sync(); else __syncthreads();
-  float* Gf = red;                                  // [SG][SG+1]
-  float* Mt = red + L::GF;                          // [SG][2*HRP], 16-byte aligned
-  for (int k = tid; k < NP; k += kRThreads) {
-    float s = 0.0f;
-    for (int c = 0; c < C; ++c) s += slots[c * NP + k];
-    const int rq = k / kRTiles, tile = k - rq * kRTiles;
-    const int r = rq / TS, q = rq - r * TS;
-    const int i = c_rtile_a[tile] + kRGrid * r, j = c_rtile_b[tile] + kRGrid * q;
-    Gf[i * (SG + 1) + j] = s;
-    if (c_rtile_a[tile] != c_rtile_b[tile]) Gf[j * (SG + 1) + i] = s;
-  }
-  __syncthreads();
 
-  // ---------------- 3. weights: one warp per anchor row ----------------
-  if (tid < SG) {
-    const float n2 = tid < S ? Gf[tid * (SG + 1) + tid] : 1.0f;
-    // tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12))  (losses.py:7)
-    invn[tid] = rsqrtf(fmaxf(n2, 1e-12f));
-    nflag[tid] = n2 >= 1e-12f ? 1.0f : 0.0f;     // below the clamp the normalisation is a pure scale
-  }
-  __syncthreads();
-  float* Gw = slots;                              // dL/ds_ij
-  float* Sraw = slots + SG * SG;                  // cosine similarity before the relu
+  // ---------------- 3. weights: warp w owns anchor rows w, w+8, w+16, w+24 (interleaved), lane = column j ----------------
+  // G_ij is summed straight out of the exchange slots in a fixed order (identical in every CTA of the cluster).
+  auto gram = [&](int i, int j) -> float {
+    int a = i % kRGrid, r = i / kRGrid, b = j % kRGrid, q = j / kRGrid;
+    if (a > b) { int x = a; a = b; b = x; x = r; r = q; q = x; }
+    const int k = (r * TS + q) * kRTiles + (a * kRGrid - (a * (a - 1)) / 2 + (b - a));
+    float v = 0.0f;
+    for (int c = 0; c < C; ++c) v += slots[c * NP + k];
+    return v;
+  };
+  float* Gw = red;                                // dL/ds_ij        [SG][SG]
+  float* Sraw = red + SG * SG;                    // cosine similarity before the relu
+  float* Mt = slots;                              // written after every warp is done with the slots
+  const int jj = lane < S ? lane : 0;
+  const float n2 = gram(jj, jj);
+  // tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12))  (losses.py:7); below the clamp it is a pure scale
+  const float invn_j = rsqrtf(fmaxf(n2, 1e-12f));
+  const float nflag_j = n2 >= 1e-12f ? 1.0f : 0.0f;
   const float invS = 1.0f / float(S);
+  const bool jvalid = lane < S;
+  float invn_i[4], raw[4], sv[4];
+  bool rvalid[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int i = warp + kRWarps * k;
-    if (i >= S) break;                            // warp-uniform
-    const int j = lane;
-    const bool valid = j < S;
-    const float wp = wpv[k], wn = wnv[k];
-    float raw = 0.0f, s = 0.0f;
-    if (valid) {
-      raw = Gf[i * (SG + 1) + j] * invn[i] * invn[j];
-      s = fmaxf(raw, 0.0f);                                              // losses.py:26
+    rvalid[k] = i < S;
+    const int ii = rvalid[k] ? i : 0;
+    invn_i[k] = __shfl_sync(0xffffffffu, invn_j, ii);
+    raw[k] = (rvalid[k] && jvalid) ? gram(ii, jj) * invn_i[k] * invn_j : 0.0f;
+    sv[k] = fmaxf(raw[k], 0.0f);                                           // losses.py:26
+  }
+  MsRowStats st[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    st[k].maxv = jvalid ? sv[k] * wnv[k] : -INFINITY;
+    st[k].tmp = jvalid ? sv[k] * wpv[k] : -INFINITY;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      st[k].maxv = fmaxf(st[k].maxv, __shfl_xor_sync(0xffffffffu, st[k].maxv, o));
+      st[k].tmp = fmaxf(st[k].tmp, __shfl_xor_sync(0xffffffffu, st[k].tmp, o));
     }
-    MsRowStats st;
-    st.maxv = warp_max(valid ? s * wn : -INFINITY);
-    st.tmp = warp_max(valid ? s * wp : -INFINITY);
-    st.minv = warp_min(valid ? (s - st.tmp) * wp : INFINITY) + st.tmp;
-    bool kp = false, kn = false;
-    float ep = 0.0f, en = 0.0f;
-    if (valid) ms_elem(s, wp, wn, st, p, kp, kn, ep, en);
-    const float A = warp_sum(ep), B = warp_sum(en);
-    if (valid) {
-      float gw = ms_elem_grad(wp, wn, kp, kn, ep, en, A, B, p) * invS;
-      if (!(raw >= 0.0f)) gw = 0.0f;                                     // tf.maximum passes gradient when x >= 0
-      Gw[i * SG + j] = gw;
-      Sraw[i * SG + j] = raw;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st[k].minv = jvalid ? (sv[k] - st[k].tmp) * wpv[k] : INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st[k].minv = fminf(st[k].minv, __shfl_xor_sync(0xffffffffu, st[k].minv, o));
+  bool kp[4], kn[4];
+  float ep[4], en[4], A[4], B[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    st[k].minv += st[k].tmp;
+    kp[k] = kn[k] = false;
+    ep[k] = en[k] = 0.0f;
+    if (jvalid && rvalid[k]) ms_elem(sv[k], wpv[k], wnv[k], st[k], p, kp[k], kn[k], ep[k], en[k]);
+    A[k] = ep[k];
+    B[k] = en[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      A[k] += __shfl_xor_sync(0xffffffffu, A[k], o);
+      B[k] += __shfl_xor_sync(0xffffffffu, B[k], o);
     }
-    if (lane == 0) rowloss[i] = ms_row_loss(A, B, p) * invS;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = warp + kRWarps * k;
+    if (rvalid[k]) {
+      if (jvalid) {
+        float gw = ms_elem_grad(wpv[k], wnv[k], kp[k], kn[k], ep[k], en[k], A[k], B[k], p) * invS;
+        if (!(raw[k] >= 0.0f)) gw = 0.0f;                                  // tf.maximum passes gradient when x >= 0
+        Gw[i * SG + lane] = gw;
+        Sraw[i * SG + lane] = raw[k];
+      }
+      if (lane == 0) rowloss[i] = ms_row_loss(A[k], B[k], p) * invS;
+    }
     if (kept != nullptr && crank == 0) {
-      const unsigned mp = __ballot_sync(0xffffffffu, kp), mn = __ballot_sync(0xffffffffu, kn);
-      if (lane == 0) {
+      const unsigned mp = __ballot_sync(0xffffffffu, kp[k]), mn = __ballot_sync(0xffffffffu, kn[k]);
+      if (lane == 0 && rvalid[k]) {
         kept[(size_t(t) * S + i) * 2 + 0] = mp;
         kept[(size_t(t) * S + i) * 2 + 1] = mn;
       }
     }
   }
   __syncthreads();
-  // M = (1/T) diag(invn) (W - diag(c)) diag(invn), W = Gw + Gw^T, c_i = sum_j W_ij s_ij(raw)  (projection of l2norm)
+  // M = (1/T) diag(invn) (W - diag(c)) diag(invn), W = Gw + Gw^T, c_i = sum_j W_ij s_ij(raw)  (projection of l2norm),
+  // stored transposed and split in two row halves for the backward: Mt[j][h*HRP + r] = M[h*HR + r][j]
+  const float invT = 1.0f / float(T);
+  float wij[4], cpart[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int i = warp + kRWarps * k;
-    if (i >= S) break;
-    float part = 0.0f;
-    if (lane < S) part = (Gw[i * SG + lane] + Gw[lane * SG + i]) * Sraw[i * SG + lane];
-    const float c = warp_sum(part) * nflag[i];
-    if (lane == 0) cvec[i] = c;
+    wij[k] = (rvalid[k] && jvalid) ? Gw[i * SG + lane] + Gw[lane * SG + i] : 0.0f;
+    cpart[k] = (rvalid[k] && jvalid) ? wij[k] * Sraw[i * SG + lane] : 0.0f;
   }
-  for (int k = tid; k < L::MT; k += kRThreads) Mt[k] = 0.0f;
-  __syncthreads();
-  const float invT = 1.0f / float(T);
-  for (int k = tid; k < S * S; k += kRThreads) {
-    const int i = k / S, j = k - i * S;
-    float w = Gw[i * SG + j] + Gw[j * SG + i];
-    if (i == j) w -= cvec[i];
-    const int h = i / HR, r = i - h * HR;
-    Mt[j * (2 * HRP) + h * HRP + r] = invn[i] * w * invn[j] * invT;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cpart[k] += __shfl_xor_sync(0xffffffffu, cpart[k], o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = warp + kRWarps * k;
+    const float c = cpart[k] * __shfl_sync(0xffffffffu, nflag_j, rvalid[k] ? i : 0);
+    if (rvalid[k] && jvalid) {
+      const float w = (i == lane) ? wij[k] - c : wij[k];
+      const int h = i / HR, r = i - h * HR;
+      Mt[lane * (2 * HRP) + h * HRP + r] = invn_i[k] * w * invn_j * invT;
+    }
   }
 
   // ---------------- loss ----------------

@@ -1,0 +1,446 @@
+// wms_tuple_stream.cu -- W1 tuple mode, throughput path: fused forward + analytic backward of the weighted
+// multi-similarity loss for large batches of tuples, one tuple per CTA at a time, descriptors STREAMED through a
+// shared-memory ring by a dedicated producer warp.
+//
+// Replaces wms_loss (/root/reference/model/losses.py:5-60, call train/train.py:852) and the TF autodiff of it
+// (train.py:874-878) for T independent tuples of S <= 32 descriptors of any dimension D (multiple of 4).
+//
+// Persistent CTAs (two per SM); CTA b handles tuples b, b + grid, ...  Per tuple the eight consumer warps run
+//   A. Gram: the S x D tile arrives in 256-column chunks (cp.async.bulk per row, mbarrier per ring stage); the
+//      symmetric 5x5 grid of TSxTS register tiles accumulates E E^T with packed FFMA2 (even/odd columns in one
+//      register pair); a two-round cross-warp reduction leaves the S x S Gram in shared memory;
+//   B. weights: GPS soft masks (losses.py:11-22) from the prefetched distance block, l2-normalisation, mining
+//      thresholds, log-sum-exp weights (ms_row.cuh), four anchor rows interleaved per warp; the l2-norm Jacobian
+//      and the 1/T batch mean are folded into one S x S matrix M;
+//   C. backward: the tile is streamed a second time (last chunk first, so the re-read finds it in L2) and
+//      d loss / d emb = M E leaves as 512-byte-per-row coalesced streaming stores; M enters FFMA2 as a broadcast
+//      scalar operand.
+// The producer warp runs ahead of the consumers across phases and tuples (the first chunks of tuple t+1 are in
+// flight while tuple t finishes), so neither the scalar phase B nor the load latency leaves the FP32 pipes idle as
+// long as the other CTA of the SM has work.  No cluster, no cross-CTA exchange, nothing computed redundantly.
+// HBM traffic is the algorithmic minimum as long as the second read hits L2: emb read once, demb written once.
+#include <atomic>
+#include <cstdlib>
+
+#include "ms_row.cuh"
+#include "tc_common.cuh"
+#include "tuple_common.cuh"
+
+namespace scl {
+
+using namespace tc;
+
+constexpr int kSWarps = 8;                                 // consumer warps
+constexpr int kSConsumers = kSWarps * 32;
+constexpr int kSThreads = kSConsumers + 32;                // + one producer warp
+constexpr int kSGrid = 5;                                  // 5 x 5 grid of TS x TS tiles
+constexpr int kSTiles = kSGrid * (kSGrid + 1) / 2;         // 15 symmetric tiles
+constexpr int kSStages = 4;
+constexpr int kSChunk = 256;                               // columns per ring stage
+constexpr int kSPitch = kSChunk + 4;                       // floats; rows 16 bytes apart in bank space
+constexpr int kSRed = 4;                                   // cross-warp reduction buffers (two rounds)
+
+template <int TS>
+struct SSmem {
+  static constexpr int SG = kSGrid * TS;
+  static constexpr int NP = kSTiles * TS * TS;
+  static constexpr int HR = (SG + 1) / 2;
+  static constexpr int HRP = (HR + 3) / 4 * 4;
+  static constexpr int MT = SG * 2 * HRP;
+  static constexpr int STAGE = SG * kSPitch;                                       // floats per ring stage
+  static constexpr int GW = int(al4(SG * SG));
+  static constexpr int WORK = (kSRed * NP > GW + MT) ? kSRed * NP : GW + MT;       // reduction, then Gw | Mt
+  static constexpr int DIST = int(al4(SG * SG));
+  static constexpr size_t floats = size_t(kSStages) * STAGE + al4(NP) + al4(WORK) + DIST + 32;
+  static constexpr size_t bytes = floats * sizeof(float) + (2 * kSStages + 2) * sizeof(uint64_t);
+};
+
+__constant__ unsigned char c_stile_a[kSTiles] = {0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 4};
+__constant__ unsigned char c_stile_b[kSTiles] = {0, 1, 2, 3, 4, 1, 2, 3, 4, 2, 3, 4, 3, 4, 4};
+
+__device__ __forceinline__ void s_ffma2(float2& d, const float2 a, const float2 b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(dd)
+      : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+__device__ __forceinline__ void s_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSConsumers) : "memory"); }
+
+template <int TS>
+__global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kernel(
+    const float* __restrict__ emb, const float* __restrict__ dist, int T, int S, int D, scl_ms_params p,
+    float* __restrict__ per_tuple, float* __restrict__ demb, uint32_t* __restrict__ kept, float* __restrict__ loss_out,
+    unsigned int* __restrict__ done_counter) {
+  using L = SSmem<TS>;
+  constexpr int SG = L::SG, NP = L::NP, HR = L::HR, HRP = L::HRP, STAGE = L::STAGE;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  float* ring = smem;                                   // [kSStages][SG][kSPitch]
+  float* Pg = ring + size_t(kSStages) * STAGE;          // reduced Gram in tile order [TS*TS][15]
+  float* work = Pg + al4(NP);                           // reduction buffers, later Gw [SG][SG] | Mt [SG][2*HRP]
+  float* dsm = work + al4(L::WORK);                     // this tuple's GPS distances [S][S]
+  float* rowloss = dsm + L::DIST;
+  uint64_t* full = reinterpret_cast<uint64_t*>(rowloss + 32);
+  uint64_t* empty = full + kSStages;
+  uint64_t* dfull = empty + kSStages;
+  uint64_t* dempty = dfull + 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < kSStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kSWarps);
+    }
+    mbar_init(dfull, 32);                                // one cp.async-completion arrival per producer lane
+    mbar_init(dempty, kSWarps);
+    fence_barrier_init();
+  }
+  // padding rows (>= S) of every stage stay zero for the whole kernel: the copies only write rows < S
+  for (int s = 0; s < kSStages; ++s)
+    for (int i = S * kSPitch + tid; i < SG * kSPitch; i += kSThreads) ring[size_t(s) * STAGE + i] = 0.0f;
+  __syncthreads();
+
+  const int nchunks = (D + kSChunk - 1) / kSChunk;
+  const int npairs = (nchunks + 1) / 2;
+  const bool need_bwd = demb != nullptr;
+
+  if (warp == kSWarps) {
+    // ============================ producer warp ============================
+    uint32_t pos = 0;                                   // ring position, runs across phases and tuples
+    uint32_t iter = 0;
+    for (int t = blockIdx.x; t < T; t += gridDim.x, ++iter) {
+      const float* E_t = emb + size_t(t) * S * D;
+      const int nseq = nchunks + (need_bwd ? nchunks : 0);
+      const int kdist = nseq > 2 ? 2 : nseq - 1;        // after the first chunks are in flight
+      for (int k = 0; k < nseq; ++k, ++pos) {
+        if (k == kdist) {
+          // GPS distances of this tuple (single buffer: free once phase B of the previous tuple has read it);
+          // 4-byte cp.async because S*S*4 is not a multiple of 16 for odd S
+          mbar_wait(dempty, (iter & 1) ^ 1);
+          const float* dsrc = dist + size_t(t) * S * S;
+          for (int i = lane; i < S * S; i += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dsm + i)), "l"(dsrc + i) : "memory");
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(dfull)) : "memory");
+        }
+        // phase A: chunks ascending; phase C: pairs descending, inside a pair ascending
+        int ch;
+        if (k < nchunks) {
+          ch = k;
+        } else {
+          const int kk = k - nchunks;                   // 0 .. nchunks-1
+          const int top = npairs - 1;                   // the (possibly half-filled) last pair comes first
+          const int first = nchunks - 2 * top;          // chunks in the last pair: 1 or 2
+          if (kk < first) ch = 2 * top + kk;
+          else { const int r = kk - first; ch = 2 * (top - 1 - r / 2) + (r & 1); }
+        }
+        const int stage = pos % kSStages;
+        mbar_wait(&empty[stage], ((pos / kSStages) & 1) ^ 1);
+        const int c0 = ch * kSChunk;
+        const uint32_t bytes = uint32_t(min(kSChunk, D - c0)) * 4u;
+        if (lane == 0) mbar_arrive_expect_tx(&full[stage], bytes * uint32_t(S));
+        __syncwarp();
+        if (lane < S) s_bulk_load(ring + size_t(stage) * STAGE + lane * kSPitch, E_t + size_t(lane) * D + c0, bytes, &full[stage]);
+      }
+    }
+    return;
+  }
+
+  // ============================ consumer warps ============================
+  const int tl = lane % kSTiles;
+  const int dg = lane / kSTiles;                   // 0,1 (lanes 30,31 -> 2: idle in the Gram)
+  const int ta = c_stile_a[tl], tb = c_stile_b[tl];
+  const int dgid = warp * 2 + dg;                  // 16 column groups per CTA
+  const bool jvalid = lane < S;
+  const int jj = jvalid ? lane : 0;
+  const float invS = 1.0f / float(S);
+  const float invT = 1.0f / float(T);
+  float* Gw = work;                                // dL/ds_ij [SG][SG]
+  float* Mt = work + L::GW;                        // [SG][2*HRP], 16-byte aligned
+  uint32_t pos = 0;
+  uint32_t iter = 0;
+
+  for (int t = blockIdx.x; t < T; t += gridDim.x, ++iter) {
+    // ---------------- A. Gram ----------------
+    float2 acc[TS][TS];
+#pragma unroll
+    for (int r = 0; r < TS; ++r)
+#pragma unroll
+      for (int q = 0; q < TS; ++q) acc[r][q] = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+    for (int ch = 0; ch < nchunks; ++ch, ++pos) {
+      const int stage = pos % kSStages;
+      const int nq = min(kSChunk, D - ch * kSChunk) >> 2;
+      const float* Es = ring + size_t(stage) * STAGE;
+      mbar_wait(&full[stage], (pos / kSStages) & 1);
+      if (dg < 2) {
+#pragma unroll 1
+        for (int c4 = dgid; c4 < nq; c4 += 2 * kSWarps) {
+          float4 x[TS], y[TS];
+#pragma unroll
+          for (int r = 0; r < TS; ++r) {
+            x[r] = *reinterpret_cast<const float4*>(Es + (ta + kSGrid * r) * kSPitch + 4 * c4);
+            y[r] = *reinterpret_cast<const float4*>(Es + (tb + kSGrid * r) * kSPitch + 4 * c4);
+          }
+#pragma unroll
+          for (int r = 0; r < TS; ++r)
+#pragma unroll
+            for (int q = 0; q < TS; ++q) {
+              s_ffma2(acc[r][q], make_float2(x[r].x, x[r].y), make_float2(y[q].x, y[q].y));
+              s_ffma2(acc[r][q], make_float2(x[r].z, x[r].w), make_float2(y[q].z, y[q].w));
+            }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+    // fold even/odd columns, the two column groups of a warp, then the warps (two rounds over kSRed buffers)
+    consumer_sync();                               // nobody still reads Mt of the previous tuple (tiny D)
+    {
+      float g[TS][TS];
+#pragma unroll
+      for (int r = 0; r < TS; ++r)
+#pragma unroll
+        for (int q = 0; q < TS; ++q) {
+          const float v = acc[r][q].x + acc[r][q].y;
+          g[r][q] = v + __shfl_down_sync(0xffffffffu, v, kSTiles);
+        }
+      if (warp >= kSRed && lane < kSTiles) {
+#pragma unroll
+        for (int r = 0; r < TS; ++r)
+#pragma unroll
+          for (int q = 0; q < TS; ++q) work[(warp - kSRed) * NP + (r * TS + q) * kSTiles + tl] = g[r][q];
+      }
+      consumer_sync();
+      if (warp < kSRed && lane < kSTiles) {
+#pragma unroll
+        for (int r = 0; r < TS; ++r)
+#pragma unroll
+          for (int q = 0; q < TS; ++q) work[warp * NP + (r * TS + q) * kSTiles + tl] += g[r][q];
+      }
+      consumer_sync();
+      for (int k = tid; k < NP; k += kSConsumers) Pg[k] = (work[k] + work[NP + k]) + (work[2 * NP + k] + work[3 * NP + k]);
+      consumer_sync();
+    }
+
+    // ---------------- B. weights: warp w owns anchor rows w, w+8, w+16, w+24 (interleaved), lane = column j ----------------
+    auto gram = [&](int i, int j) -> float {
+      int a = i % kSGrid, r = i / kSGrid, b = j % kSGrid, q = j / kSGrid;
+      if (a > b) { int x = a; a = b; b = x; x = r; r = q; q = x; }
+      return Pg[(r * TS + q) * kSTiles + (a * kSGrid - (a * (a - 1)) / 2 + (b - a))];
+    };
+    mbar_wait(dfull, iter & 1);
+    float wpv[4], wnv[4];
+    bool rvalid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = warp + kSWarps * k;
+      rvalid[k] = i < S;
+      wpv[k] = 0.0f;
+      wnv[k] = 0.0f;
+      if (rvalid[k] && jvalid) {
+        wms_masks(dsm[i * S + lane], p.d_alpha, p.d_beta, p.wfunction, wpv[k], wnv[k]);   // losses.py:11-19
+        if (i == lane) wpv[k] -= 1.0f;                                                     // losses.py:22
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(dempty);
+    const float n2 = gram(jj, jj);
+    // tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12))  (losses.py:7); below the clamp it is a pure scale
+    const float invn_j = rsqrtf(fmaxf(n2, 1e-12f));
+    const float nflag_j = n2 >= 1e-12f ? 1.0f : 0.0f;
+    float invn_i[4], raw[4], sv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ii = rvalid[k] ? warp + kSWarps * k : 0;
+      invn_i[k] = __shfl_sync(0xffffffffu, invn_j, ii);
+      raw[k] = (rvalid[k] && jvalid) ? gram(ii, jj) * invn_i[k] * invn_j : 0.0f;
+      sv[k] = fmaxf(raw[k], 0.0f);                                           // losses.py:26
+    }
+    MsRowStats st[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      st[k].maxv = jvalid ? sv[k] * wnv[k] : -INFINITY;
+      st[k].tmp = jvalid ? sv[k] * wpv[k] : -INFINITY;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        st[k].maxv = fmaxf(st[k].maxv, __shfl_xor_sync(0xffffffffu, st[k].maxv, o));
+        st[k].tmp = fmaxf(st[k].tmp, __shfl_xor_sync(0xffffffffu, st[k].tmp, o));
+      }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) st[k].minv = jvalid ? (sv[k] - st[k].tmp) * wpv[k] : INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) st[k].minv = fminf(st[k].minv, __shfl_xor_sync(0xffffffffu, st[k].minv, o));
+    bool kp[4], kn[4];
+    float ep[4], en[4], A[4], B[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      st[k].minv += st[k].tmp;
+      kp[k] = kn[k] = false;
+      ep[k] = en[k] = 0.0f;
+      if (jvalid && rvalid[k]) ms_elem(sv[k], wpv[k], wnv[k], st[k], p, kp[k], kn[k], ep[k], en[k]);
+      A[k] = ep[k];
+      B[k] = en[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        A[k] += __shfl_xor_sync(0xffffffffu, A[k], o);
+        B[k] += __shfl_xor_sync(0xffffffffu, B[k], o);
+      }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = warp + kSWarps * k;
+      if (rvalid[k]) {
+        if (jvalid) {
+          float gw = ms_elem_grad(wpv[k], wnv[k], kp[k], kn[k], ep[k], en[k], A[k], B[k], p) * invS;
+          if (!(raw[k] >= 0.0f)) gw = 0.0f;                                  // tf.maximum passes gradient when x >= 0
+          Gw[i * SG + lane] = gw;
+        }
+        if (lane == 0) rowloss[i] = ms_row_loss(A[k], B[k], p) * invS;
+      }
+      if (kept != nullptr) {
+        const unsigned mp = __ballot_sync(0xffffffffu, kp[k]), mn = __ballot_sync(0xffffffffu, kn[k]);
+        if (lane == 0 && rvalid[k]) {
+          kept[(size_t(t) * S + i) * 2 + 0] = mp;
+          kept[(size_t(t) * S + i) * 2 + 1] = mn;
+        }
+      }
+    }
+    consumer_sync();
+    // M = (1/T) diag(invn) (W - diag(c)) diag(invn), W = Gw + Gw^T, c_i = sum_j W_ij s_ij(raw)  (projection of l2norm),
+    // stored transposed and split in two row halves for the backward: Mt[j][h*HRP + r] = M[h*HR + r][j]
+    {
+      float wij[4], cpart[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = warp + kSWarps * k;
+        wij[k] = (rvalid[k] && jvalid) ? Gw[i * SG + lane] + Gw[lane * SG + i] : 0.0f;
+        cpart[k] = wij[k] * raw[k];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cpart[k] += __shfl_xor_sync(0xffffffffu, cpart[k], o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = warp + kSWarps * k;
+        const float c = cpart[k] * __shfl_sync(0xffffffffu, nflag_j, rvalid[k] ? i : 0);
+        if (rvalid[k] && jvalid) {
+          const float w = (i == lane) ? wij[k] - c : wij[k];
+          const int h = i / HR, r = i - h * HR;
+          Mt[lane * (2 * HRP) + h * HRP + r] = invn_i[k] * w * invn_j * invT;
+        }
+      }
+    }
+    // ---------------- loss ----------------
+    if (warp == 0) {
+      float v = lane < S ? rowloss[lane] : 0.0f;
+      v = warp_sum(v);
+      if (lane == 0 && per_tuple != nullptr) per_tuple[t] = v;
+      tup_finish_loss(done_counter, t, T, v, loss_out, lane);
+    }
+    consumer_sync();
+
+    // ---------------- C. backward: demb = M * E, chunk pairs in descending order ----------------
+    if (need_bwd) {
+      float* dE_t = demb + size_t(t) * S * D;
+#pragma unroll 1
+      for (int pr = npairs - 1; pr >= 0; --pr) {
+        const int chA = 2 * pr, chB = 2 * pr + 1;
+        const bool hasB = chB < nchunks;
+        const int stA = pos % kSStages, stB = (pos + 1) % kSStages;
+        const int nqA = min(kSChunk, D - chA * kSChunk) >> 2;
+        const int nqB = hasB ? (min(kSChunk, D - chB * kSChunk) >> 2) : 0;
+        mbar_wait(&full[stA], (pos / kSStages) & 1);
+        if (hasB) mbar_wait(&full[stB], ((pos + 1) / kSStages) & 1);
+        const int nq = nqA + nqB;
+        for (int item = tid; item < 2 * nq; item += kSConsumers) {
+          const int h = item / nq, c4 = item - h * nq;
+          const float* ecol = (c4 < nqA) ? ring + size_t(stA) * STAGE + 4 * c4 : ring + size_t(stB) * STAGE + 4 * (c4 - nqA);
+          const float* mcol = Mt + h * HRP;
+          float2 o[HR][2];
+#pragma unroll
+          for (int r = 0; r < HR; ++r) o[r][0] = o[r][1] = make_float2(0.0f, 0.0f);
+#pragma unroll 5
+          for (int j = 0; j < S; ++j) {
+            const float4 e = *reinterpret_cast<const float4*>(ecol + j * kSPitch);
+            const float4* mrow = reinterpret_cast<const float4*>(mcol + j * (2 * HRP));
+#pragma unroll
+            for (int r4 = 0; r4 < HRP / 4; ++r4) {
+              const float4 m = mrow[r4];
+              const float mv[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int r = r4 * 4 + u;
+                if (r < HR) {
+                  s_ffma2(o[r][0], make_float2(mv[u], mv[u]), make_float2(e.x, e.y));
+                  s_ffma2(o[r][1], make_float2(mv[u], mv[u]), make_float2(e.z, e.w));
+                }
+              }
+            }
+          }
+          float* dcol = dE_t + size_t(chA) * kSChunk + 4 * c4;
+#pragma unroll
+          for (int r = 0; r < HR; ++r) {
+            const int i = h * HR + r;
+            if (i < S)
+              stg_stream(reinterpret_cast<float4*>(dcol + size_t(i) * D), make_float4(o[r][0].x, o[r][0].y, o[r][1].x, o[r][1].y));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&empty[stA]);
+          if (hasB) mbar_arrive(&empty[stB]);
+        }
+        pos += hasB ? 2 : 1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int TS>
+static int stream_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p,
+                         float* per_tuple, float* demb, uint32_t* kept, float* loss, unsigned int* counter,
+                         cudaStream_t stream) {
+  auto kern = wms_stream_kernel<TS>;
+  static std::atomic<int> configured{0};
+  if (!configured.load(std::memory_order_relaxed)) {
+    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SSmem<TS>::bytes)));
+    configured.store(1, std::memory_order_relaxed);
+  }
+  const int per_sm = TS == 5 ? 2 : 1;
+  int grid = num_sms() * per_sm;
+  if (grid > T) grid = T;
+  kern<<<grid, kSThreads, SSmem<TS>::bytes, stream>>>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+// SCL_ERR_UNSUPPORTED: small batches go to the cluster kernels (more SMs per tuple).
+int wms_stream_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
+                      float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream) {
+  const char* env = getenv("SCL_WMS_STREAM");          // 0: never, 1: always, unset: large batches
+  const int mode = env ? atoi(env) : -1;
+  if (mode == 0) return SCL_ERR_UNSUPPORTED;
+  if (S < 2 || S > 32 || D < 4 || (D & 3)) return SCL_ERR_UNSUPPORTED;
+  if (mode != 1 && T < num_sms()) return SCL_ERR_UNSUPPORTED;
+  if (S <= 25) return stream_launch<5>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
+  if (S <= 30) return stream_launch<6>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
+  return stream_launch<7>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
+}
+
+}  // namespace scl

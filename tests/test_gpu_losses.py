@@ -93,6 +93,67 @@ def test_wms_cluster_sizes_agree(cuda_lib, cluster, monkeypatch):
     assert rel(loss, ref) < LOSS_TOL and grad_err(grad, rg) < GRAD_TOL
 
 
+# the three tuple-mode kernels: streaming (large batches), cluster-resident (small batches), cluster-chunked (slice too
+# large for shared memory); each is forced through the same shapes, incl. ragged D (not a multiple of the 256-column
+# ring stage), odd S (distance block not 16-byte sized), S = 32 (widest register tile) and a forward-only call
+WMS_PATHS = {"stream": {"SCL_WMS_STREAM": "1"}, "resident": {"SCL_WMS_STREAM": "0"},
+             "chunked": {"SCL_WMS_STREAM": "0", "SCL_WMS_CHUNKED": "1"}}
+
+
+@pytest.mark.parametrize("path", list(WMS_PATHS))
+@pytest.mark.parametrize("T,P,N,D", [(7, 12, 12, 4096), (3, 15, 16, 1024), (5, 3, 4, 64), (4, 12, 12, 1000),
+                                     (3, 13, 14, 772), (2, 12, 12, 256), (1, 12, 12, 8192)])
+def test_wms_kernel_paths_vs_oracle(cuda_lib, monkeypatch, path, T, P, N, D):
+    from soft_contrastive_learning_b200 import losses
+    for k, v in WMS_PATHS[path].items():
+        monkeypatch.setenv(k, v)
+    emb, dist, _ = synth.wms_batch(T=T, P=P, N=N, D=D, seed=11)
+    loss, grad, kept = losses.wms_loss_value_and_grad(dist, emb, 0.8, 15.0, return_kept=True)
+    ref, (rg,) = _oracle_wms(emb, dist)
+    assert rel(loss, ref) < LOSS_TOL, (loss, ref)
+    assert grad_err(grad, rg) < GRAD_TOL
+    S = 1 + P + N
+    kp, kn = _kept_bits(kept, S)
+    for t in range(T):
+        _, mp, mn = ol.wms_loss(dist[t].astype(np.float64), emb[t].astype(np.float64), 0.8, 15.0, return_masks=True)
+        assert np.array_equal(kp[t], mp.numpy()) and np.array_equal(kn[t], mn.numpy())
+
+
+@pytest.mark.parametrize("path", list(WMS_PATHS))
+def test_wms_kernel_paths_variants_and_forward_only(cuda_lib, monkeypatch, golden, path):
+    from soft_contrastive_learning_b200 import losses
+    for k, v in WMS_PATHS[path].items():
+        monkeypatch.setenv(k, v)
+    g = golden("wms_flat_S25_D64")
+    for tag, kw in WMS_VARIANTS.items():
+        loss, grad = losses.wms_loss_value_and_grad(g["dist"], g["emb"], 0.8, 15.0, **kw)
+        assert rel(loss, float(g["loss_" + tag])) < LOSS_TOL
+        assert grad_err(grad, g["grad_" + tag]) < GRAD_TOL
+    e = torch.tensor(g["emb"], device="cuda")
+    d = torch.tensor(g["dist"], device="cuda")
+    with torch.no_grad():
+        l = losses.wms_loss(d, e, 0.8, 15.0)               # forward only: demb == NULL in the C call
+    assert rel(float(l), float(g["loss_exp_ms_mine"])) < LOSS_TOL
+
+
+def test_wms_stream_large_batch_matches_small_batch_kernels(cuda_lib, monkeypatch):
+    """T = 600 tuples (several per persistent CTA): the streaming kernel against the cluster kernel, per tuple."""
+    from soft_contrastive_learning_b200 import losses
+    emb, dist, _ = synth.wms_batch(T=40, P=12, N=12, D=1024, seed=21)
+    emb = np.tile(emb, (15, 1, 1)) + 1e-3 * np.random.default_rng(0).standard_normal((600, 25, 1024)).astype(np.float32)
+    dist = np.tile(dist, (15, 1, 1))
+    p = losses._ms_params(0.8, 15.0)
+    e, d = torch.tensor(emb, device="cuda"), torch.tensor(dist, device="cuda")
+    monkeypatch.setenv("SCL_WMS_STREAM", "1")
+    l1, g1, k1, t1 = losses._wms_tuple_raw(e, d, p, need_grad=True, want_kept=True, want_per_tuple=True)
+    monkeypatch.setenv("SCL_WMS_STREAM", "0")
+    l0, g0, k0, t0 = losses._wms_tuple_raw(e, d, p, need_grad=True, want_kept=True, want_per_tuple=True)
+    assert torch.equal(k1, k0)
+    assert torch.allclose(t1, t0, rtol=2e-6, atol=0)
+    assert rel(float(l1), float(l0)) < 2e-6
+    assert float((g1 - g0).abs().max() / g0.abs().max()) < GRAD_TOL
+
+
 def test_wms_autograd_wrapper_and_2d_call(cuda_lib):
     from soft_contrastive_learning_b200 import losses
     emb, dist, _ = synth.wms_batch(T=1, P=12, N=12, D=256, seed=9)
