@@ -210,12 +210,12 @@ def bench_retrieval(args, torch, dist_mod, rank, world, pk):
         torch.cuda.empty_cache()
         t0 = time.perf_counter()
         db = host.to("cuda", non_blocking=True)
-        tree = retrieval.KDTree(db)
+        tree = retrieval.KDTree(db, index_offset=lo)
         torch.cuda.synchronize()
         t_build_h2d = time.perf_counter() - t0
         del host
     else:
-        tree = retrieval.KDTree(db)
+        tree = retrieval.KDTree(db, index_offset=lo)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     if dist_mod is not None:

@@ -30,18 +30,20 @@ namespace scl {
 
 using namespace tc;
 
-constexpr int kSWarps = 8;                                 // consumer warps
-constexpr int kSConsumers = kSWarps * 32;
-constexpr int kSThreads = kSConsumers + 32;                // + one producer warp
 constexpr int kSGrid = 5;                                  // 5 x 5 grid of TS x TS tiles
 constexpr int kSTiles = kSGrid * (kSGrid + 1) / 2;         // 15 symmetric tiles
 constexpr int kSStages = 4;
-constexpr int kSChunk = 256;                               // columns per ring stage
-constexpr int kSPitch = kSChunk + 4;                       // floats; rows 16 bytes apart in bank space
 constexpr int kSRed = 4;                                   // cross-warp reduction buffers (two rounds)
 
-template <int TS>
+// NW consumer warps (+ one producer warp), CH columns per ring stage.  Two configurations are instantiated:
+//   <8, 256>  two CTAs per SM  -- two tuples in flight per SM: 2 x 148 x 410 KB of live descriptors do not fit in L2
+//                                 next to the gradient stream, so ~60 % of the backward's re-read comes from HBM;
+//   <16, 512> one CTA per SM   -- one tuple in flight per SM (60 MB live): the re-read hits L2; 17 warps are
+//                                 allocated as 20, which caps the kernel at 96 registers per thread;
+//   <15, 480> one CTA per SM   -- the same with 16 warps in total: 128 registers per thread.
+template <int TS, int CH>
 struct SSmem {
+  static constexpr int kSPitch = CH + 4;                   // floats; rows 16 bytes apart in bank space
   static constexpr int SG = kSGrid * TS;
   static constexpr int NP = kSTiles * TS * TS;
   static constexpr int HR = (SG + 1) / 2;
@@ -65,21 +67,43 @@ __device__ __forceinline__ void s_ffma2(float2& d, const float2 a, const float2 
       : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
   d = *reinterpret_cast<float2*>(&dd);
 }
-__device__ __forceinline__ void s_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void s_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+// L2 eviction policies: the first read of a tuple should survive until the backward re-reads it (evict_last); the
+// re-read and the gradient stores are dead on arrival (evict_first) and must not push the live tuples out
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void stg_hint(float4* ptr, const float4& v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+               "l"(policy)
                : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSConsumers) : "memory"); }
+template <int N>
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
-template <int TS>
-__global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kernel(
+template <int TS, int NW, int CH>
+__global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW == 8) ? 2 : 1)) wms_stream_kernel(
     const float* __restrict__ emb, const float* __restrict__ dist, int T, int S, int D, scl_ms_params p,
     float* __restrict__ per_tuple, float* __restrict__ demb, uint32_t* __restrict__ kept, float* __restrict__ loss_out,
     unsigned int* __restrict__ done_counter) {
-  using L = SSmem<TS>;
+  using L = SSmem<TS, CH>;
   constexpr int SG = L::SG, NP = L::NP, HR = L::HR, HRP = L::HRP, STAGE = L::STAGE;
+  constexpr int kSWarps = NW, kSConsumers = NW * 32, kSThreads = NW * 32 + 32, kSChunk = CH, kSPitch = CH + 4;
+  constexpr int RPW = (32 + NW - 1) / NW;            // anchor rows per warp in phase B (S <= 32)
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -111,14 +135,16 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
   const int npairs = (nchunks + 1) / 2;
   const bool need_bwd = demb != nullptr;
 
+  // ============================ producer warp ============================
+  // Ring positions run across phases and tuples: per tuple nchunks positions for phase A (chunks ascending) and, with
+  // a backward, nchunks more for phase C (pairs descending, ascending inside a pair).  (Folding this role into a
+  // consumer warp was measured 25 % slower: that warp blocks on the ring's empty barriers and becomes the straggler.)
   if (warp == kSWarps) {
-    // ============================ producer warp ============================
-    uint32_t pos = 0;                                   // ring position, runs across phases and tuples
-    uint32_t iter = 0;
+    const int nseq = nchunks + (need_bwd ? nchunks : 0);
+    const int kdist = nseq > 2 ? 2 : nseq - 1;          // distance block: after the first chunks are in flight
+    const uint64_t pol_keep = policy_evict_last(), pol_drop = policy_evict_first();
+    uint32_t pos = 0, iter = 0;
     for (int t = blockIdx.x; t < T; t += gridDim.x, ++iter) {
-      const float* E_t = emb + size_t(t) * S * D;
-      const int nseq = nchunks + (need_bwd ? nchunks : 0);
-      const int kdist = nseq > 2 ? 2 : nseq - 1;        // after the first chunks are in flight
       for (int k = 0; k < nseq; ++k, ++pos) {
         if (k == kdist) {
           // GPS distances of this tuple (single buffer: free once phase B of the previous tuple has read it);
@@ -129,7 +155,6 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dsm + i)), "l"(dsrc + i) : "memory");
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(dfull)) : "memory");
         }
-        // phase A: chunks ascending; phase C: pairs descending, inside a pair ascending
         int ch;
         if (k < nchunks) {
           ch = k;
@@ -146,7 +171,9 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
         const uint32_t bytes = uint32_t(min(kSChunk, D - c0)) * 4u;
         if (lane == 0) mbar_arrive_expect_tx(&full[stage], bytes * uint32_t(S));
         __syncwarp();
-        if (lane < S) s_bulk_load(ring + size_t(stage) * STAGE + lane * kSPitch, E_t + size_t(lane) * D + c0, bytes, &full[stage]);
+        if (lane < S)
+          s_bulk_load(ring + size_t(stage) * STAGE + lane * kSPitch, emb + (size_t(t) * S + lane) * D + c0, bytes, &full[stage],
+                      (k < nchunks && need_bwd) ? pol_keep : pol_drop);
       }
     }
     return;
@@ -165,6 +192,7 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
   float* Mt = work + L::GW;                        // [SG][2*HRP], 16-byte aligned
   uint32_t pos = 0;
   uint32_t iter = 0;
+  const uint64_t pol_drop = policy_evict_first();
 
   for (int t = blockIdx.x; t < T; t += gridDim.x, ++iter) {
     // ---------------- A. Gram ----------------
@@ -182,26 +210,29 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
       if (dg < 2) {
 #pragma unroll 1
         for (int c4 = dgid; c4 < nq; c4 += 2 * kSWarps) {
-          float4 x[TS], y[TS];
+          // y rows stay in registers for the iteration, x rows are double-buffered one ahead of their use
+          const float* xcol = Es + ta * kSPitch + 4 * c4;
+          const float* ycol = Es + tb * kSPitch + 4 * c4;
+          float4 y[TS];
+#pragma unroll
+          for (int r = 0; r < TS; ++r) y[r] = *reinterpret_cast<const float4*>(ycol + kSGrid * r * kSPitch);
+          float4 xn = *reinterpret_cast<const float4*>(xcol);
 #pragma unroll
           for (int r = 0; r < TS; ++r) {
-            x[r] = *reinterpret_cast<const float4*>(Es + (ta + kSGrid * r) * kSPitch + 4 * c4);
-            y[r] = *reinterpret_cast<const float4*>(Es + (tb + kSGrid * r) * kSPitch + 4 * c4);
+            const float4 x = xn;
+            if (r + 1 < TS) xn = *reinterpret_cast<const float4*>(xcol + kSGrid * (r + 1) * kSPitch);
+#pragma unroll
+            for (int q = 0; q < TS; ++q) s_ffma2(acc[r][q], make_float2(x.x, x.y), make_float2(y[q].x, y[q].y));
+#pragma unroll
+            for (int q = 0; q < TS; ++q) s_ffma2(acc[r][q], make_float2(x.z, x.w), make_float2(y[q].z, y[q].w));
           }
-#pragma unroll
-          for (int r = 0; r < TS; ++r)
-#pragma unroll
-            for (int q = 0; q < TS; ++q) {
-              s_ffma2(acc[r][q], make_float2(x[r].x, x[r].y), make_float2(y[q].x, y[q].y));
-              s_ffma2(acc[r][q], make_float2(x[r].z, x[r].w), make_float2(y[q].z, y[q].w));
-            }
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[stage]);
     }
     // fold even/odd columns, the two column groups of a warp, then the warps (two rounds over kSRed buffers)
-    consumer_sync();                               // nobody still reads Mt of the previous tuple (tiny D)
+    consumer_sync<kSConsumers>();                               // nobody still reads Mt of the previous tuple (tiny D)
     {
       float g[TS][TS];
 #pragma unroll
@@ -211,22 +242,24 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
           const float v = acc[r][q].x + acc[r][q].y;
           g[r][q] = v + __shfl_down_sync(0xffffffffu, v, kSTiles);
         }
-      if (warp >= kSRed && lane < kSTiles) {
+      // groups of kSRed warps take turns, highest warps first: write, then add-and-write, ... (fixed order: deterministic)
+      const int wrev = kSWarps - 1 - warp;
 #pragma unroll
-        for (int r = 0; r < TS; ++r)
+      for (int grp = 0; grp < (kSWarps + kSRed - 1) / kSRed; ++grp) {
+        if (wrev / kSRed == grp && lane < kSTiles) {
+          float* dst = work + (wrev % kSRed) * NP;
 #pragma unroll
-          for (int q = 0; q < TS; ++q) work[(warp - kSRed) * NP + (r * TS + q) * kSTiles + tl] = g[r][q];
+          for (int r = 0; r < TS; ++r)
+#pragma unroll
+            for (int q = 0; q < TS; ++q) {
+              const int a = (r * TS + q) * kSTiles + tl;
+              dst[a] = (grp == 0) ? g[r][q] : dst[a] + g[r][q];
+            }
+        }
+        consumer_sync<kSConsumers>();
       }
-      consumer_sync();
-      if (warp < kSRed && lane < kSTiles) {
-#pragma unroll
-        for (int r = 0; r < TS; ++r)
-#pragma unroll
-          for (int q = 0; q < TS; ++q) work[warp * NP + (r * TS + q) * kSTiles + tl] += g[r][q];
-      }
-      consumer_sync();
       for (int k = tid; k < NP; k += kSConsumers) Pg[k] = (work[k] + work[NP + k]) + (work[2 * NP + k] + work[3 * NP + k]);
-      consumer_sync();
+      consumer_sync<kSConsumers>();
     }
 
     // ---------------- B. weights: warp w owns anchor rows w, w+8, w+16, w+24 (interleaved), lane = column j ----------------
@@ -236,10 +269,10 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
       return Pg[(r * TS + q) * kSTiles + (a * kSGrid - (a * (a - 1)) / 2 + (b - a))];
     };
     mbar_wait(dfull, iter & 1);
-    float wpv[4], wnv[4];
-    bool rvalid[4];
+    float wpv[RPW], wnv[RPW];
+    bool rvalid[RPW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < RPW; ++k) {
       const int i = warp + kSWarps * k;
       rvalid[k] = i < S;
       wpv[k] = 0.0f;
@@ -255,37 +288,37 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
     // tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12))  (losses.py:7); below the clamp it is a pure scale
     const float invn_j = rsqrtf(fmaxf(n2, 1e-12f));
     const float nflag_j = n2 >= 1e-12f ? 1.0f : 0.0f;
-    float invn_i[4], raw[4], sv[4];
+    float invn_i[RPW], raw[RPW], sv[RPW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < RPW; ++k) {
       const int ii = rvalid[k] ? warp + kSWarps * k : 0;
       invn_i[k] = __shfl_sync(0xffffffffu, invn_j, ii);
       raw[k] = (rvalid[k] && jvalid) ? gram(ii, jj) * invn_i[k] * invn_j : 0.0f;
       sv[k] = fmaxf(raw[k], 0.0f);                                           // losses.py:26
     }
-    MsRowStats st[4];
+    MsRowStats st[RPW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < RPW; ++k) {
       st[k].maxv = jvalid ? sv[k] * wnv[k] : -INFINITY;
       st[k].tmp = jvalid ? sv[k] * wpv[k] : -INFINITY;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < RPW; ++k) {
         st[k].maxv = fmaxf(st[k].maxv, __shfl_xor_sync(0xffffffffu, st[k].maxv, o));
         st[k].tmp = fmaxf(st[k].tmp, __shfl_xor_sync(0xffffffffu, st[k].tmp, o));
       }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) st[k].minv = jvalid ? (sv[k] - st[k].tmp) * wpv[k] : INFINITY;
+    for (int k = 0; k < RPW; ++k) st[k].minv = jvalid ? (sv[k] - st[k].tmp) * wpv[k] : INFINITY;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) st[k].minv = fminf(st[k].minv, __shfl_xor_sync(0xffffffffu, st[k].minv, o));
-    bool kp[4], kn[4];
-    float ep[4], en[4], A[4], B[4];
+      for (int k = 0; k < RPW; ++k) st[k].minv = fminf(st[k].minv, __shfl_xor_sync(0xffffffffu, st[k].minv, o));
+    bool kp[RPW], kn[RPW];
+    float ep[RPW], en[RPW], A[RPW], B[RPW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < RPW; ++k) {
       st[k].minv += st[k].tmp;
       kp[k] = kn[k] = false;
       ep[k] = en[k] = 0.0f;
@@ -296,12 +329,12 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < RPW; ++k) {
         A[k] += __shfl_xor_sync(0xffffffffu, A[k], o);
         B[k] += __shfl_xor_sync(0xffffffffu, B[k], o);
       }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < RPW; ++k) {
       const int i = warp + kSWarps * k;
       if (rvalid[k]) {
         if (jvalid) {
@@ -319,13 +352,13 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
         }
       }
     }
-    consumer_sync();
+    consumer_sync<kSConsumers>();
     // M = (1/T) diag(invn) (W - diag(c)) diag(invn), W = Gw + Gw^T, c_i = sum_j W_ij s_ij(raw)  (projection of l2norm),
     // stored transposed and split in two row halves for the backward: Mt[j][h*HRP + r] = M[h*HR + r][j]
     {
-      float wij[4], cpart[4];
+      float wij[RPW], cpart[RPW];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < RPW; ++k) {
         const int i = warp + kSWarps * k;
         wij[k] = (rvalid[k] && jvalid) ? Gw[i * SG + lane] + Gw[lane * SG + i] : 0.0f;
         cpart[k] = wij[k] * raw[k];
@@ -333,9 +366,9 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) cpart[k] += __shfl_xor_sync(0xffffffffu, cpart[k], o);
+        for (int k = 0; k < RPW; ++k) cpart[k] += __shfl_xor_sync(0xffffffffu, cpart[k], o);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < RPW; ++k) {
         const int i = warp + kSWarps * k;
         const float c = cpart[k] * __shfl_sync(0xffffffffu, nflag_j, rvalid[k] ? i : 0);
         if (rvalid[k] && jvalid) {
@@ -352,7 +385,7 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
       if (lane == 0 && per_tuple != nullptr) per_tuple[t] = v;
       tup_finish_loss(done_counter, t, T, v, loss_out, lane);
     }
-    consumer_sync();
+    consumer_sync<kSConsumers>();
 
     // ---------------- C. backward: demb = M * E, chunk pairs in descending order ----------------
     if (need_bwd) {
@@ -364,7 +397,7 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
         const int stA = pos % kSStages, stB = (pos + 1) % kSStages;
         const int nqA = min(kSChunk, D - chA * kSChunk) >> 2;
         const int nqB = hasB ? (min(kSChunk, D - chB * kSChunk) >> 2) : 0;
-        mbar_wait(&full[stA], (pos / kSStages) & 1);
+          mbar_wait(&full[stA], (pos / kSStages) & 1);
         if (hasB) mbar_wait(&full[stB], ((pos + 1) / kSStages) & 1);
         const int nq = nqA + nqB;
         for (int item = tid; item < 2 * nq; item += kSConsumers) {
@@ -397,7 +430,8 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
           for (int r = 0; r < HR; ++r) {
             const int i = h * HR + r;
             if (i < S)
-              stg_stream(reinterpret_cast<float4*>(dcol + size_t(i) * D), make_float4(o[r][0].x, o[r][0].y, o[r][1].x, o[r][1].y));
+              stg_hint(reinterpret_cast<float4*>(dcol + size_t(i) * D), make_float4(o[r][0].x, o[r][0].y, o[r][1].x, o[r][1].y),
+                       pol_drop);
           }
         }
         __syncwarp();
@@ -412,22 +446,40 @@ __global__ void __launch_bounds__(kSThreads, (TS == 5 ? 2 : 1)) wms_stream_kerne
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int TS>
+template <int TS, int NW, int CH>
 static int stream_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p,
                          float* per_tuple, float* demb, uint32_t* kept, float* loss, unsigned int* counter,
                          cudaStream_t stream) {
-  auto kern = wms_stream_kernel<TS>;
+  auto kern = wms_stream_kernel<TS, NW, CH>;
+  constexpr size_t smem = SSmem<TS, CH>::bytes;
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_relaxed)) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SSmem<TS>::bytes)));
+    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     configured.store(1, std::memory_order_relaxed);
   }
-  const int per_sm = TS == 5 ? 2 : 1;
+  const int per_sm = (TS == 5 && NW == 8) ? 2 : 1;
   int grid = num_sms() * per_sm;
   if (grid > T) grid = T;
-  kern<<<grid, kSThreads, SSmem<TS>::bytes, stream>>>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter);
+  kern<<<grid, NW * 32 + 32, smem, stream>>>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter);
   SCL_LAUNCH_CHECK();
   return SCL_OK;
+}
+
+template <int TS>
+static int stream_dispatch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p,
+                           float* per_tuple, float* demb, uint32_t* kept, float* loss, unsigned int* counter,
+                           cudaStream_t stream) {
+  // 1: <16,512>, 2: <8,256> x 2 CTAs/SM (default), 3: <15,480>.  Measured on B200, T = 4096, S = 25, D = 4096:
+  // cfg 2 1.04-1.08 ms (HBM reads 2.5 GB), cfg 3 1.13 ms (1.98 GB), cfg 1 1.30 ms (1.89 GB): one tuple pipeline per SM
+  // keeps the re-read in L2 but leaves the FP32 pipes idle during the scalar phase and the barriers.
+  const char* ce = getenv("SCL_WMS_STREAM_CFG");
+  const int cfg = ce ? atoi(ce) : 2;
+  // the wider register tiles (S > 25) need more registers than 16+ warps leave per thread
+  if constexpr (TS == 5) {
+    if (cfg == 3) return stream_launch<TS, 15, 480>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
+    if (cfg == 1) return stream_launch<TS, 16, 512>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
+  }
+  return stream_launch<TS, 8, 256>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
 }
 
 // SCL_ERR_UNSUPPORTED: small batches go to the cluster kernels (more SMs per tuple).
@@ -438,9 +490,9 @@ int wms_stream_launch(const float* emb, const float* dist, int T, int S, int D, 
   if (mode == 0) return SCL_ERR_UNSUPPORTED;
   if (S < 2 || S > 32 || D < 4 || (D & 3)) return SCL_ERR_UNSUPPORTED;
   if (mode != 1 && T < num_sms()) return SCL_ERR_UNSUPPORTED;
-  if (S <= 25) return stream_launch<5>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
-  if (S <= 30) return stream_launch<6>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
-  return stream_launch<7>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
+  if (S <= 25) return stream_dispatch<5>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
+  if (S <= 30) return stream_dispatch<6>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
+  return stream_dispatch<7>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
 }
 
 }  // namespace scl
