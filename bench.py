@@ -132,7 +132,7 @@ def wms_cpu_port(T=32, S=25, D=D_FULL, reps=3):
             "sample": f"oracle (torch-CPU float64 autograd transcription of losses.py:5-60) fwd+bwd on {T} tuples x {S} x {D}, mean of {reps}"}
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -151,7 +151,7 @@ def run_reference(args):
                 "config": {"workload": "top-25 retrieval, 1Mx4096 fp32 db (BASELINE config 4), bounded CPU sample scaled to 1M rows"},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -334,6 +334,10 @@ def bench_wms(args, torch, pk, T=4096):
 
 
 def main():
+    # libraries (NCCL's version banner) may write to fd 1: keep the real stdout for the ONE JSON line, send the rest to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -349,7 +353,7 @@ def main():
     args.warmup = max(3, args.warmup)
 
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, real_stdout)
         return
 
     import torch
@@ -376,7 +380,7 @@ def main():
                 torch.cuda.empty_cache()
                 line["secondary"] = [bench_wms(args, torch, pk)]
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if dist_mod is not None:
         dist_mod.barrier()
         dist_mod.destroy_process_group()

@@ -149,10 +149,17 @@ int scl_netvlad_bwd(const float* x, const float* assign_w, const float* centers,
 /* P1: PCA-whitening projection.  Replaces train/train.py:646-652
  *   y = matmul(x - m, v, adjoint_b=True) / sqrt(var)           (eval twin: evaluation/top-n.py:74-77)
  *   x [B,Din], v [Dout,Din], m [Din], var [Dout] -> y [B,Dout];  backward: dx = (dy / sqrt(var)) v. */
+int scl_pca_workspace_bytes(int B, int Din, int Dout, size_t* bytes);
 int scl_pca_fwd(const float* x, const float* v, const float* m, const float* var, int B, int Din, int Dout,
-                float* y, scl_stream_t stream);
+                float* y, void* workspace, size_t workspace_bytes, scl_stream_t stream);
 int scl_pca_bwd(const float* dy, const float* v, const float* var, int B, int Din, int Dout,
-                float* dx, scl_stream_t stream);
+                float* dx, void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* Precision of the tensor-core contractions (PCA, flat-mode Gram and its backward): 0 = fp32-grade 3xTF32 (default:
+ * meets the 1e-5 tolerance of the reference's fp32 graph), 1 = one TF32 pass (relative error ~1e-3, three times the
+ * throughput).  Process-wide setting. */
+int scl_set_gemm_precision(int mode);
+int scl_get_gemm_precision(void);
 
 /* ------------------------------------------------------------------------------------------------
  * R1: exact brute-force kNN.  Replaces

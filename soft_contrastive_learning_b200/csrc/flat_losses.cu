@@ -9,6 +9,7 @@
 //   4. dE = M E                                    (sgemm.cuh)
 #include "ms_row.cuh"
 #include "sgemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace scl {
 
@@ -164,8 +165,18 @@ static int flat_run(const float* emb, const float* dist, const int32_t* labels, 
   if (workspace_bytes < flat_ws_bytes(B)) return SCL_ERR_WORKSPACE;
   FlatWs w = flat_carve(workspace, workspace_bytes, B);
 
-  GemmArgs g = gemm_args(emb, emb, w.G, B, B, D, D, D, B, 0, 1);       // G = E E^T
-  rc = gemm_launch(g, stream);
+  // G = E E^T and dE = M E run on the tcgen05 GEMM (fp32-grade 3xTF32 unless scl_set_gemm_precision(1)); shapes
+  // whose row pitch TMA cannot address (B or D not a multiple of 4) use the FP32 FFMA GEMM
+  const bool tc = (B % 4 == 0) && (D % 4 == 0) && aligned16(emb) && (!demb || aligned16(demb)) && !getenv("SCL_GEMM_SIMT");
+  if (tc) {
+    TcGemmDesc d = {};
+    d.A = emb; d.B = emb; d.C = w.G; d.M = B; d.N = B; d.K = D; d.lda = D; d.ldb = D; d.ldc = B;
+    d.a_mn = false; d.b_mn = false; d.colscale = nullptr; d.precision = tc_gemm_precision();
+    rc = tc_gemm(d, stream);
+  } else {
+    GemmArgs g = gemm_args(emb, emb, w.G, B, B, D, D, D, B, 0, 1);       // G = E E^T
+    rc = gemm_launch(g, stream);
+  }
   if (rc) return rc;
   flat_norm_kernel<<<(B + 255) / 256, 256, 0, stream>>>(w.G, B, w.invn, w.nflag);
   SCL_LAUNCH_CHECK();
@@ -180,8 +191,15 @@ static int flat_run(const float* emb, const float* dist, const int32_t* labels, 
   if (demb) {
     flat_m_kernel<<<B, 256, 0, stream>>>(w.G, w.Gw, B, w.invn, w.nflag, w.Mm);
     SCL_LAUNCH_CHECK();
-    GemmArgs h = gemm_args(w.Mm, emb, demb, B, D, B, B, D, D, 0, 0);   // dE = M E
-    rc = gemm_launch(h, stream);
+    if (tc) {
+      TcGemmDesc d = {};
+      d.A = w.Mm; d.B = emb; d.C = demb; d.M = B; d.N = D; d.K = B; d.lda = B; d.ldb = D; d.ldc = D;
+      d.a_mn = false; d.b_mn = true; d.colscale = nullptr; d.precision = tc_gemm_precision();   // E read MN-major
+      rc = tc_gemm(d, stream);
+    } else {
+      GemmArgs h = gemm_args(w.Mm, emb, demb, B, D, B, B, D, D, 0, 0);   // dE = M E
+      rc = gemm_launch(h, stream);
+    }
     if (rc) return rc;
   }
   return SCL_OK;

@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "sgemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace scl {
 
@@ -357,13 +358,66 @@ extern "C" int scl_netvlad_bwd(const float* x, const float* assign_w, const floa
   return SCL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// P1: PCA whitening on the tcgen05 GEMM (tc_gemm.cu).  The centring x - m is done first, in fp32, exactly like the
+// reference graph (train.py:650), so the contraction sees the same operands; 1/sqrt(var) is a column scale of the
+// epilogue (forward) and a pre-scale of dy (backward: dx = (dy / sqrt(var)) V, V read MN-major, no transposed copy).
+__global__ void __launch_bounds__(256) pca_center_kernel(const float* __restrict__ x, const float* __restrict__ m,
+                                                         long long n4, int Din4, float* __restrict__ xc) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = ldg_stream(reinterpret_cast<const float4*>(x) + i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(m) + (i % Din4));
+    reinterpret_cast<float4*>(xc)[i] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+  }
+}
+__global__ void pca_rs_kernel(const float* __restrict__ var, int Dout, float* __restrict__ rs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Dout) rs[i] = 1.0f / sqrtf(var[i]);
+}
+__global__ void __launch_bounds__(256) pca_scale_dy_kernel(const float* __restrict__ dy, const float* __restrict__ var,
+                                                           long long n, int Dout, float* __restrict__ dys) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dys[i] = dy[i] / sqrtf(var[i % Dout]);
+}
+
+static bool pca_tc_ok(const void* a, const void* b, const void* c, int Din, int Dout) {
+  return (Din % 4 == 0) && (Dout % 4 == 0) && aligned16(a) && aligned16(b) && aligned16(c) && !getenv("SCL_GEMM_SIMT");
+}
+
+extern "C" int scl_pca_workspace_bytes(int B, int Din, int Dout, size_t* bytes) {
+  if (!bytes || B < 1 || Din < 1 || Dout < 1) return SCL_ERR_BAD_ARG;
+  const size_t fwd = carve_bytes(size_t(B) * Din, 4) + carve_bytes(size_t(Dout), 4);
+  const size_t bwd = carve_bytes(size_t(B) * Dout, 4);
+  *bytes = fwd > bwd ? fwd : bwd;
+  return SCL_OK;
+}
+
 extern "C" int scl_pca_fwd(const float* x, const float* v, const float* m, const float* var, int B, int Din, int Dout,
-                           float* y, scl_stream_t stream_) {
+                           float* y, void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
   if (!x || !v || !m || !var || !y) return SCL_ERR_BAD_ARG;
   if (B < 1 || Din < 1 || Dout < 1) return SCL_ERR_BAD_SHAPE;
   int rc = check_device();
   if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (pca_tc_ok(x, v, y, Din, Dout) && aligned16(m)) {
+    size_t need = 0;
+    scl_pca_workspace_bytes(B, Din, Dout, &need);
+    if (!workspace || workspace_bytes < need) return SCL_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255u) return SCL_ERR_ALIGN;
+    Carver c(workspace, workspace_bytes);
+    float* xc = c.take<float>(size_t(B) * Din);
+    float* rs = c.take<float>(Dout);
+    const long long n4 = (long long)B * Din / 4;
+    pca_center_kernel<<<unsigned(std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 16)), 256, 0, stream>>>(x, m, n4, Din / 4, xc);
+    SCL_LAUNCH_CHECK();
+    pca_rs_kernel<<<(Dout + 255) / 256, 256, 0, stream>>>(var, Dout, rs);
+    SCL_LAUNCH_CHECK();
+    TcGemmDesc d = {};
+    d.A = xc; d.B = v; d.C = y; d.M = B; d.N = Dout; d.K = Din; d.lda = Din; d.ldb = Din; d.ldc = Dout;
+    d.a_mn = false; d.b_mn = false; d.colscale = rs; d.precision = tc_gemm_precision();
+    return tc_gemm(d, stream);
+  }
+  // shapes the TMA path cannot address (row pitch not a multiple of 16 bytes): FP32 FFMA GEMM
   GemmArgs g = gemm_args(x, v, y, B, Dout, Din, Din, Din, Dout, 0, 1);      // (x - m) V^T, then / sqrt(var)
   g.a_sub_k = m;
   g.col_isqrt = var;
@@ -378,12 +432,27 @@ extern "C" int scl_pca_fwd(const float* x, const float* v, const float* m, const
 }
 
 extern "C" int scl_pca_bwd(const float* dy, const float* v, const float* var, int B, int Din, int Dout, float* dx,
-                           scl_stream_t stream_) {
+                           void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
   if (!dy || !v || !var || !dx) return SCL_ERR_BAD_ARG;
   if (B < 1 || Din < 1 || Dout < 1) return SCL_ERR_BAD_SHAPE;
   int rc = check_device();
   if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (pca_tc_ok(dy, v, dx, Din, Dout)) {
+    size_t need = 0;
+    scl_pca_workspace_bytes(B, Din, Dout, &need);
+    if (!workspace || workspace_bytes < need) return SCL_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) & 255u) return SCL_ERR_ALIGN;
+    float* dys = static_cast<float*>(workspace);
+    const long long n = (long long)B * Dout;
+    pca_scale_dy_kernel<<<unsigned(std::min<long long>((n + 255) / 256, (long long)num_sms() * 16)), 256, 0, stream>>>(dy, var, n, Dout, dys);
+    SCL_LAUNCH_CHECK();
+    TcGemmDesc d = {};
+    d.A = dys; d.B = v; d.C = dx; d.M = B; d.N = Din; d.K = Dout; d.lda = Dout; d.ldb = Din; d.ldc = Din;
+    d.a_mn = false; d.b_mn = true; d.colscale = nullptr; d.precision = tc_gemm_precision();
+    return tc_gemm(d, stream);
+  }
   GemmArgs g = gemm_args(dy, v, dx, B, Din, Dout, Dout, Din, Din, 0, 0);    // (dy / sqrt(var)) V
   g.a_isqrt_k = var;
-  return gemm_launch(g, static_cast<cudaStream_t>(stream_));
+  return gemm_launch(g, stream);
 }

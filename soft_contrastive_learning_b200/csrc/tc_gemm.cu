@@ -1,0 +1,259 @@
+// tc_gemm.cu -- fp32-in / fp32-out GEMM on tcgen05 (kind::tf32), the contraction engine of the PCA projection
+// (train/train.py:646-652), the flat-mode Gram matrix E E^T and its backward M E (model/losses.py:25, :94), and the
+// NetVLAD contractions (model/nets.py:66-67).
+//
+//   C[M,N] = (A . B^T) * colscale[n]        A: M x K, B: N x K, each either K-major ([rows,K] row-major) or
+//                                            MN-major ([K,rows] row-major: the transposed operand, no copy)
+//
+// Precision modes
+//   x1  one kind::tf32 MMA per product: operands are read as fp32 and truncated to tf32 by the tensor core
+//       (10-bit mantissa, relative error ~1e-3 per product; stated tolerance of callers: 2e-3 of the result norm);
+//   x3  fp32-grade "3xTF32": with hi = the tf32 truncation the hardware applies anyway and lo = x - hi (exact in
+//       fp32), D += hi_a hi_b + hi_a lo_b + lo_a hi_b.  The lo tiles are produced on the fly by four "splitter"
+//       warps from the TMA-landed fp32 tile (same swizzled offsets, so no layout math) and never touch HBM; the dropped
+//       lo_a lo_b term and the tf32 truncation of lo are each <= 2^-20 relative.
+//
+// One 128 x BN output tile per CTA (cta_group::1, UMMA 128 x BN x 8), K swept in 32-float (128-byte, SWIZZLE_128B)
+// stages through an mbarrier ring: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
+// (tcgen05.ld 32x32b: one accumulator row per thread), warps 6-9 = splitters (x3 only).
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace scl {
+
+using namespace tc;
+
+constexpr int kGBM = 128, kGBK = 32;                 // tile rows, floats per stage along K (= one 128-byte swizzle row)
+constexpr uint32_t kGABytes = kGBM * kGBK * 4;       // 16 KB
+
+template <int BN, bool kX3>
+struct GCfg {
+  static constexpr uint32_t kBBytes = BN * kGBK * 4;
+  static constexpr uint32_t kHiBytes = kGABytes + kBBytes;
+  static constexpr uint32_t kStageBytes = kX3 ? 2 * kHiBytes : kHiBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kThreads = kX3 ? 320 : 192;
+  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+};
+
+struct GSmemTail {
+  uint64_t full[8], split[8], empty[8], acc_full;
+  uint32_t tmem_base;
+};
+
+// MN-major operand tile, 128-byte swizzle: groups of 32 MN-elements (128 bytes) x 32 k-rows = 4 KB per TMA box;
+//   leading byte offset = distance between MN groups (4096), stride byte offset = distance between 8-k-row atoms (1024)
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(4096 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+
+template <int BN, bool kX3, bool kAMn, bool kBMn>
+__global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcGemmArgs g) {
+  using Cfg = GCfg<BN, kX3>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  GSmemTail* tail = reinterpret_cast<GSmemTail*>(smem + size_t(kStages) * Cfg::kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * kGBM, n0 = blockIdx.x * BN;
+  const int num_k = (g.K + kGBK - 1) / kGBK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&tail->full[s], 1);
+      mbar_init(&tail->split[s], 4);
+      mbar_init(&tail->empty[s], 1);
+    }
+    mbar_init(&tail->acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tail->tmem_base, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kc = 0; kc < num_k; ++kc) {
+        const int stage = kc % kStages;
+        mbar_wait(&tail->empty[stage], ((kc / kStages) & 1) ^ 1);
+        uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
+        uint8_t* sb = sa + kGABytes;
+        mbar_arrive_expect_tx(&tail->full[stage], Cfg::kHiBytes);
+        if (kAMn) {
+#pragma unroll
+          for (int grp = 0; grp < kGBM / 32; ++grp) tma_load_2d(sa + grp * 4096, &tmA, &tail->full[stage], m0 + 32 * grp, kc * kGBK);
+        } else {
+          tma_load_2d(sa, &tmA, &tail->full[stage], kc * kGBK, m0);
+        }
+        if (kBMn) {
+#pragma unroll
+          for (int grp = 0; grp < BN / 32; ++grp) tma_load_2d(sb + grp * 4096, &tmB, &tail->full[stage], n0 + 32 * grp, kc * kGBK);
+        } else {
+          tma_load_2d(sb, &tmB, &tail->full[stage], kc * kGBK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, kGBM, BN) | (kAMn ? (1u << 15) : 0u) | (kBMn ? (1u << 16) : 0u);
+      // K advance of 8 tf32 inside a stage: K-major +32 bytes within the swizzle row, MN-major +1024 bytes (next atom)
+      constexpr uint64_t stepA = kAMn ? (1024 >> 4) : (32 >> 4), stepB = kBMn ? (1024 >> 4) : (32 >> 4);
+      for (int kc = 0; kc < num_k; ++kc) {
+        const int stage = kc % kStages;
+        mbar_wait(kX3 ? &tail->split[stage] : &tail->full[stage], (kc / kStages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + size_t(stage) * Cfg::kStageBytes);
+        const uint32_t sb = sa + kGABytes;
+        const uint64_t da = kAMn ? smem_desc_sw128_mn(sa) : smem_desc_sw128(sa);
+        const uint64_t db = kBMn ? smem_desc_sw128_mn(sb) : smem_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < kGBK / 8; ++k)
+          mma_tf32_ss(tmem_base, da + stepA * k, db + stepB * k, idesc, (kc | k) != 0 ? 1u : 0u);
+        if (kX3) {
+          const uint64_t dal = kAMn ? smem_desc_sw128_mn(sa + Cfg::kHiBytes) : smem_desc_sw128(sa + Cfg::kHiBytes);
+          const uint64_t dbl = kBMn ? smem_desc_sw128_mn(sb + Cfg::kHiBytes) : smem_desc_sw128(sb + Cfg::kHiBytes);
+#pragma unroll
+          for (int k = 0; k < kGBK / 8; ++k) {
+            mma_tf32_ss(tmem_base, da + stepA * k, dbl + stepB * k, idesc, 1u);     // hi_a * lo_b
+            mma_tf32_ss(tmem_base, dal + stepA * k, db + stepB * k, idesc, 1u);     // lo_a * hi_b
+          }
+        }
+        mma_commit(&tail->empty[stage]);              // frees the stage when these MMAs retire
+      }
+      mma_commit(&tail->acc_full);
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int lq = warp & 3;                            // TMEM lane quarter this warp may read
+    const int m = m0 + lq * 32 + lane;
+    mbar_wait(&tail->acc_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr + c * 32, v);
+      tmem_ld_wait();
+      const int nb = n0 + c * 32;
+      if (m < g.M) {
+        float* crow = g.C + size_t(m) * g.ldc;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int n = nb + 4 * j4;
+          if (n + 3 < g.N) {
+            float4 o = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]), __uint_as_float(v[4 * j4 + 2]),
+                                   __uint_as_float(v[4 * j4 + 3]));
+            if (g.colscale) {
+              const float4 s = __ldg(reinterpret_cast<const float4*>(g.colscale + n));
+              o.x *= s.x; o.y *= s.y; o.z *= s.z; o.w *= s.w;
+            }
+            *reinterpret_cast<float4*>(crow + n) = o;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (n + u < g.N) crow[n + u] = __uint_as_float(v[4 * j4 + u]) * (g.colscale ? g.colscale[n + u] : 1.0f);
+          }
+        }
+      }
+    }
+  } else if (kX3) {
+    // ===================== splitters: lo = x - tf32_trunc(x), same swizzled offsets =====================
+    const int st = threadIdx.x - 192;                   // 0..127
+    constexpr int kVec = int(Cfg::kHiBytes / 16);       // float4s in the hi part of a stage
+    for (int kc = 0; kc < num_k; ++kc) {
+      const int stage = kc % kStages;
+      mbar_wait(&tail->full[stage], (kc / kStages) & 1);
+      const float4* hi = reinterpret_cast<const float4*>(smem + size_t(stage) * Cfg::kStageBytes);
+      float4* lo = reinterpret_cast<float4*>(smem + size_t(stage) * Cfg::kStageBytes + Cfg::kHiBytes);
+#pragma unroll 4
+      for (int i = st; i < kVec; i += 128) {
+        const float4 x = hi[i];
+        float4 l;
+        l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+        l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+        l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+        l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        lo[i] = l;
+      }
+      fence_proxy_async();                              // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->split[stage]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool kX3, bool kAMn, bool kBMn>
+static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
+  using Cfg = GCfg<BN, kX3>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major: dims {K, rows}, box {32, tile rows}; MN-major: dims {rows, K}, box {32, 32}
+  if (kAMn) rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.A, uint64_t(d.M), uint64_t(d.K), uint64_t(d.lda) * 4, 32, 32);
+  else rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.A, uint64_t(d.K), uint64_t(d.M), uint64_t(d.lda) * 4, 32, kGBM);
+  if (rc) return rc;
+  if (kBMn) rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.B, uint64_t(d.N), uint64_t(d.K), uint64_t(d.ldb) * 4, 32, 32);
+  else rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.B, uint64_t(d.K), uint64_t(d.N), uint64_t(d.ldb) * 4, 32, BN);
+  if (rc) return rc;
+  auto kern = tc_gemm_kernel<BN, kX3, kAMn, kBMn>;
+  const size_t smem = 1024 + size_t(Cfg::kStages) * Cfg::kStageBytes + sizeof(GSmemTail);
+  static bool configured = false;
+  if (!configured) {
+    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    configured = true;
+  }
+  TcGemmArgs g;
+  g.M = d.M; g.N = d.N; g.K = d.K; g.colscale = d.colscale; g.C = d.C; g.ldc = d.ldc;
+  dim3 grid(unsigned((d.N + BN - 1) / BN), unsigned((d.M + kGBM - 1) / kGBM));
+  kern<<<grid, Cfg::kThreads, smem, stream>>>(tmA, tmB, g);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+template <int BN, bool kX3>
+static int tc_gemm_major(const TcGemmDesc& d, cudaStream_t stream) {
+  if (d.a_mn) {
+    if (d.b_mn) return tc_gemm_launch<BN, kX3, true, true>(d, stream);
+    return tc_gemm_launch<BN, kX3, true, false>(d, stream);
+  }
+  if (d.b_mn) return tc_gemm_launch<BN, kX3, false, true>(d, stream);
+  return tc_gemm_launch<BN, kX3, false, false>(d, stream);
+}
+
+static std::atomic<int> g_gemm_precision{0};
+int tc_gemm_precision() { return g_gemm_precision.load(std::memory_order_relaxed); }
+
+// Shapes: lda/ldb/ldc multiples of 4 floats, pointers 16-byte aligned, N multiple of 4.
+int tc_gemm(const TcGemmDesc& d, cudaStream_t stream) {
+  if (!d.A || !d.B || !d.C || d.M < 1 || d.N < 1 || d.K < 1) return SCL_ERR_BAD_ARG;
+  if ((d.lda & 3) || (d.ldb & 3) || (d.ldc & 3) || !aligned16(d.A) || !aligned16(d.B) || !aligned16(d.C)) return SCL_ERR_ALIGN;
+  const bool x3 = d.precision == 0;
+  // narrow tiles for narrow outputs; otherwise 128 x 128 (x3 keeps hi+lo of both operands per stage)
+  if (d.N <= 64) return x3 ? tc_gemm_major<64, true>(d, stream) : tc_gemm_major<64, false>(d, stream);
+  return x3 ? tc_gemm_major<128, true>(d, stream) : tc_gemm_major<128, false>(d, stream);
+}
+
+}  // namespace scl
+
+// precision of every tensor-core contraction behind the C ABI: 0 = fp32-grade (3xTF32, default), 1 = single TF32 pass
+extern "C" int scl_set_gemm_precision(int mode) {
+  if (mode != 0 && mode != 1) return SCL_ERR_BAD_ARG;
+  scl::g_gemm_precision.store(mode, std::memory_order_relaxed);
+  return SCL_OK;
+}
+extern "C" int scl_get_gemm_precision(void) { return scl::tc_gemm_precision(); }

@@ -68,6 +68,17 @@ def netVLAD(inputs, assignment_kernel, cluster_centers, num_clusters=64):
     return out.cpu().numpy() if isinstance(inputs, np.ndarray) else out
 
 
+def _pca_ws(B, Din, Dout, dev):
+    n = C.c_size_t()
+    check(lib().scl_pca_workspace_bytes(B, Din, Dout, C.byref(n)), "scl_pca_workspace_bytes")
+    return _ws(n.value, dev)
+
+
+def set_gemm_precision(mode):
+    """0: fp32-grade 3xTF32 tensor-core contractions (default); 1: single TF32 pass (stated tolerance 2e-3)."""
+    check(lib().scl_set_gemm_precision(int(mode)), "scl_set_gemm_precision")
+
+
 class _PcaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, v, m, var):
@@ -75,7 +86,9 @@ class _PcaFn(torch.autograd.Function):
         B, Din = x2.shape
         Dout = v2.shape[0]
         y = torch.empty((B, Dout), dtype=torch.float32, device=x2.device)
-        check(lib().scl_pca_fwd(_p(x2), _p(v2), _p(m1), _p(var1), B, Din, Dout, _p(y), _stream()), "scl_pca_fwd")
+        ws = _pca_ws(B, Din, Dout, x2.device)
+        check(lib().scl_pca_fwd(_p(x2), _p(v2), _p(m1), _p(var1), B, Din, Dout, _p(y), _p(ws), ws.numel(), _stream()),
+              "scl_pca_fwd")
         ctx.save_for_backward(v2, var1)
         ctx.dims = (B, Din, Dout)
         return y
@@ -86,7 +99,9 @@ class _PcaFn(torch.autograd.Function):
         B, Din, Dout = ctx.dims
         dy = _f32(dy)
         dx = torch.empty((B, Din), dtype=torch.float32, device=dy.device)
-        check(lib().scl_pca_bwd(_p(dy), _p(v2), _p(var1), B, Din, Dout, _p(dx), _stream()), "scl_pca_bwd")
+        ws = _pca_ws(B, Din, Dout, dy.device)
+        check(lib().scl_pca_bwd(_p(dy), _p(v2), _p(var1), B, Din, Dout, _p(dx), _p(ws), ws.numel(), _stream()),
+              "scl_pca_bwd")
         return dx, None, None, None          # v, m, var are fed placeholders, not trained (train.py:647-649)
 
 

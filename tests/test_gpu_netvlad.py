@@ -58,3 +58,46 @@ def test_pca_forward_backward_and_sklearn(cuda_lib):
     v2, m2, var2 = netvlad.pca_from_sklearn(pca)
     got = netvlad.pca_project(X[:32], v2, m2, var2)
     assert np.allclose(got, pca.transform(X[:32]), rtol=2e-4, atol=2e-4)
+
+
+# ---------------- tcgen05 GEMM behind PCA (tc_gemm.cu) ----------------
+@pytest.mark.parametrize("B,Din,Dout", [(96, 2048, 256),      # full tiles
+                                        (70, 1000, 132),      # ragged: K % 32 != 0, M and N tails
+                                        (256, 4096, 64),      # narrow output tile (BN = 64)
+                                        (3, 36, 8), (130, 520, 260)])
+@pytest.mark.parametrize("precision", [0, 1])
+def test_pca_tensor_core_gemm_shapes(cuda_lib, B, Din, Dout, precision):
+    """fp32-grade 3xTF32 (precision 0) must meet the fp32 tolerance of the reference graph; the single-pass TF32 mode has
+    a stated tolerance of 2e-3 of the result's max magnitude.  Backward reads V MN-major (no transposed copy)."""
+    from soft_contrastive_learning_b200 import netvlad
+    rng = np.random.default_rng(B * 7 + Dout)
+    x = rng.standard_normal((B, Din)).astype(np.float32)
+    V = (rng.standard_normal((Dout, Din)) / np.sqrt(Din)).astype(np.float32)
+    m = (0.1 * rng.standard_normal(Din)).astype(np.float32)
+    var = rng.uniform(0.5, 2.0, Dout).astype(np.float32)
+    dy = rng.standard_normal((B, Dout)).astype(np.float32)
+    netvlad.set_gemm_precision(precision)
+    try:
+        xt = torch.tensor(x, device="cuda", requires_grad=True)
+        y = netvlad.pca_project(xt, torch.tensor(V, device="cuda"), torch.tensor(m, device="cuda"), torch.tensor(var, device="cuda"))
+        (y * torch.tensor(dy, device="cuda")).sum().backward()
+    finally:
+        netvlad.set_gemm_precision(0)
+    yo = ((x.astype(np.float64) - m) @ V.astype(np.float64).T) / np.sqrt(var.astype(np.float64))
+    dxo = (dy.astype(np.float64) / np.sqrt(var.astype(np.float64))) @ V.astype(np.float64)
+    tol = 1e-5 if precision == 0 else 2e-3
+    assert relmax(y.detach().cpu().numpy(), yo) < tol
+    assert relmax(xt.grad.cpu().numpy(), dxo) < tol
+
+
+def test_pca_tensor_core_matches_simt_fallback(cuda_lib, monkeypatch):
+    from soft_contrastive_learning_b200 import netvlad
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((64, 1024)).astype(np.float32)
+    V = (rng.standard_normal((128, 1024)) / 32).astype(np.float32)
+    m = (0.1 * rng.standard_normal(1024)).astype(np.float32)
+    var = rng.uniform(0.5, 2.0, 128).astype(np.float32)
+    a = netvlad.pca_project(x, V, m, var)
+    monkeypatch.setenv("SCL_GEMM_SIMT", "1")
+    b = netvlad.pca_project(x, V, m, var)
+    assert relmax(a, b) < 1e-5
