@@ -160,6 +160,11 @@ int scl_pca_bwd(const float* dy, const float* v, const float* var, int B, int Di
  * throughput).  Process-wide setting. */
 int scl_set_gemm_precision(int mode);
 int scl_get_gemm_precision(void);
+/* The contraction engine itself: C[M,N] = A . B^T (* colscale[n]) on tcgen05 kind::tf32.
+ *   a_mn = 0: A(m,k) = A[m*lda + k];  a_mn = 1: A(m,k) = A[k*lda + m]  (same for B with n);  colscale may be NULL.
+ * Requires lda, ldb, ldc multiples of 4 and 16-byte aligned pointers. */
+int scl_gemm_tf32(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                  int a_mn, int b_mn, const float* colscale, int precision, scl_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * R1: exact brute-force kNN.  Replaces

@@ -387,7 +387,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, size_t elem_bytes, const void* base, uint64_t inner,
-                 uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
+                 uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_atom32) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -405,7 +405,8 @@ int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, size_t elem_bytes,
   cuuint32_t estr[2] = {1, 1};
   (void)elem_bytes;
   CUresult r = fn(out, dtype, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[96];
     snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d", int(r));

@@ -194,7 +194,8 @@ constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2;
 }  // namespace tc
 
 // Host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+// swizzle_atom32 = 0: SWIZZLE_128B; 1: SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands)
 int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, size_t elem_bytes, const void* base, uint64_t inner,
-                 uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer);
+                 uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_atom32 = 0);
 
 }  // namespace scl

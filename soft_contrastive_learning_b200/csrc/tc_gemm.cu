@@ -8,10 +8,10 @@
 // Precision modes
 //   x1  one kind::tf32 MMA per product: operands are read as fp32 and truncated to tf32 by the tensor core
 //       (10-bit mantissa, relative error ~1e-3 per product; stated tolerance of callers: 2e-3 of the result norm);
-//   x3  fp32-grade "3xTF32": with hi = the tf32 truncation the hardware applies anyway and lo = x - hi (exact in
-//       fp32), D += hi_a hi_b + hi_a lo_b + lo_a hi_b.  The lo tiles are produced on the fly by four "splitter"
-//       warps from the TMA-landed fp32 tile (same swizzled offsets, so no layout math) and never touch HBM; the dropped
-//       lo_a lo_b term and the tf32 truncation of lo are each <= 2^-20 relative.
+//   x3  fp32-grade "3xTF32": hi = rn_tf32(x), lo = rn_tf32(x - hi) (x - hi is exact in fp32),
+//       D += hi_a hi_b + hi_a lo_b + lo_a hi_b.  Four "splitter" warps rewrite the TMA-landed fp32 tile in place as hi
+//       and write the lo tile next to it (same swizzled offsets, so no layout math); neither ever touches HBM.  The
+//       dropped lo_a lo_b term and the rounding of lo are each <= 2^-22 relative and unbiased.
 //
 // One 128 x BN output tile per CTA (cta_group::1, UMMA 128 x BN x 8), K swept in 32-float (128-byte, SWIZZLE_128B)
 // stages through an mbarrier ring: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
@@ -33,19 +33,31 @@ struct GCfg {
   static constexpr uint32_t kStageBytes = kX3 ? 2 * kHiBytes : kHiBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kThreads = kX3 ? 320 : 192;
-  static constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr uint32_t kTmemCols = 2 * BN;         // two accumulators: the MMAs fill one while the other is drained
+  // The tensor core adds into its fp32 accumulator with truncation: the error grows linearly with the number of
+  // accumulation steps (measured 2e-8 of the result per step -> 2e-4 at K = 32768).  The accumulator is therefore
+  // flushed into registers (round-to-nearest adds) every kFlush stages: 2 stages = 24 MMA steps in 3xTF32 mode.
+  static constexpr int kFlush = kX3 ? 2 : 32;
 };
 
 struct GSmemTail {
-  uint64_t full[8], split[8], empty[8], acc_full;
+  uint64_t full[8], split[8], empty[8], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
-// MN-major operand tile, 128-byte swizzle: groups of 32 MN-elements (128 bytes) x 32 k-rows = 4 KB per TMA box;
-//   leading byte offset = distance between MN groups (4096), stride byte offset = distance between 8-k-row atoms (1024)
+// MN-major 32-bit operand tile.  tcgen05 accepts exactly one layout for it: 128-byte swizzle with 32-byte atomicity
+// (descriptor layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), atoms of 4 k-rows x 128 bytes.  One TMA box is
+// 32 MN-elements (128 bytes) x 32 k-rows = 4 KB:
+//   leading byte offset = distance between MN groups (next box, 4096), stride byte offset = between 4-k-row atoms (512)
 __device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr) {
-  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(4096 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) |
-         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(4096 >> 4) << 16) | (uint64_t(512 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
+
+__device__ __forceinline__ float tf32_rn(float x) {     // round to nearest tf32 (10-bit mantissa), result as fp32 bits
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
 
 template <int BN, bool kX3, bool kAMn, bool kBMn>
@@ -68,7 +80,10 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
       mbar_init(&tail->split[s], 4);
       mbar_init(&tail->empty[s], 1);
     }
-    mbar_init(&tail->acc_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tail->acc_full[b], 1);
+      mbar_init(&tail->acc_empty[b], 4);              // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tail->tmem_base, Cfg::kTmemCols);
@@ -108,59 +123,76 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
       constexpr uint64_t stepA = kAMn ? (1024 >> 4) : (32 >> 4), stepB = kBMn ? (1024 >> 4) : (32 >> 4);
       for (int kc = 0; kc < num_k; ++kc) {
         const int stage = kc % kStages;
+        const int grp = kc / Cfg::kFlush, buf = grp & 1, in_grp = kc - grp * Cfg::kFlush;
+        if (in_grp == 0) {
+          mbar_wait(&tail->acc_empty[buf], ((grp >> 1) & 1) ^ 1);       // the epilogue drained this accumulator
+          tc_fence_after();
+        }
         mbar_wait(kX3 ? &tail->split[stage] : &tail->full[stage], (kc / kStages) & 1);
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(buf) * BN;
         const uint32_t sa = smem_u32(smem + size_t(stage) * Cfg::kStageBytes);
         const uint32_t sb = sa + kGABytes;
         const uint64_t da = kAMn ? smem_desc_sw128_mn(sa) : smem_desc_sw128(sa);
         const uint64_t db = kBMn ? smem_desc_sw128_mn(sb) : smem_desc_sw128(sb);
 #pragma unroll
         for (int k = 0; k < kGBK / 8; ++k)
-          mma_tf32_ss(tmem_base, da + stepA * k, db + stepB * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          mma_tf32_ss(d_tmem, da + stepA * k, db + stepB * k, idesc, (in_grp | k) != 0 ? 1u : 0u);
         if (kX3) {
           const uint64_t dal = kAMn ? smem_desc_sw128_mn(sa + Cfg::kHiBytes) : smem_desc_sw128(sa + Cfg::kHiBytes);
           const uint64_t dbl = kBMn ? smem_desc_sw128_mn(sb + Cfg::kHiBytes) : smem_desc_sw128(sb + Cfg::kHiBytes);
 #pragma unroll
           for (int k = 0; k < kGBK / 8; ++k) {
-            mma_tf32_ss(tmem_base, da + stepA * k, dbl + stepB * k, idesc, 1u);     // hi_a * lo_b
-            mma_tf32_ss(tmem_base, dal + stepA * k, db + stepB * k, idesc, 1u);     // lo_a * hi_b
+            mma_tf32_ss(d_tmem, da + stepA * k, dbl + stepB * k, idesc, 1u);     // hi_a * lo_b
+            mma_tf32_ss(d_tmem, dal + stepA * k, db + stepB * k, idesc, 1u);     // lo_a * hi_b
           }
         }
         mma_commit(&tail->empty[stage]);              // frees the stage when these MMAs retire
+        if (in_grp == Cfg::kFlush - 1 || kc == num_k - 1) mma_commit(&tail->acc_full[buf]);
       }
-      mma_commit(&tail->acc_full);
     }
   } else if (warp < 6) {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> register accumulators (per flush group) -> global =====================
     const int lq = warp & 3;                            // TMEM lane quarter this warp may read
     const int m = m0 + lq * 32 + lane;
-    mbar_wait(&tail->acc_full, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16);
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
+    const int ngroups = (num_k + Cfg::kFlush - 1) / Cfg::kFlush;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr + c * 32, v);
-      tmem_ld_wait();
-      const int nb = n0 + c * 32;
-      if (m < g.M) {
-        float* crow = g.C + size_t(m) * g.ldc;
+    for (int grp = 0; grp < ngroups; ++grp) {
+      const int buf = grp & 1;
+      mbar_wait(&tail->acc_full[buf], (grp >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16) + uint32_t(buf) * BN;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const int n = nb + 4 * j4;
-          if (n + 3 < g.N) {
-            float4 o = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]), __uint_as_float(v[4 * j4 + 2]),
-                                   __uint_as_float(v[4 * j4 + 3]));
-            if (g.colscale) {
-              const float4 s = __ldg(reinterpret_cast<const float4*>(g.colscale + n));
-              o.x *= s.x; o.y *= s.y; o.z *= s.z; o.w *= s.w;
-            }
-            *reinterpret_cast<float4*>(crow + n) = o;
-          } else {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (n + u < g.N) crow[n + u] = __uint_as_float(v[4 * j4 + u]) * (g.colscale ? g.colscale[n + u] : 1.0f);
+        for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->acc_empty[buf]);
+    }
+    if (m < g.M) {
+      float* crow = g.C + size_t(m) * g.ldc;
+#pragma unroll
+      for (int j4 = 0; j4 < BN / 4; ++j4) {
+        const int n = n0 + 4 * j4;
+        if (n + 3 < g.N) {
+          float4 o = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+          if (g.colscale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(g.colscale + n));
+            o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w;
           }
+          *reinterpret_cast<float4*>(crow + n) = o;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (n + u < g.N) crow[n + u] = acc[4 * j4 + u] * (g.colscale ? g.colscale[n + u] : 1.0f);
         }
       }
     }
@@ -171,16 +203,17 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
     for (int kc = 0; kc < num_k; ++kc) {
       const int stage = kc % kStages;
       mbar_wait(&tail->full[stage], (kc / kStages) & 1);
-      const float4* hi = reinterpret_cast<const float4*>(smem + size_t(stage) * Cfg::kStageBytes);
+      float4* hi = reinterpret_cast<float4*>(smem + size_t(stage) * Cfg::kStageBytes);
       float4* lo = reinterpret_cast<float4*>(smem + size_t(stage) * Cfg::kStageBytes + Cfg::kHiBytes);
 #pragma unroll 4
       for (int i = st; i < kVec; i += 128) {
         const float4 x = hi[i];
-        float4 l;
-        l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-        l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-        l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-        l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        float4 h, l;
+        h.x = tf32_rn(x.x); l.x = tf32_rn(x.x - h.x);
+        h.y = tf32_rn(x.y); l.y = tf32_rn(x.y - h.y);
+        h.z = tf32_rn(x.z); l.z = tf32_rn(x.z - h.z);
+        h.w = tf32_rn(x.w); l.w = tf32_rn(x.w - h.w);
+        hi[i] = h;                                      // tf32-representable: whatever rounding the MMA applies is a no-op
         lo[i] = l;
       }
       fence_proxy_async();                              // generic-proxy writes -> visible to the tensor core
@@ -204,10 +237,10 @@ static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   int rc;
   // K-major: dims {K, rows}, box {32, tile rows}; MN-major: dims {rows, K}, box {32, 32}
-  if (kAMn) rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.A, uint64_t(d.M), uint64_t(d.K), uint64_t(d.lda) * 4, 32, 32);
+  if (kAMn) rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.A, uint64_t(d.M), uint64_t(d.K), uint64_t(d.lda) * 4, 32, 32, 1);
   else rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.A, uint64_t(d.K), uint64_t(d.M), uint64_t(d.lda) * 4, 32, kGBM);
   if (rc) return rc;
-  if (kBMn) rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.B, uint64_t(d.N), uint64_t(d.K), uint64_t(d.ldb) * 4, 32, 32);
+  if (kBMn) rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.B, uint64_t(d.N), uint64_t(d.K), uint64_t(d.ldb) * 4, 32, 32, 1);
   else rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.B, uint64_t(d.K), uint64_t(d.N), uint64_t(d.ldb) * 4, 32, BN);
   if (rc) return rc;
   auto kern = tc_gemm_kernel<BN, kX3, kAMn, kBMn>;
@@ -257,3 +290,15 @@ extern "C" int scl_set_gemm_precision(int mode) {
   return SCL_OK;
 }
 extern "C" int scl_get_gemm_precision(void) { return scl::tc_gemm_precision(); }
+
+// The contraction engine itself (tests, and callers that want it directly):
+//   C[M,N] = A . B^T (* colscale[n]),  a_mn / b_mn select the transposed (MN-major) storage of an operand.
+extern "C" int scl_gemm_tf32(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                             int a_mn, int b_mn, const float* colscale, int precision, scl_stream_t stream) {
+  int rc = scl::check_device();
+  if (rc) return rc;
+  scl::TcGemmDesc d = {};
+  d.A = A; d.B = B; d.C = C; d.M = M; d.N = N; d.K = K; d.lda = lda; d.ldb = ldb; d.ldc = ldc;
+  d.a_mn = a_mn != 0; d.b_mn = b_mn != 0; d.colscale = colscale; d.precision = precision;
+  return scl::tc_gemm(d, static_cast<cudaStream_t>(stream));
+}
