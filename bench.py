@@ -326,11 +326,122 @@ def bench_wms(args, torch, pk, T=4096):
             "dtype": "f32", "config": {"workload": f"wms tuple mode, T={T} S={S} D={D} fp32 (config 1 shape x{T // 32}; inputs 3.4 GB > L2)",
                                        "config1_T32_us_per_launch": ms32 * 1e3, "config1_T32_tuples_per_s": 32 / (ms32 * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                         "peak_source": pk["source"], "kernel": "wms_tuple_kernel<5>",
+                         "peak_source": pk["source"], "kernel": "wms_stream_kernel<5,8,256>",
                          "algorithmic_bytes_per_tuple": 2 * S * D * 4 + S * S * 4, "traffic": None},
             "e2e": {"value": T / (ms_e2e * 1e-3), "unit": "tuples/s", "h2d_bytes_per_step": int(emb.numel() * 4 + dist.numel() * 4),
                     "d2h_bytes_per_step": int(emb.numel() * 4 + 4)},
             "cpu_baseline": cb, "gpu_launches": max(args.steps, 10)}
+
+
+def _time_ms(torch, fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_netvlad_pca(args, torch, pk, B=256, H=30, W=40, Cc=512, K=64, Dout=4096):
+    """BASELINE config 2: NetVLAD head K=64 over 30x40x512 maps + PCA 32768->4096, forward and backward, batch 256."""
+    import ctypes as C
+    from soft_contrastive_learning_b200._lib import check, lib
+    from soft_contrastive_learning_b200.losses import _p, _stream, _ws
+    L = lib()
+    HW, Din = H * W, Cc * K
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.randn((B, HW, Cc), generator=g, device="cuda")
+    aw = 0.05 * torch.randn((Cc, K), generator=g, device="cuda")
+    cc = 0.05 * torch.randn((Cc, K), generator=g, device="cuda")
+    V = torch.randn((Dout, Din), generator=g, device="cuda") / Din ** 0.5
+    m = 0.01 * torch.randn(Din, generator=g, device="cuda")
+    var = 0.5 + 1.5 * torch.rand(Dout, generator=g, device="cuda")
+    n = C.c_size_t()
+    check(L.scl_netvlad_workspace_bytes(B, HW, Cc, K, C.byref(n)), "ws")
+    ws = _ws(n.value, x.device)
+    check(L.scl_pca_workspace_bytes(B, Din, Dout, C.byref(n)), "ws")
+    pws = _ws(n.value, x.device)
+    vlad = torch.empty((B, Din), device="cuda")
+    y = torch.empty((B, Dout), device="cuda")
+    dy = torch.randn((B, Dout), generator=g, device="cuda")
+    dvlad = torch.empty((B, Din), device="cuda")
+    dx, dw, dc = torch.empty_like(x), torch.empty_like(aw), torch.empty_like(cc)
+    st = _stream()
+    f_nv = lambda: check(L.scl_netvlad_fwd(_p(x), _p(aw), _p(cc), B, HW, Cc, K, _p(vlad), _p(ws), ws.numel(), st), "nv fwd")
+    f_pf = lambda: check(L.scl_pca_fwd(_p(vlad), _p(V), _p(m), _p(var), B, Din, Dout, _p(y), _p(pws), pws.numel(), st), "pca fwd")
+    f_pb = lambda: check(L.scl_pca_bwd(_p(dy), _p(V), _p(var), B, Din, Dout, _p(dvlad), _p(pws), pws.numel(), st), "pca bwd")
+    f_nb = lambda: check(L.scl_netvlad_bwd(_p(x), _p(aw), _p(cc), _p(dvlad), B, HW, Cc, K, _p(dx), _p(dw), _p(dc), _p(ws),
+                                           ws.numel(), st), "nv bwd")
+    out = {}
+    for prec, tag in ((0, "fp32-grade 3xTF32"), (1, "single-pass TF32")):
+        check(L.scl_set_gemm_precision(prec), "prec")
+        t = {"netvlad_fwd": _time_ms(torch, f_nv, 5), "pca_fwd": _time_ms(torch, f_pf, 5), "pca_bwd": _time_ms(torch, f_pb, 5),
+             "netvlad_bwd": _time_ms(torch, f_nb, 5)}
+        t["total"] = sum(t.values())
+        out[tag] = t
+    check(L.scl_set_gemm_precision(0), "prec")
+    flops = {"netvlad_fwd": 2 * 2.0 * B * HW * Cc * K, "netvlad_bwd": 4 * 2.0 * B * HW * Cc * K,
+             "pca_fwd": 2.0 * B * Din * Dout, "pca_bwd": 2.0 * B * Din * Dout}
+    t0 = out["fp32-grade 3xTF32"]
+    tot_flops = sum(flops.values())
+    ach = tot_flops / (t0["total"] * 1e-3) / 1e12
+    return {"metric": "NetVLAD head + PCA fwd+bwd images/s", "value": B / (t0["total"] * 1e-3), "unit": "images/s",
+            "ms_per_step": t0["total"], "dtype": "tf32 x3 (fp32-grade) on tcgen05, fp32 accumulate",
+            "config": {"workload": f"BASELINE config 2: B={B}, {H}x{W}x{Cc} conv5 maps, K={K}, PCA {Din}->{Dout}, fwd+bwd",
+                       "ms": out, "inputs": "x 629 MB + V 537 MB fp32 (>> L2)"},
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / pk["tf_sustained"], "peak_source": pk["source"] + " cuBLAS bf16 sustained (no tf32 peak measured; "
+                         "kind::tf32 is nominally half the bf16 rate and the fp32-grade mode issues 3 MMAs per product)",
+                         "algorithmic_flops_per_step": tot_flops, "kernel": "tc_gemm_kernel", "traffic": None},
+            "gpu_launches": 5 * (6 + 12 + 4 + 2)}
+
+
+def bench_losses_cfg3(args, torch, pk, T=32, P=15, N=16, D=D_FULL):
+    """BASELINE config 3: every hot-path loss, forward+backward, on a 1024-descriptor batch (32 tuples x 32, D=4096)."""
+    from soft_contrastive_learning_b200 import losses, synth
+    rng = np.random.default_rng(42)
+    S = 1 + P + N
+    xy = synth.tuple_xy(rng, T, P, N)
+    emb = synth.tuple_descriptors(rng, T, P, N, D)
+    e3 = torch.tensor(emb, device="cuda")
+    e2 = e3.reshape(T * S, D)
+    d3 = torch.tensor(synth.pairwise_euclid(xy).astype(np.float32), device="cuda")
+    xyf = xy.reshape(-1, 2)
+    dflat = torch.tensor(np.sqrt(((xyf[:, None] - xyf[None]) ** 2).sum(-1)).astype(np.float32), device="cuda")
+    sqd = torch.tensor(synth.anchor_sq_dists(xy, P).astype(np.float32), device="cuda")
+    labels = losses.ms_labels(T, P, N)
+    # logratio needs P == N (model/losses.py:125-135): 15 + 15 on the first 31 rows of each tuple
+    e_lr = e3[:, :31].contiguous().reshape(T * 31, D)
+    sp, sn = synth.logratio_sq_dists(xy[:, :31], 15, 15)
+    sp, sn = torch.tensor(sp.astype(np.float32), device="cuda"), torch.tensor(sn.astype(np.float32), device="cuda")
+    p = losses._ms_params(0.8, 15.0)
+    runs = {
+        "triplet": lambda: losses.tuple_loss_value_and_grad("triplet_loss", e2, T, P, N),
+        "lazy_triplet": lambda: losses.tuple_loss_value_and_grad("lazy_triplet_loss", e2, T, P, N),
+        "quadruplet": lambda: losses.tuple_loss_value_and_grad("quadruplet_loss", e2, T, P, N - 1),
+        "lazy_quadruplet": lambda: losses.tuple_loss_value_and_grad("lazy_quadruplet_loss", e2, T, P, N - 1),
+        "huber_distance_triplet": lambda: losses.tuple_loss_value_and_grad("triplet_loss", e2, T, P, N, squared_d_dists=sqd,
+                                                                             distance_loss_name="huber_distance_loss"),
+        "logratio": lambda: losses.logratio_loss_value_and_grad(e_lr, T, 15, 15, sp, sn),
+        "ms_loss (flat, B=1024)": lambda: losses._flat_raw(e2, None, losses._labels_i32(labels, e2.device), losses._ms_params()),
+        "wms (flat, B=1024)": lambda: losses._flat_raw(e2, dflat, None, p),
+        "wms (tuples, T=32 S=32)": lambda: losses._wms_tuple_raw(e3, d3, p),
+    }
+    ms = {k: _time_ms(torch, f, 20, 5) for k, f in runs.items()}
+    total = sum(ms.values())
+    bytes_alg = 2.0 * T * S * D * 4
+    return {"metric": "all hot-path losses fwd+bwd on a 1024-descriptor batch, sweeps/s", "value": 1e3 / total, "unit": "sweeps/s",
+            "ms_per_step": total, "dtype": "f32",
+            "config": {"workload": f"BASELINE config 3: T={T} tuples x S={S} (P={P}, N={N}; quadruplet N={N - 1}+1; logratio 15+15), D={D}",
+                       "ms_per_loss": ms, "note": "33.5 MB in+out per loss: launch-latency bound at this size (4 us at HBM peak)"},
+            "roofline": {"bound": "hbm", "achieved": len(ms) * bytes_alg / (total * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": len(ms) * bytes_alg / (total * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"],
+                         "algorithmic_bytes_per_loss": bytes_alg, "traffic": None},
+            "gpu_launches": 20 * len(ms)}
 
 
 def main():
@@ -343,7 +454,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="retrieval", choices=["retrieval", "wms"])
+    ap.add_argument("--workload", default="retrieval", choices=["retrieval", "wms", "netvlad", "losses"])
     ap.add_argument("--rows", type=int, default=R_FULL)
     ap.add_argument("--queries", type=int, default=Q_STEP)
     ap.add_argument("--no-secondary", action="store_true")
@@ -366,7 +477,11 @@ def main():
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
     pk = peaks()
-    if args.workload == "wms":
+    if args.workload in ("netvlad", "losses"):
+        line = (bench_netvlad_pca if args.workload == "netvlad" else bench_losses_cfg3)(args, torch, pk)
+        line.update({"n_gpus": 1, "steps": 5, "warmup": 3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                     "data": "synthetic"})
+    elif args.workload == "wms":
         line = bench_wms(args, torch, pk)
         line.update({"n_gpus": 1, "steps": max(args.steps, 10), "warmup": max(args.warmup, 3), "higher_is_better": True,
                      "scaling": "weak", "vs_baseline": None, "data": "synthetic"})
@@ -379,6 +494,12 @@ def main():
             if not args.no_secondary:
                 torch.cuda.empty_cache()
                 line["secondary"] = [bench_wms(args, torch, pk)]
+                for fn in (bench_netvlad_pca, bench_losses_cfg3):
+                    torch.cuda.empty_cache()
+                    try:
+                        line["secondary"].append(fn(args, torch, pk))
+                    except Exception as e:          # a secondary line must never cost the headline
+                        line["secondary"].append({"metric": fn.__name__, "error": repr(e)[:300]})
     if rank == 0:
         print(json.dumps(line), file=real_stdout, flush=True)
     if dist_mod is not None:

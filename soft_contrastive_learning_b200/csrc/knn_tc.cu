@@ -416,6 +416,36 @@ int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, size_t elem_bytes,
   return SCL_OK;
 }
 
+int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, uint64_t inner, uint64_t outer,
+                 uint64_t batch, uint64_t row_pitch_bytes, uint64_t batch_pitch_bytes, uint32_t box_inner,
+                 uint32_t box_outer, int swizzle_atom32) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SCL_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !p) {
+      set_last_error("cuTensorMapEncodeTiled entry point", cudaErrorUnknown);
+      return SCL_ERR_CUDA;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  cuuint64_t dims[3] = {inner, outer, batch};
+  cuuint64_t strides[2] = {row_pitch_bytes, batch_pitch_bytes};
+  cuuint32_t box[3] = {box_inner, box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, dtype, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", int(r));
+    set_last_error(msg, cudaErrorInvalidValue);
+    return SCL_ERR_CUDA;
+  }
+  return SCL_OK;
+}
+
 static int tc_variant() {
   // 1 = single-CTA 128x256 tiles, 2 = CTA pairs 256x256 with double-buffered accumulators (default: the epilogue
   // of tile i overlaps the MMAs of tile i+1), 3 = CTA pairs 256x512 (a quarter less L2->SM traffic, no overlap)

@@ -9,8 +9,11 @@
 // The [B,h,w,C,K] residual tensor of the upstream graph is never formed: V = X^T A + Cc * colsum(A).
 // P1 replaces train/train.py:650-651:  y = ((x - m) V^T) / sqrt(var).
 //
-// Contractions run on sgemm.cuh (FP32 FFMA) in this version; the row-normalisation, soft-max, and the two vector
-// norms are fused warp-shuffle kernels.
+// All six contractions (assignment logits, aggregation, and the four of the backward) run on the tcgen05 GEMM of
+// tc_gemm.cu (fp32-grade 3xTF32 by default): x is read K-major for the logits and MN-major -- the same buffer, no
+// transposed copy -- for the aggregation; the l2-normalisation of x is never materialised (row scale in the epilogue,
+// or folded into the soft assignments).  The row-normalisation, soft-max and the two vector norms are fused
+// warp-shuffle kernels.
 #include <algorithm>
 
 #include "sgemm.cuh"
@@ -28,13 +31,14 @@ struct NvWs {
   float* dV;      // [B,C,K]
   float* da;      // [B*HW,K] (backward scratch: da then ds)
   float* dasum;   // [B,K]
+  float* part;    // [B,C,K] per-image partial dW (backward)
 };
 
 static size_t nv_ws_bytes(int B, int HW, int C, int K) {
   size_t n = 0;
   n += carve_bytes(size_t(B) * HW, 4);
   n += 2 * carve_bytes(size_t(B) * HW * K, 4);
-  n += 2 * carve_bytes(size_t(B) * C * K, 4);
+  n += 3 * carve_bytes(size_t(B) * C * K, 4);
   n += 3 * carve_bytes(size_t(B) * K, 4);
   n += carve_bytes(B, 4);
   return n;
@@ -47,6 +51,7 @@ static NvWs nv_carve(void* p, size_t bytes, int B, int HW, int C, int K) {
   w.da = c.take<float>(size_t(B) * HW * K);
   w.V = c.take<float>(size_t(B) * C * K);
   w.dV = c.take<float>(size_t(B) * C * K);
+  w.part = c.take<float>(size_t(B) * C * K);
   w.asum = c.take<float>(size_t(B) * K);
   w.nk = c.take<float>(size_t(B) * K);
   w.dasum = c.take<float>(size_t(B) * K);
@@ -70,8 +75,10 @@ __global__ void __launch_bounds__(256) nv_rownorm_kernel(const float* __restrict
   if (lane == 0) inv[p] = rsqrtf(fmaxf(s, 1e-12f));
 }
 
-// in-place softmax over K = 64 columns; one warp per position (2 values per lane)
-__global__ void __launch_bounds__(256) nv_softmax_kernel(float* __restrict__ a, long long P) {
+// in-place softmax over K = 64 columns; one warp per position (2 values per lane).  a_scaled = a * inv[p] is the
+// operand of the aggregation GEMM (the l2-normalisation of x folded into the assignments).
+__global__ void __launch_bounds__(256) nv_softmax_kernel(float* __restrict__ a, long long P, const float* __restrict__ inv,
+                                                         float* __restrict__ a_scaled) {
   const int lane = threadIdx.x & 31;
   const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= P) return;
@@ -81,8 +88,32 @@ __global__ void __launch_bounds__(256) nv_softmax_kernel(float* __restrict__ a, 
   v0 = expf(v0 - m);
   v1 = expf(v1 - m);
   const float s = warp_sum(v0 + v1);
-  row[lane] = v0 / s;
-  row[lane + 32] = v1 / s;
+  v0 /= s;
+  v1 /= s;
+  row[lane] = v0;
+  row[lane + 32] = v1;
+  const float iv = inv[p];
+  a_scaled[size_t(p) * 64 + lane] = v0 * iv;
+  a_scaled[size_t(p) * 64 + lane + 32] = v1 * iv;
+}
+
+// rows of a [P,64] matrix scaled in place by inv[p]
+__global__ void __launch_bounds__(256) nv_scale_rows_kernel(float* __restrict__ a, long long P, const float* __restrict__ inv) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  const float iv = inv[p];
+  a[size_t(p) * 64 + lane] *= iv;
+  a[size_t(p) * 64 + lane + 32] *= iv;
+}
+
+// out[i] = sum_b part[b][i]   (fixed order: deterministic)
+__global__ void __launch_bounds__(256) nv_sum_batch_kernel(const float* __restrict__ part, int B, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.0f;
+  for (int b = 0; b < B; ++b) acc += part[size_t(b) * n + i];
+  out[i] = acc;
 }
 
 // asum[b,k] = sum_n a[b,n,k].  One CTA (256 threads) per image: 4 row groups x 64 columns.
@@ -278,22 +309,28 @@ extern "C" int scl_netvlad_fwd(const float* x, const float* assign_w, const floa
   const long long P = (long long)B * HW;
   nv_rownorm_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(x, P, C, w.inv);
   SCL_LAUNCH_CHECK();
-  // logits = (X W) * inv[row]
-  GemmArgs g = gemm_args(x, assign_w, w.a, int(P), K, C, C, K, K, 0, 0);
-  g.row_scale = w.inv;
-  rc = gemm_launch(g, stream);
-  if (rc) return rc;
-  nv_softmax_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(w.a, P);
+  const int prec = tc_gemm_precision();
+  // logits = (X W) * inv[row]: X K-major, W [C,K] read MN-major
+  {
+    TcGemmDesc d = {};
+    d.A = x; d.B = assign_w; d.C = w.a; d.M = int(P); d.N = K; d.K = C; d.lda = C; d.ldb = K; d.ldc = K;
+    d.a_mn = false; d.b_mn = true; d.rowscale = w.inv; d.precision = prec;
+    rc = tc_gemm(d, stream);
+    if (rc) return rc;
+  }
+  nv_softmax_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(w.a, P, w.inv, w.da);      // w.da: a * inv (scratch)
   SCL_LAUNCH_CHECK();
   nv_colsum_kernel<<<B, 256, 0, stream>>>(w.a, HW, w.asum);
   SCL_LAUNCH_CHECK();
-  // V[b] = (X[b] * inv)^T A[b]     M = C, N = K, contraction over the HW positions
-  GemmArgs h = gemm_args(x, w.a, w.V, C, K, HW, C, K, K, 1, 0);
-  h.batch = B;
-  h.sA = (long long)HW * C; h.sB = (long long)HW * K; h.sC = (long long)C * K;
-  h.a_mul_k = w.inv; h.a_mul_k_stride = HW;
-  rc = gemm_launch(h, stream);
-  if (rc) return rc;
+  // V[b] = X[b]^T (A[b] * inv)     M = C, N = K, contraction over the HW positions; both operands MN-major
+  {
+    TcGemmDesc d = {};
+    d.A = x; d.B = w.da; d.C = w.V; d.M = C; d.N = K; d.K = HW; d.lda = C; d.ldb = K; d.ldc = K;
+    d.a_mn = true; d.b_mn = true; d.precision = prec;
+    d.batch = B; d.sA = (long long)HW * C; d.sB = (long long)HW * K; d.sC = (long long)C * K;
+    rc = tc_gemm(d, stream);
+    if (rc) return rc;
+  }
   nv_norm_fwd_kernel<<<B, 256, 0, stream>>>(w.V, centers, w.asum, C, w.nk, w.nt, out);
   SCL_LAUNCH_CHECK();
   return SCL_OK;
@@ -319,40 +356,48 @@ extern "C" int scl_netvlad_bwd(const float* x, const float* assign_w, const floa
   }
   nv_dasum_kernel<<<B, 256, 0, stream>>>(w.dV, centers, C, w.dasum);
   SCL_LAUNCH_CHECK();
-  // da[b] = (X[b] dV[b]) * inv[row]      M = HW, N = K, contraction over C
-  GemmArgs g = gemm_args(x, w.dV, w.da, HW, K, C, C, K, K, 0, 0);
-  g.batch = B;
-  g.sA = (long long)HW * C; g.sB = (long long)C * K; g.sC = (long long)HW * K;
-  g.row_scale = w.inv; g.row_scale_stride = HW;
-  rc = gemm_launch(g, stream);
-  if (rc) return rc;
-  nv_softmax_bwd_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(w.a, w.da, w.dasum, P, HW);
-  SCL_LAUNCH_CHECK();
-  if (dassign_w) {
-    // dW = (X * inv)^T dS      M = C, N = K, contraction over all B*HW positions (split-K with atomics)
-    SCL_CUDA_TRY(cudaMemsetAsync(dassign_w, 0, size_t(C) * K * sizeof(float), stream));
-    GemmArgs d = gemm_args(x, w.da, dassign_w, C, K, int(P), C, K, K, 1, 0);
-    d.a_mul_k = w.inv;
-    long long chunks = (P + kGemmBK - 1) / kGemmBK;
-    d.split_k = int(std::min<long long>(chunks, 2ll * num_sms() / ((C + 127) / 128)));
-    if (d.split_k < 1) d.split_k = 1;
-    rc = gemm_launch(d, stream);
+  const int prec = tc_gemm_precision();
+  // da[b] = (X[b] dV[b]) * inv[row]      M = HW, N = K, contraction over C; dV[b] [C,K] read MN-major
+  {
+    TcGemmDesc d = {};
+    d.A = x; d.B = w.dV; d.C = w.da; d.M = HW; d.N = K; d.K = C; d.lda = C; d.ldb = K; d.ldc = K;
+    d.a_mn = false; d.b_mn = true; d.rowscale = w.inv; d.rowscale_stride = HW; d.precision = prec;
+    d.batch = B; d.sA = (long long)HW * C; d.sB = (long long)C * K; d.sC = (long long)HW * K;
+    rc = tc_gemm(d, stream);
     if (rc) return rc;
   }
+  nv_softmax_bwd_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(w.a, w.da, w.dasum, P, HW);
+  SCL_LAUNCH_CHECK();
   if (dx) {
     if (!aligned16(dx)) return SCL_ERR_ALIGN;
     // dxh[b] = A[b] dV[b]^T (aggregation path)   M = HW, N = C, contraction over K
-    GemmArgs e = gemm_args(w.a, w.dV, dx, HW, C, K, K, K, C, 0, 1);
-    e.batch = B;
-    e.sA = (long long)HW * K; e.sB = (long long)C * K; e.sC = (long long)HW * C;
-    rc = gemm_launch(e, stream);
+    TcGemmDesc e = {};
+    e.A = w.a; e.B = w.dV; e.C = dx; e.M = HW; e.N = C; e.K = K; e.lda = K; e.ldb = K; e.ldc = C;
+    e.a_mn = false; e.b_mn = false; e.precision = prec;
+    e.batch = B; e.sA = (long long)HW * K; e.sB = (long long)C * K; e.sC = (long long)HW * C;
+    rc = tc_gemm(e, stream);
     if (rc) return rc;
     // dxh += dS W^T (assignment path)
-    GemmArgs f = gemm_args(w.da, assign_w, dx, int(P), C, K, K, K, C, 0, 1);
-    f.accumulate = 1;
-    rc = gemm_launch(f, stream);
+    TcGemmDesc f = {};
+    f.A = w.da; f.B = assign_w; f.C = dx; f.M = int(P); f.N = C; f.K = K; f.lda = K; f.ldb = K; f.ldc = C;
+    f.a_mn = false; f.b_mn = false; f.accumulate = 1; f.precision = prec;
+    rc = tc_gemm(f, stream);
     if (rc) return rc;
     nv_l2norm_bwd_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(x, w.inv, P, C, dx);
+    SCL_LAUNCH_CHECK();
+  }
+  if (dassign_w) {
+    // dW = X^T (dS * inv): per-image partials [B,C,K] (M = C, N = K, contraction over HW, both operands MN-major),
+    // then a fixed-order sum over the images.  dS is scaled in place: nothing reads it afterwards.
+    nv_scale_rows_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(w.da, P, w.inv);
+    SCL_LAUNCH_CHECK();
+    TcGemmDesc d = {};
+    d.A = x; d.B = w.da; d.C = w.part; d.M = C; d.N = K; d.K = HW; d.lda = C; d.ldb = K; d.ldc = K;
+    d.a_mn = true; d.b_mn = true; d.precision = prec;
+    d.batch = B; d.sA = (long long)HW * C; d.sB = (long long)HW * K; d.sC = (long long)C * K;
+    rc = tc_gemm(d, stream);
+    if (rc) return rc;
+    nv_sum_batch_kernel<<<(C * K + 255) / 256, 256, 0, stream>>>(w.part, B, C * K, dassign_w);
     SCL_LAUNCH_CHECK();
   }
   return SCL_OK;
@@ -415,6 +460,12 @@ extern "C" int scl_pca_fwd(const float* x, const float* v, const float* m, const
     TcGemmDesc d = {};
     d.A = xc; d.B = v; d.C = y; d.M = B; d.N = Dout; d.K = Din; d.lda = Din; d.ldb = Din; d.ldc = Dout;
     d.a_mn = false; d.b_mn = false; d.colscale = rs; d.precision = tc_gemm_precision();
+    // few output tiles and a long K (B = 256: 2 x 32 tiles, K = 32768): two CTAs per tile fill the machine
+    const int tiles = ((B + 127) / 128) * ((Dout + 127) / 128);
+    if (2 * tiles <= num_sms() && Din >= 2048) {
+      d.split_k = 2;
+      SCL_CUDA_TRY(cudaMemsetAsync(y, 0, size_t(B) * Dout * sizeof(float), stream));
+    }
     return tc_gemm(d, stream);
   }
   // shapes the TMA path cannot address (row pitch not a multiple of 16 bytes): FP32 FFMA GEMM

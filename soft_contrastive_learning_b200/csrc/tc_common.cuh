@@ -65,6 +65,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3-D tiled load (innermost coordinate first); used with a batch index as the outermost coordinate
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ------------------------------- tcgen05 -------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -197,5 +206,9 @@ constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2;
 // swizzle_atom32 = 0: SWIZZLE_128B; 1: SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands)
 int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, size_t elem_bytes, const void* base, uint64_t inner,
                  uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_atom32 = 0);
+// rank-3 variant: dims {inner, outer, batch}, strides {row_pitch_bytes, batch_pitch_bytes}, box {box_inner, box_outer, 1}
+int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, uint64_t inner, uint64_t outer,
+                 uint64_t batch, uint64_t row_pitch_bytes, uint64_t batch_pitch_bytes, uint32_t box_inner,
+                 uint32_t box_outer, int swizzle_atom32);
 
 }  // namespace scl

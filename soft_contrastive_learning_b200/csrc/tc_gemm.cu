@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
   GSmemTail* tail = reinterpret_cast<GSmemTail*>(smem + size_t(kStages) * Cfg::kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kGBM, n0 = blockIdx.x * BN;
-  const int num_k = (g.K + kGBK - 1) / kGBK;
+  const int bz = int(blockIdx.z) / g.split_k, ks = int(blockIdx.z) - bz * g.split_k;      // batch index, K slice
+  const int total_k = (g.K + kGBK - 1) / kGBK;
+  const int k_begin = (total_k * ks) / g.split_k, k_end = (total_k * (ks + 1)) / g.split_k;
+  const int num_k = k_end - k_begin;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -103,15 +106,17 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
         mbar_arrive_expect_tx(&tail->full[stage], Cfg::kHiBytes);
         if (kAMn) {
 #pragma unroll
-          for (int grp = 0; grp < kGBM / 32; ++grp) tma_load_2d(sa + grp * 4096, &tmA, &tail->full[stage], m0 + 32 * grp, kc * kGBK);
+          for (int grp = 0; grp < kGBM / 32; ++grp)
+            tma_load_3d(sa + grp * 4096, &tmA, &tail->full[stage], m0 + 32 * grp, (k_begin + kc) * kGBK, bz);
         } else {
-          tma_load_2d(sa, &tmA, &tail->full[stage], kc * kGBK, m0);
+          tma_load_3d(sa, &tmA, &tail->full[stage], (k_begin + kc) * kGBK, m0, bz);
         }
         if (kBMn) {
 #pragma unroll
-          for (int grp = 0; grp < BN / 32; ++grp) tma_load_2d(sb + grp * 4096, &tmB, &tail->full[stage], n0 + 32 * grp, kc * kGBK);
+          for (int grp = 0; grp < BN / 32; ++grp)
+            tma_load_3d(sb + grp * 4096, &tmB, &tail->full[stage], n0 + 32 * grp, (k_begin + kc) * kGBK, g.b_shared ? 0 : bz);
         } else {
-          tma_load_2d(sb, &tmB, &tail->full[stage], kc * kGBK, n0);
+          tma_load_3d(sb, &tmB, &tail->full[stage], (k_begin + kc) * kGBK, n0, g.b_shared ? 0 : bz);
         }
       }
     }
@@ -178,21 +183,34 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
       if (lane == 0) mbar_arrive(&tail->acc_empty[buf]);
     }
     if (m < g.M) {
-      float* crow = g.C + size_t(m) * g.ldc;
+      float* crow = g.C + size_t(bz) * g.sC + size_t(m) * g.ldc;
+      const float rs = g.rowscale ? __ldg(g.rowscale + size_t(bz) * g.rowscale_stride + m) : 1.0f;
 #pragma unroll
       for (int j4 = 0; j4 < BN / 4; ++j4) {
         const int n = n0 + 4 * j4;
         if (n + 3 < g.N) {
-          float4 o = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+          float4 o = make_float4(acc[4 * j4] * rs, acc[4 * j4 + 1] * rs, acc[4 * j4 + 2] * rs, acc[4 * j4 + 3] * rs);
           if (g.colscale) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(g.colscale + n));
             o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w;
           }
-          *reinterpret_cast<float4*>(crow + n) = o;
+          if (g.split_k > 1) {
+            atomicAdd(crow + n, o.x); atomicAdd(crow + n + 1, o.y); atomicAdd(crow + n + 2, o.z); atomicAdd(crow + n + 3, o.w);
+          } else {
+            if (g.accumulate) {
+              const float4 c0 = *reinterpret_cast<const float4*>(crow + n);
+              o.x += c0.x; o.y += c0.y; o.z += c0.z; o.w += c0.w;
+            }
+            *reinterpret_cast<float4*>(crow + n) = o;
+          }
         } else {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (n + u < g.N) crow[n + u] = acc[4 * j4 + u] * (g.colscale ? g.colscale[n + u] : 1.0f);
+            if (n + u < g.N) {
+              const float v = acc[4 * j4 + u] * rs * (g.colscale ? g.colscale[n + u] : 1.0f);
+              if (g.split_k > 1) atomicAdd(crow + n + u, v);
+              else crow[n + u] = g.accumulate ? crow[n + u] + v : v;
+            }
         }
       }
     }
@@ -236,12 +254,16 @@ static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
   using Cfg = GCfg<BN, kX3>;
   CUtensorMap tmA, tmB;
   int rc;
-  // K-major: dims {K, rows}, box {32, tile rows}; MN-major: dims {rows, K}, box {32, 32}
-  if (kAMn) rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.A, uint64_t(d.M), uint64_t(d.K), uint64_t(d.lda) * 4, 32, 32, 1);
-  else rc = make_tmap_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.A, uint64_t(d.K), uint64_t(d.M), uint64_t(d.lda) * 4, 32, kGBM);
+  // K-major: dims {K, rows, batch}, box {32, tile rows, 1}; MN-major: dims {rows, K, batch}, box {32, 32, 1}
+  const uint64_t nb = d.batch > 1 ? uint64_t(d.batch) : 1;
+  const uint64_t pA = (nb > 1 ? uint64_t(d.sA) : uint64_t(d.lda) * (d.a_mn ? d.K : d.M)) * 4;
+  const uint64_t pB = ((nb > 1 && d.sB) ? uint64_t(d.sB) : uint64_t(d.ldb) * (d.b_mn ? d.K : d.N)) * 4;
+  const uint64_t nbB = (nb > 1 && d.sB == 0) ? 1 : nb;      // shared B: every batch reads slice 0
+  if (kAMn) rc = make_tmap_3d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.A, uint64_t(d.M), uint64_t(d.K), nb, uint64_t(d.lda) * 4, pA, 32, 32, 1);
+  else rc = make_tmap_3d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.A, uint64_t(d.K), uint64_t(d.M), nb, uint64_t(d.lda) * 4, pA, 32, kGBM, 0);
   if (rc) return rc;
-  if (kBMn) rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.B, uint64_t(d.N), uint64_t(d.K), uint64_t(d.ldb) * 4, 32, 32, 1);
-  else rc = make_tmap_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d.B, uint64_t(d.K), uint64_t(d.N), uint64_t(d.ldb) * 4, 32, BN);
+  if (kBMn) rc = make_tmap_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.B, uint64_t(d.N), uint64_t(d.K), nbB, uint64_t(d.ldb) * 4, pB, 32, 32, 1);
+  else rc = make_tmap_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.B, uint64_t(d.K), uint64_t(d.N), nbB, uint64_t(d.ldb) * 4, pB, 32, BN, 0);
   if (rc) return rc;
   auto kern = tc_gemm_kernel<BN, kX3, kAMn, kBMn>;
   const size_t smem = 1024 + size_t(Cfg::kStages) * Cfg::kStageBytes + sizeof(GSmemTail);
@@ -252,7 +274,11 @@ static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
   }
   TcGemmArgs g;
   g.M = d.M; g.N = d.N; g.K = d.K; g.colscale = d.colscale; g.C = d.C; g.ldc = d.ldc;
-  dim3 grid(unsigned((d.N + BN - 1) / BN), unsigned((d.M + kGBM - 1) / kGBM));
+  g.sC = d.sC; g.rowscale = d.rowscale; g.rowscale_stride = d.rowscale_stride; g.accumulate = d.accumulate;
+  g.batch = int(nb);
+  g.b_shared = (nb > 1 && d.sB == 0) ? 1 : 0;
+  g.split_k = (d.split_k == 2 && (d.K + kGBK - 1) / kGBK >= 2 && !d.accumulate) ? 2 : 1;
+  dim3 grid(unsigned((d.N + BN - 1) / BN), unsigned((d.M + kGBM - 1) / kGBM), unsigned(g.batch * g.split_k));
   kern<<<grid, Cfg::kThreads, smem, stream>>>(tmA, tmB, g);
   SCL_LAUNCH_CHECK();
   return SCL_OK;

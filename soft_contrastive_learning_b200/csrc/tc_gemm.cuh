@@ -6,7 +6,7 @@
 
 namespace scl {
 
-// C[M,N] = (A . B^T) * colscale[n]
+// C[b][M,N] (+)= (A[b] . B[b]^T) * rowscale[b][m] * colscale[n]      for b < batch
 //   a_mn = false: A(m,k) = A[m*lda + k]   (K-major)      a_mn = true: A(m,k) = A[k*lda + m]   (MN-major)
 //   b_mn = false: B(n,k) = B[n*ldb + k]   (K-major)      b_mn = true: B(n,k) = B[k*ldb + n]   (MN-major)
 //   precision 0: fp32-grade 3xTF32, 1: one TF32 pass
@@ -19,6 +19,14 @@ struct TcGemmDesc {
   bool a_mn, b_mn;
   const float* colscale;   // optional [N]
   int precision;
+  // optional extensions (zero-initialised = off)
+  int batch;               // 0/1: single problem; > 1: blockIdx.z, operands at A + b*sA, B + b*sB, C + b*sC
+  long long sA, sB, sC;    // batch strides in elements (multiples of 4); sB may be 0 (shared B)
+  const float* rowscale;   // optional [batch][M] (+ b*rowscale_stride)
+  long long rowscale_stride;
+  int accumulate;          // C += result
+  int split_k;             // 0/1: off; 2: two CTAs per tile, each half of K, combined with atomicAdd (C zeroed by the caller;
+                           //       two addends commute, so the result stays deterministic)
 };
 
 struct TcGemmArgs {
@@ -26,6 +34,13 @@ struct TcGemmArgs {
   const float* colscale;
   float* C;
   int ldc;
+  long long sC;
+  const float* rowscale;
+  long long rowscale_stride;
+  int accumulate;
+  int batch;               // grid.z = batch * split_k
+  int split_k;
+  int b_shared;            // every batch reads B slice 0
 };
 
 int tc_gemm(const TcGemmDesc& d, cudaStream_t stream);
