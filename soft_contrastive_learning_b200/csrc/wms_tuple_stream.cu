@@ -40,7 +40,8 @@ constexpr int kSRed = 4;                                   // cross-warp reducti
 //                                 next to the gradient stream, so ~60 % of the backward's re-read comes from HBM;
 //   <16, 512> one CTA per SM   -- one tuple in flight per SM (60 MB live): the re-read hits L2; 17 warps are
 //                                 allocated as 20, which caps the kernel at 96 registers per thread;
-//   <15, 480> one CTA per SM   -- the same with 16 warps in total: 128 registers per thread.
+//   <15, 480> one CTA per SM   -- the same with 16 warps in total: 128 registers per thread;
+//   <7, 224>  two CTAs per SM  -- 8 warps in total per CTA: 128 registers per thread instead of 96.
 template <int TS, int CH>
 struct SSmem {
   static constexpr int kSPitch = CH + 4;                   // floats; rows 16 bytes apart in bank space
@@ -96,7 +97,7 @@ template <int N>
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
 template <int TS, int NW, int CH>
-__global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW == 8) ? 2 : 1)) wms_stream_kernel(
+__global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) wms_stream_kernel(
     const float* __restrict__ emb, const float* __restrict__ dist, int T, int S, int D, scl_ms_params p,
     float* __restrict__ per_tuple, float* __restrict__ demb, uint32_t* __restrict__ kept, float* __restrict__ loss_out,
     unsigned int* __restrict__ done_counter) {
@@ -457,7 +458,7 @@ static int stream_launch(const float* emb, const float* dist, int T, int S, int 
     SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     configured.store(1, std::memory_order_relaxed);
   }
-  const int per_sm = (TS == 5 && NW == 8) ? 2 : 1;
+  const int per_sm = (TS == 5 && NW <= 8) ? 2 : 1;
   int grid = num_sms() * per_sm;
   if (grid > T) grid = T;
   kern<<<grid, NW * 32 + 32, smem, stream>>>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter);
@@ -476,6 +477,7 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   const int cfg = ce ? atoi(ce) : 2;
   // the wider register tiles (S > 25) need more registers than 16+ warps leave per thread
   if constexpr (TS == 5) {
+    if (cfg == 4) return stream_launch<TS, 7, 224>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
     if (cfg == 3) return stream_launch<TS, 15, 480>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
     if (cfg == 1) return stream_launch<TS, 16, 512>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   }
