@@ -195,16 +195,27 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
     s_need = 0;
   }
   __syncthreads();
-  // the lists are short once the shared threshold has tightened: sort only what is there (compact, padded to 2^n)
+  // Only candidates at or below the final published threshold can be among the kKeep best of the union (the range that
+  // published it holds kKeep entries at or below it), so the rest is dropped before the sort: typically ~100 keys
+  // survive out of several hundred.  Compact, pad to 2^n, sort.
   const int total = s_off[NR];
-  int n_pow2 = kKeep;
-  while (n_pow2 < total) n_pow2 <<= 1;
-  for (int i = total + threadIdx.x; i < n_pow2; i += blockDim.x) mkeys[i] = ~0ull;
+  const unsigned int pub = q_thr[q];
+  const float t_pub = pub == 0xffffffffu ? INFINITY : key64_score((unsigned long long)pub << 32);
   for (int r = 0; r < NR; ++r) {
-    const int o = s_off[r], c = s_off[r + 1] - o;
+    const int c = s_off[r + 1] - s_off[r];
     const size_t base = (size_t(q) * NR + r) * kCandCap;
-    for (int e = threadIdx.x; e < c; e += blockDim.x) mkeys[o + e] = cand_key64(cand_s[base + e], cand_i[base + e]);
+    for (int e = threadIdx.x; e < c; e += blockDim.x) {
+      const float sc = cand_s[base + e];
+      if (sc <= t_pub) mkeys[atomicAdd(&s_need, 1)] = cand_key64(sc, cand_i[base + e]);
+    }
   }
+  __syncthreads();
+  const int kept = s_need;
+  int n_pow2 = kKeep;
+  while (n_pow2 < kept) n_pow2 <<= 1;
+  for (int i = kept + threadIdx.x; i < n_pow2; i += blockDim.x) mkeys[i] = ~0ull;
+  __syncthreads();
+  if (threadIdx.x == 0) s_need = 0;
   bitonic_sort_smem(mkeys, n_pow2);
   // Everything that is NOT among the selected entries scored >= T:
   //   entries left in the lists score >= the kKeep-th smallest of the union;
@@ -212,11 +223,9 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   // Of the kKeep best, only candidates within 2*eps of the k-th best fp16 score can belong to the exact top-k
   // (a candidate c beyond that has exact_c >= s_c - eps > s_k + eps >= the exact score of each of the k best), so the
   // rest is not rescored and T is lowered to that cutoff.
-  const unsigned int pub = q_thr[q];
-  const float t_pub = pub == 0xffffffffu ? INFINITY : key64_score((unsigned long long)pub << 32);
-  const float t_sel = total >= kKeep ? key64_score(mkeys[kKeep - 1]) : INFINITY;
+  const float t_sel = kept >= kKeep ? key64_score(mkeys[kKeep - 1]) : INFINITY;
   float T = fminf(t_sel, t_pub);
-  int n_sel = total < kKeep ? total : kKeep;
+  int n_sel = kept < kKeep ? kept : kKeep;
   if (total > k && (long long)total < h->R) {
     const double eps = knn_eps(sqrt(qn2[q]), qexp[q], h);
     const double cut = double(key64_score(mkeys[k - 1])) + 2.0 * eps;

@@ -96,6 +96,34 @@ __device__ __forceinline__ void stg_hint(float4* ptr, const float4& v, uint64_t 
 template <int N>
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
+// R rows x 4 columns of dE = M E for one column quad: o[r] += M[r0 + r][j] * E[j][c4*4 .. +3] over the S rows j.
+// An LDS.128 costs four shared-memory wavefronts whether or not its lanes agree on the address, so the broadcast M
+// operands are fetched with exactly ceil(R/4) vector loads (+ scalar loads for the remainder), never for padding.
+template <int R, int PITCH, int MSTRIDE>
+__device__ __forceinline__ void bwd_tile(const float* __restrict__ ecol, const float* __restrict__ mcol, int S,
+                                         float2 (&o)[R][2]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) o[r][0] = o[r][1] = make_float2(0.0f, 0.0f);
+#pragma unroll 5
+  for (int j = 0; j < S; ++j) {
+    const float4 e = *reinterpret_cast<const float4*>(ecol + j * PITCH);
+    const float* mrow = mcol + j * MSTRIDE;
+    float mv[R];
+#pragma unroll
+    for (int r4 = 0; r4 < R / 4; ++r4) {
+      const float4 m = *reinterpret_cast<const float4*>(mrow + 4 * r4);
+      mv[4 * r4] = m.x; mv[4 * r4 + 1] = m.y; mv[4 * r4 + 2] = m.z; mv[4 * r4 + 3] = m.w;
+    }
+#pragma unroll
+    for (int r = (R / 4) * 4; r < R; ++r) mv[r] = mrow[r];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      s_ffma2(o[r][0], make_float2(mv[r], mv[r]), make_float2(e.x, e.y));
+      s_ffma2(o[r][1], make_float2(mv[r], mv[r]), make_float2(e.z, e.w));
+    }
+  }
+}
+
 template <int TS, int NW, int CH>
 __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) wms_stream_kernel(
     const float* __restrict__ emb, const float* __restrict__ dist, int T, int S, int D, scl_ms_params p,
@@ -184,7 +212,9 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
   const int tl = lane % kSTiles;
   const int dg = lane / kSTiles;                   // 0,1 (lanes 30,31 -> 2: idle in the Gram)
   const int ta = c_stile_a[tl], tb = c_stile_b[tl];
-  const int dgid = warp * 2 + dg;                  // 16 column groups per CTA
+  // the warp's two column groups sit kSWarps quads apart (8 quads = 128 bytes: the same banks, so the 5 rows of one
+  // group never collide with a row of the other inside a quarter-warp phase)
+  const int dgid = warp + dg * kSWarps;             // 2 * kSWarps column groups per CTA
   const bool jvalid = lane < S;
   const int jj = jvalid ? lane : 0;
   const float invS = 1.0f / float(S);
@@ -404,35 +434,23 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
         for (int item = tid; item < 2 * nq; item += kSConsumers) {
           const int h = item / nq, c4 = item - h * nq;
           const float* ecol = (c4 < nqA) ? ring + size_t(stA) * STAGE + 4 * c4 : ring + size_t(stB) * STAGE + 4 * (c4 - nqA);
-          const float* mcol = Mt + h * HRP;
-          float2 o[HR][2];
-#pragma unroll
-          for (int r = 0; r < HR; ++r) o[r][0] = o[r][1] = make_float2(0.0f, 0.0f);
-#pragma unroll 5
-          for (int j = 0; j < S; ++j) {
-            const float4 e = *reinterpret_cast<const float4*>(ecol + j * kSPitch);
-            const float4* mrow = reinterpret_cast<const float4*>(mcol + j * (2 * HRP));
-#pragma unroll
-            for (int r4 = 0; r4 < HRP / 4; ++r4) {
-              const float4 m = mrow[r4];
-              const float mv[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int r = r4 * 4 + u;
-                if (r < HR) {
-                  s_ffma2(o[r][0], make_float2(mv[u], mv[u]), make_float2(e.x, e.y));
-                  s_ffma2(o[r][1], make_float2(mv[u], mv[u]), make_float2(e.z, e.w));
-                }
-              }
-            }
-          }
           float* dcol = dE_t + size_t(chA) * kSChunk + 4 * c4;
+          if (h == 0) {
+            float2 o[HR][2];
+            bwd_tile<HR, kSPitch, 2 * HRP>(ecol, Mt, S, o);
 #pragma unroll
-          for (int r = 0; r < HR; ++r) {
-            const int i = h * HR + r;
-            if (i < S)
-              stg_hint(reinterpret_cast<float4*>(dcol + size_t(i) * D), make_float4(o[r][0].x, o[r][0].y, o[r][1].x, o[r][1].y),
-                       pol_drop);
+            for (int r = 0; r < HR; ++r)
+              if (r < S)
+                stg_hint(reinterpret_cast<float4*>(dcol + size_t(r) * D), make_float4(o[r][0].x, o[r][0].y, o[r][1].x, o[r][1].y),
+                         pol_drop);
+          } else {
+            float2 o[SG - HR][2];
+            bwd_tile<SG - HR, kSPitch, 2 * HRP>(ecol, Mt + HRP, S, o);
+#pragma unroll
+            for (int r = 0; r < SG - HR; ++r)
+              if (HR + r < S)
+                stg_hint(reinterpret_cast<float4*>(dcol + size_t(HR + r) * D),
+                         make_float4(o[r][0].x, o[r][0].y, o[r][1].x, o[r][1].y), pol_drop);
           }
         }
         __syncwarp();
