@@ -251,8 +251,11 @@ def bench_retrieval(args, torch, dist_mod, rank, world, pk):
     i_host = torch.empty((Q, k), dtype=torch.int64, pin_memory=True)
 
     def step_e2e():
-        qd = q_host.to("cuda", non_blocking=True)
-        d, i = index.query_device(qd, k)
+        if dist_mod is not None:
+            d, i = index.query_from_host(q_host, k)      # 1/N of the queries per rank over PCIe, all-gather over NVLink
+        else:
+            qd = q_host.to("cuda", non_blocking=True)
+            d, i = index.query_device(qd, k)
         d_host.copy_(d, non_blocking=True)
         i_host.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -277,7 +280,7 @@ def bench_retrieval(args, torch, dist_mod, rank, world, pk):
                      "peak_source": f"{pk['source']} cuBLAS bf16 sustained (kernel runs ~{tc_avg_ms:.0f} ms back to back under the power cap)",
                      "kernel": "knn_tc_kernel", "kernel_ms": tc_avg_ms, "kernel_share_of_step": tc_avg_ms / ms,
                      "algorithmic_flops_per_launch": flops, "traffic": None},
-        "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4,
+        "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4 // world if world > 1 else Q * D * 4,
                 "d2h_bytes_per_step": Q * k * 16, "ms_per_step": ms_e2e},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,

@@ -188,23 +188,27 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   __shared__ int s_off[65];
   __shared__ int s_need;
   const int q = blockIdx.x;
+  __shared__ int s_cnt[64];
+  if (threadIdx.x < NR) s_cnt[threadIdx.x] = cand_cnt[size_t(q) * NR + threadIdx.x];      // NR <= 64, loaded in parallel
+  __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int r = 0; r < NR; ++r) { s_off[r] = acc; acc += cand_cnt[size_t(q) * NR + r]; }
+    for (int r = 0; r < NR; ++r) { s_off[r] = acc; acc += s_cnt[r]; }
     s_off[NR] = acc;
     s_need = 0;
   }
   __syncthreads();
   // Only candidates at or below the final published threshold can be among the kKeep best of the union (the range that
   // published it holds kKeep entries at or below it), so the rest is dropped before the sort: typically ~100 keys
-  // survive out of several hundred.  Compact, pad to 2^n, sort.
+  // survive out of several hundred.  Compact, pad to 2^n, sort.  One warp per range at a time (8 ranges in flight).
   const int total = s_off[NR];
   const unsigned int pub = q_thr[q];
   const float t_pub = pub == 0xffffffffu ? INFINITY : key64_score((unsigned long long)pub << 32);
-  for (int r = 0; r < NR; ++r) {
-    const int c = s_off[r + 1] - s_off[r];
+  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int r = threadIdx.x >> 5; r < NR; r += nwarps) {
+    const int c = s_cnt[r];
     const size_t base = (size_t(q) * NR + r) * kCandCap;
-    for (int e = threadIdx.x; e < c; e += blockDim.x) {
+    for (int e = lane; e < c; e += 32) {
       const float sc = cand_s[base + e];
       if (sc <= t_pub) mkeys[atomicAdd(&s_need, 1)] = cand_key64(sc, cand_i[base + e]);
     }

@@ -114,6 +114,72 @@ __device__ __forceinline__ void prune_row(int L, int lane, float* __restrict__ c
   __syncwarp();
 }
 
+// Cheap prune: instead of ranking all ~128 entries (O(n^2/32) compares), sort a 32-entry sample with a shuffle network,
+// take the sample quantile that should leave ~72 entries as the pivot, count, and compact everything <= pivot.  Any
+// pivot is a VALID threshold (whatever is dropped or later rejected scores >= it, which is all the exactness
+// certificate needs); the count only has to stay comfortably above k, otherwise the exact prune runs instead.
+__device__ __forceinline__ void prune_row_fast(int L, int lane, float* __restrict__ cs, uint32_t* __restrict__ ci,
+                                               size_t base, int& cnt, float& thr, unsigned long long* keys,
+                                               float* thr_slot, unsigned int* q_thr_of_lane) {
+  const int n = __shfl_sync(0xffffffffu, cnt, L);
+  const unsigned long long b64 = static_cast<unsigned long long>(base);
+  const size_t bL = static_cast<size_t>(__shfl_sync(0xffffffffu, b64, L));
+  __syncwarp();
+  float ms[kCandCap / 32];
+  uint32_t mi[kCandCap / 32];
+#pragma unroll
+  for (int u = 0; u < kCandCap / 32; ++u) {
+    const int e = lane + 32 * u;
+    ms[u] = INFINITY;
+    mi[u] = 0;
+    if (e < n) {
+      ms[u] = __ldcg(cs + bL + e);
+      mi[u] = __ldcg(ci + bL + e);
+    }
+  }
+  // bitonic sort of the 32 samples ms[0] (entries 0..31 exist: n > kCandCap - 32 >= 32)
+  float v = ms[0];
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool up = ((lane & k) == 0);
+      const bool lower = ((lane & j) == 0);
+      v = (lower == up) ? fminf(v, o) : fmaxf(v, o);
+    }
+  }
+  int t = (32 * 72 + n / 2) / n;                    // sample rank that leaves ~72 of n
+  t = t < 8 ? 8 : (t > 31 ? 31 : t);
+  const float pivot = __shfl_sync(0xffffffffu, v, t);
+  int c = 0;
+#pragma unroll
+  for (int u = 0; u < kCandCap / 32; ++u) c += __popc(__ballot_sync(0xffffffffu, ms[u] <= pivot));
+  if (c < 48 || c > kCandCap - 40) {                // unlucky sample: exact prune (warp-uniform branch)
+    prune_row(L, lane, cs, ci, base, cnt, thr, keys, thr_slot, q_thr_of_lane);
+    return;
+  }
+  int run = 0;
+#pragma unroll
+  for (int u = 0; u < kCandCap / 32; ++u) {
+    const bool keep = ms[u] <= pivot;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int o = run + __popc(bal & ((1u << lane) - 1u));
+      cs[bL + o] = ms[u];
+      ci[bL + o] = mi[u];
+    }
+    run += __popc(bal);
+  }
+  __syncwarp();
+  if (lane == L) {
+    cnt = c;
+    thr = pivot;
+    atomicMin(q_thr_of_lane, f2ord(pivot));
+  }
+  __syncwarp();
+}
+
 // Work item -> (database range, query unit).  Items are ordered group-major: a group of `group_m` query units runs
 // against every range before the next group starts, so the CTAs that are resident at the same time share a small set
 // of query blocks (kept hot in L2) and each database range is streamed from HBM once per group, by CTAs in lockstep.
@@ -349,7 +415,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
           unsigned need = __ballot_sync(0xffffffffu, cnt > kCandCap - 32);
           while (need) {
             const int L = __ffs(need) - 1;
-            prune_row(L, lane, a.cand_s, a.cand_i, base, cnt, thr, keys, thr_slot, my_thr);
+            prune_row_fast(L, lane, a.cand_s, a.cand_i, base, cnt, thr, keys, thr_slot, my_thr);
             need &= need - 1;
           }
         }
@@ -361,13 +427,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
           else mbar_arrive(&tail->tmem_empty[buf]);
         }
       }
-      // end of the item: bring every list down to <= k' entries and publish its length
-      unsigned need = __ballot_sync(0xffffffffu, cnt > kKeep);
-      while (need) {
-        const int L = __ffs(need) - 1;
-        prune_row(L, lane, a.cand_s, a.cand_i, base, cnt, thr, keys, thr_slot, my_thr);
-        need &= need - 1;
-      }
+      // end of the item: publish the list length (<= kCandCap entries, unsorted; knn_cand_merge_kernel filters them by
+      // the final published threshold and sorts what is left)
       if (valid) a.cand_cnt[size_t(q) * a.NR + range] = cnt;
     }
   }

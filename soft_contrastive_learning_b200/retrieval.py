@@ -117,6 +117,25 @@ class ShardedKDTree:
         dist.all_gather_into_tensor(i_all, i.contiguous(), group=self.group)
         return topk_merge(d_all.view(self.world, Q, kk), i_all.view(self.world, Q, kk))
 
+    def query_from_host(self, q_host, k=1):
+        """Queries that live in (pinned) host memory, identical on every rank: each rank copies only its 1/G slice over
+        PCIe and the slices are all-gathered over NVLink, instead of G full host->device copies competing for the host
+        links.  Returns device tensors like ``query_device``."""
+        import torch.distributed as dist
+        if self.world == 1:
+            return self.local.query_device(q_host.to(self.local.db.device, non_blocking=True), k)
+        rank = dist.get_rank(self.group)
+        Q, D = q_host.shape
+        per = (Q + self.world - 1) // self.world
+        dev = self.local.db.device
+        mine = torch.zeros((per, D), dtype=torch.float32, device=dev)
+        lo, hi = min(Q, rank * per), min(Q, (rank + 1) * per)
+        if hi > lo:
+            mine[:hi - lo].copy_(q_host[lo:hi], non_blocking=True)
+        full = torch.empty((self.world * per, D), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(full, mine, group=self.group)
+        return self.query_device(full[:Q], k)
+
     def query(self, X, k=1, return_distance=True, sort_results=True):
         d, i = self.query_device(X, k)
         if isinstance(X, np.ndarray):
