@@ -279,7 +279,11 @@ def bench_retrieval(args, torch, dist_mod, rank, world, pk):
                      "frac": achieved / pk["tf_sustained"], "frac_of_burst_peak": achieved / pk["tf_burst"],
                      "peak_source": f"{pk['source']} cuBLAS bf16 sustained (kernel runs ~{tc_avg_ms:.0f} ms back to back under the power cap)",
                      "kernel": "knn_tc_kernel", "kernel_ms": tc_avg_ms, "kernel_share_of_step": tc_avg_ms / ms,
-                     "algorithmic_flops_per_launch": flops, "traffic": None},
+                     "algorithmic_flops_per_launch": flops,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the full 1M-row size, from the committed
+                     # `ncu --set full` capture profiles/r1_ncu_knn_tc.txt (35.05 GB + 0.77 GB); tensor-bound kernel, so this
+                     # is context (the fp16 shard is streamed ~4x per launch), not the roofline numerator
+                     "traffic": 35.82e9 if (hi - lo) == R_FULL and Q == Q_STEP else None},
         "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4 // world if world > 1 else Q * D * 4,
                 "d2h_bytes_per_step": Q * k * 16, "ms_per_step": ms_e2e},
         "gpu_launches": launches_per_step * args.steps,
@@ -330,7 +334,10 @@ def bench_wms(args, torch, pk, T=4096):
                                        "config1_T32_us_per_launch": ms32 * 1e3, "config1_T32_tuples_per_s": 32 / (ms32 * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                          "peak_source": pk["source"], "kernel": "wms_stream_kernel<5,8,256>",
-                         "algorithmic_bytes_per_tuple": 2 * S * D * 4 + S * S * 4, "traffic": None},
+                         "algorithmic_bytes_per_tuple": 2 * S * D * 4 + S * S * 4,
+                         # dram read + write of one launch (T=4096) from profiles/r1_ncu_wms.txt: 2.51 + 1.63 GB vs 3.37 GB
+                         # algorithmic -- the backward's second read of the tuple misses L2 about half of the time
+                         "traffic": 4.14e9 if T == 4096 else None},
             "e2e": {"value": T / (ms_e2e * 1e-3), "unit": "tuples/s", "h2d_bytes_per_step": int(emb.numel() * 4 + dist.numel() * 4),
                     "d2h_bytes_per_step": int(emb.numel() * 4 + 4)},
             "cpu_baseline": cb, "gpu_launches": max(args.steps, 10)}

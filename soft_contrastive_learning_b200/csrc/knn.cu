@@ -145,6 +145,7 @@ __device__ __forceinline__ float key64_score(unsigned long long k) {
   return __uint_as_float(u);
 }
 
+
 template <typename K>
 __device__ __forceinline__ void bitonic_sort_smem(K* keys, int n_pow2) {
   for (int size = 2; size <= n_pow2; size <<= 1) {
@@ -179,7 +180,7 @@ __device__ double knn_eps(double qnorm, int eq, const ShadowHeader* h) {
 __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __restrict__ cand_s,
                                                              const uint32_t* __restrict__ cand_i,
                                                              const int* __restrict__ cand_cnt,
-                                                             const unsigned int* __restrict__ q_thr, int NR, int k,
+                                                             const unsigned int* __restrict__ q_thr, int NR, int k, int kMergeCap,
                                                              const double* __restrict__ qn2, const int* __restrict__ qexp,
                                                              const ShadowHeader* __restrict__ h,
                                                              uint32_t* __restrict__ sel_idx, float* __restrict__ sel_T,
@@ -204,17 +205,23 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   const int total = s_off[NR];
   const unsigned int pub = q_thr[q];
   const float t_pub = pub == 0xffffffffu ? INFINITY : key64_score((unsigned long long)pub << 32);
-  const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int r = threadIdx.x >> 5; r < NR; r += nwarps) {
-    const int c = s_cnt[r];
-    const size_t base = (size_t(q) * NR + r) * kCandCap;
-    for (int e = lane; e < c; e += 32) {
+  // flat loop over every (range, slot): independent loads, one round trip to memory instead of one per range
+  for (int slot = threadIdx.x; slot < NR * kCandCap; slot += blockDim.x) {
+    const int r = slot / kCandCap, e = slot - r * kCandCap;
+    if (e < s_cnt[r]) {
+      const size_t base = (size_t(q) * NR + r) * kCandCap;
       const float sc = cand_s[base + e];
-      if (sc <= t_pub) mkeys[atomicAdd(&s_need, 1)] = cand_key64(sc, cand_i[base + e]);
+      if (sc <= t_pub) {
+        const int o = atomicAdd(&s_need, 1);
+        if (o < kMergeCap) mkeys[o] = cand_key64(sc, cand_i[base + e]);
+      }
     }
   }
   __syncthreads();
-  const int kept = s_need;
+  // kMergeCap = NR * kCandCap rounded up to a power of two: every candidate fits; the overflow branch (query handed
+  // to the exact path through an unsatisfiable bound) is a guard, not a code path
+  const bool overflow = s_need > kMergeCap;
+  const int kept = overflow ? kMergeCap : s_need;
   int n_pow2 = kKeep;
   while (n_pow2 < kept) n_pow2 <<= 1;
   for (int i = kept + threadIdx.x; i < n_pow2; i += blockDim.x) mkeys[i] = ~0ull;
@@ -243,8 +250,8 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   if (threadIdx.x < kKeep)
     sel_idx[size_t(q) * kKeep + threadIdx.x] = (threadIdx.x < n_sel) ? uint32_t(mkeys[threadIdx.x] & 0xffffffffu) : 0xffffffffu;
   if (threadIdx.x == 0) {
-    sel_n[q] = total;
-    sel_T[q] = T;
+    sel_n[q] = overflow ? 0x7fffffff : total;
+    sel_T[q] = overflow ? -INFINITY : T;
   }
 }
 
@@ -786,15 +793,15 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
   if (rc) return rc;
   if (timing) SCL_CUDA_TRY(cudaEventRecord(ev1, stream));
 
-  int n_pow2 = 1;
-  while (n_pow2 < a.NR * kCandCap) n_pow2 <<= 1;          // worst case: every list full
-  const size_t merge_smem = size_t(n_pow2) * sizeof(unsigned long long);
+  int merge_cap = kKeep;
+  while (merge_cap < a.NR * kCandCap) merge_cap <<= 1;
+  const size_t merge_smem = size_t(merge_cap) * sizeof(unsigned long long);
   static size_t merge_cfg = 0;
   if (merge_smem > 48 * 1024 && merge_cfg < merge_smem) {
     SCL_CUDA_TRY(cudaFuncSetAttribute(knn_cand_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(merge_smem)));
     merge_cfg = merge_smem;
   }
-  knn_cand_merge_kernel<<<Q, 256, merge_smem, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, w.q_thr, a.NR, k, w.qn2, w.qexp, h,
+  knn_cand_merge_kernel<<<Q, 256, merge_smem, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, w.q_thr, a.NR, k, merge_cap, w.qn2, w.qexp, h,
                                                         w.sel_idx, w.sel_T, w.sel_n);
   SCL_LAUNCH_CHECK();
   const long long pairs = (long long)Q * kKeep;

@@ -124,7 +124,7 @@ __device__ __forceinline__ void bwd_tile(const float* __restrict__ ecol, const f
   }
 }
 
-template <int TS, int NW, int CH>
+template <int TS, int NW, int CH, bool kPackedGram = true>
 __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) wms_stream_kernel(
     const float* __restrict__ emb, const float* __restrict__ dist, int T, int S, int D, scl_ms_params p,
     float* __restrict__ per_tuple, float* __restrict__ demb, uint32_t* __restrict__ kept, float* __restrict__ loss_out,
@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
 
   for (int t = blockIdx.x; t < T; t += gridDim.x, ++iter) {
     // ---------------- A. Gram ----------------
+    // packed: even/odd-column partial sums in one register pair (FFMA2); scalar: one accumulator per pair (FFMA), half
+    // the accumulator registers, which lets the compiler keep the operand loads further ahead of their use
     float2 acc[TS][TS];
 #pragma unroll
     for (int r = 0; r < TS; ++r)
@@ -252,10 +254,21 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
           for (int r = 0; r < TS; ++r) {
             const float4 x = xn;
             if (r + 1 < TS) xn = *reinterpret_cast<const float4*>(xcol + kSGrid * (r + 1) * kSPitch);
+            if (kPackedGram) {
 #pragma unroll
-            for (int q = 0; q < TS; ++q) s_ffma2(acc[r][q], make_float2(x.x, x.y), make_float2(y[q].x, y[q].y));
+              for (int q = 0; q < TS; ++q) s_ffma2(acc[r][q], make_float2(x.x, x.y), make_float2(y[q].x, y[q].y));
 #pragma unroll
-            for (int q = 0; q < TS; ++q) s_ffma2(acc[r][q], make_float2(x.z, x.w), make_float2(y[q].z, y[q].w));
+              for (int q = 0; q < TS; ++q) s_ffma2(acc[r][q], make_float2(x.z, x.w), make_float2(y[q].z, y[q].w));
+            } else {
+#pragma unroll
+              for (int q = 0; q < TS; ++q) acc[r][q].x = fmaf(x.x, y[q].x, acc[r][q].x);
+#pragma unroll
+              for (int q = 0; q < TS; ++q) acc[r][q].x = fmaf(x.y, y[q].y, acc[r][q].x);
+#pragma unroll
+              for (int q = 0; q < TS; ++q) acc[r][q].x = fmaf(x.z, y[q].z, acc[r][q].x);
+#pragma unroll
+              for (int q = 0; q < TS; ++q) acc[r][q].x = fmaf(x.w, y[q].w, acc[r][q].x);
+            }
           }
         }
       }
@@ -465,11 +478,11 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int TS, int NW, int CH>
+template <int TS, int NW, int CH, bool kPackedGram = true>
 static int stream_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p,
                          float* per_tuple, float* demb, uint32_t* kept, float* loss, unsigned int* counter,
                          cudaStream_t stream) {
-  auto kern = wms_stream_kernel<TS, NW, CH>;
+  auto kern = wms_stream_kernel<TS, NW, CH, kPackedGram>;
   constexpr size_t smem = SSmem<TS, CH>::bytes;
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_relaxed)) {
@@ -495,6 +508,7 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   const int cfg = ce ? atoi(ce) : 2;
   // the wider register tiles (S > 25) need more registers than 16+ warps leave per thread
   if constexpr (TS == 5) {
+    if (cfg == 5) return stream_launch<TS, 8, 256, false>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
     if (cfg == 4) return stream_launch<TS, 7, 224>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
     if (cfg == 3) return stream_launch<TS, 15, 480>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
     if (cfg == 1) return stream_launch<TS, 16, 512>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
