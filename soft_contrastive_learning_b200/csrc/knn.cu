@@ -177,56 +177,112 @@ __device__ double knn_eps(double qnorm, int eq, const ShadowHeader* h) {
   return 2.0 * e_dot + ldexp(1.0, -23) * (rmax * rmax + smax);                    // + norm and fma rounding
 }
 
+// One CTA per query.  Three dependent trips to memory in total (counts, scores, indices of the selected): every thread
+// first pulls its <= 32 list slots into registers with independent loads.  Only candidates at or below the final
+// published threshold can be among the kKeep best of the union (the range that published it holds kKeep entries at or
+// below it); of those survivors (a few hundred to a few thousand) the kKeep smallest are found with a block-wide
+// 4 x 8-bit radix select over the register-resident scores -- no shared-memory copy of the lists, no large sort --
+// and only that small set (plus score ties at the boundary) is fetched, sorted by (score, index) and cut at kKeep.
+constexpr int kMergeCap = 256;                       // selected keys: kKeep + boundary ties; more ties => exact path (guard)
+constexpr int kMergeSlots = 64 * kCandCap / 256;     // list slots per thread at the maximum of 64 ranges
+__device__ __forceinline__ uint32_t score_key32(float s) {
+  uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __restrict__ cand_s,
                                                              const uint32_t* __restrict__ cand_i,
                                                              const int* __restrict__ cand_cnt,
-                                                             const unsigned int* __restrict__ q_thr, int NR, int k, int kMergeCap,
+                                                             const unsigned int* __restrict__ q_thr, int NR, int k,
                                                              const double* __restrict__ qn2, const int* __restrict__ qexp,
                                                              const ShadowHeader* __restrict__ h,
                                                              uint32_t* __restrict__ sel_idx, float* __restrict__ sel_T,
                                                              int* __restrict__ sel_n) {
-  extern __shared__ unsigned long long mkeys[];
-  __shared__ int s_off[65];
-  __shared__ int s_need;
-  const int q = blockIdx.x;
+  __shared__ unsigned long long mkeys[kMergeCap];
   __shared__ int s_cnt[64];
-  if (threadIdx.x < NR) s_cnt[threadIdx.x] = cand_cnt[size_t(q) * NR + threadIdx.x];      // NR <= 64, loaded in parallel
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int r = 0; r < NR; ++r) { s_off[r] = acc; acc += s_cnt[r]; }
-    s_off[NR] = acc;
-    s_need = 0;
-  }
-  __syncthreads();
-  // Only candidates at or below the final published threshold can be among the kKeep best of the union (the range that
-  // published it holds kKeep entries at or below it), so the rest is dropped before the sort: typically ~100 keys
-  // survive out of several hundred.  Compact, pad to 2^n, sort.  One warp per range at a time (8 ranges in flight).
-  const int total = s_off[NR];
+  __shared__ int s_hist[256];
+  __shared__ int s_need, s_total, s_surv, s_rank;
+  __shared__ uint32_t s_prefix;
+  __shared__ double s_cut;
+  const int q = blockIdx.x;
+  if (threadIdx.x < 64) s_cnt[threadIdx.x] = threadIdx.x < NR ? cand_cnt[size_t(q) * NR + threadIdx.x] : 0;   // NR <= 64
   const unsigned int pub = q_thr[q];
-  const float t_pub = pub == 0xffffffffu ? INFINITY : key64_score((unsigned long long)pub << 32);
-  // flat loop over every (range, slot): independent loads, one round trip to memory instead of one per range
-  for (int slot = threadIdx.x; slot < NR * kCandCap; slot += blockDim.x) {
-    const int r = slot / kCandCap, e = slot - r * kCandCap;
-    if (e < s_cnt[r]) {
-      const size_t base = (size_t(q) * NR + r) * kCandCap;
-      const float sc = cand_s[base + e];
-      if (sc <= t_pub) {
-        const int o = atomicAdd(&s_need, 1);
-        if (o < kMergeCap) mkeys[o] = cand_key64(sc, cand_i[base + e]);
-      }
-    }
+  if (threadIdx.x == 0) { s_need = 0; s_surv = 0; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int t = __reduce_add_sync(0xffffffffu, s_cnt[threadIdx.x] + s_cnt[threadIdx.x + 32]);
+    if (threadIdx.x == 0) s_total = t;
   }
+  const float t_pub = pub == 0xffffffffu ? INFINITY : key64_score((unsigned long long)pub << 32);
+  const float* qs = cand_s + size_t(q) * NR * kCandCap;
+  const uint32_t* qi = cand_i + size_t(q) * NR * kCandCap;
+  uint32_t ku[kMergeSlots];                           // monotone keys of this thread's slots
+  uint32_t live = 0;                                  // bit it: slot holds a survivor
+#pragma unroll
+  for (int it = 0; it < kMergeSlots; ++it) {
+    const int slot = it * 256 + threadIdx.x, r = slot / kCandCap, e = slot % kCandCap;
+    const float sc = (r < NR && e < s_cnt[r]) ? qs[slot] : NAN;          // NaN: never <= anything
+    ku[it] = score_key32(sc);
+    live |= (sc <= t_pub) ? (1u << it) : 0u;
+  }
+  if (live) atomicAdd(&s_surv, __popc(live));
   __syncthreads();
-  // kMergeCap = NR * kCandCap rounded up to a power of two: every candidate fits; the overflow branch (query handed
-  // to the exact path through an unsatisfiable bound) is a guard, not a code path
-  const bool overflow = s_need > kMergeCap;
-  const int kept = overflow ? kMergeCap : s_need;
+  const int kept = s_surv;                            // survivors of the threshold
+  // radix select of the kKeep-th smallest key (only when there is something to cut)
+  uint32_t tau = 0xffffffffu;                         // keys < tau are selected outright, keys == tau are boundary ties
+  if (kept > kMergeCap) {
+    if (threadIdx.x == 0) { s_rank = kKeep; s_prefix = 0; }
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      s_hist[threadIdx.x] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+#pragma unroll
+      for (int it = 0; it < kMergeSlots; ++it)
+        if (((live >> it) & 1u) && (shift == 24 || (ku[it] >> (shift + 8)) == prefix))
+          atomicAdd(&s_hist[(ku[it] >> shift) & 255u], 1);
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        // bins 8*lane .. 8*lane+7 per lane, exclusive scan across lanes, then locate the bin holding rank s_rank
+        int c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = s_hist[8 * threadIdx.x + j]; sum += c[j]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (int(threadIdx.x) >= o) incl += v;
+        }
+        int before = incl - sum;
+        const int rank = s_rank;
+        if (before < rank && rank <= incl) {          // exactly one lane
+          int j = 0;
+          while (before + c[j] < rank) { before += c[j]; ++j; }
+          s_rank = rank - before;
+          s_prefix = (prefix << 8) | uint32_t(8 * threadIdx.x + j);
+        }
+      }
+      __syncthreads();
+    }
+    tau = s_prefix;
+  }
+  // gather the selected keys (everything when the survivors fit)
+  int mine = 0;
+#pragma unroll
+  for (int it = 0; it < kMergeSlots; ++it) mine += (((live >> it) & 1u) && ku[it] <= tau) ? 1 : 0;
+  int o = mine ? atomicAdd(&s_need, mine) : 0;
+#pragma unroll
+  for (int it = 0; it < kMergeSlots; ++it)
+    if (((live >> it) & 1u) && ku[it] <= tau) {
+      if (o < kMergeCap) mkeys[o] = (static_cast<unsigned long long>(ku[it]) << 32) | qi[it * 256 + threadIdx.x];
+      ++o;
+    }
+  __syncthreads();
+  const int total = s_total;
+  const bool overflow = s_need > kMergeCap;          // too many score ties at the boundary: handed to the exact path
+  const int gathered = overflow ? kMergeCap : s_need;
   int n_pow2 = kKeep;
-  while (n_pow2 < kept) n_pow2 <<= 1;
-  for (int i = kept + threadIdx.x; i < n_pow2; i += blockDim.x) mkeys[i] = ~0ull;
-  __syncthreads();
-  if (threadIdx.x == 0) s_need = 0;
+  while (n_pow2 < gathered) n_pow2 <<= 1;
+  for (int i = gathered + threadIdx.x; i < n_pow2; i += blockDim.x) mkeys[i] = ~0ull;
   bitonic_sort_smem(mkeys, n_pow2);
   // Everything that is NOT among the selected entries scored >= T:
   //   entries left in the lists score >= the kKeep-th smallest of the union;
@@ -238,8 +294,12 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   float T = fminf(t_sel, t_pub);
   int n_sel = kept < kKeep ? kept : kKeep;
   if (total > k && (long long)total < h->R) {
-    const double eps = knn_eps(sqrt(qn2[q]), qexp[q], h);
-    const double cut = double(key64_score(mkeys[k - 1])) + 2.0 * eps;
+    if (threadIdx.x == 0) {                            // float64 evaluation of the bound: one thread, not 256
+      s_need = 0;
+      s_cut = double(key64_score(mkeys[k - 1])) + 2.0 * knn_eps(sqrt(qn2[q]), qexp[q], h);
+    }
+    __syncthreads();
+    const double cut = s_cut;
     if (threadIdx.x < n_sel && double(key64_score(mkeys[threadIdx.x])) <= cut) atomicAdd(&s_need, 1);
     __syncthreads();
     if (s_need < n_sel) {
@@ -793,16 +853,8 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
   if (rc) return rc;
   if (timing) SCL_CUDA_TRY(cudaEventRecord(ev1, stream));
 
-  int merge_cap = kKeep;
-  while (merge_cap < a.NR * kCandCap) merge_cap <<= 1;
-  const size_t merge_smem = size_t(merge_cap) * sizeof(unsigned long long);
-  static size_t merge_cfg = 0;
-  if (merge_smem > 48 * 1024 && merge_cfg < merge_smem) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(knn_cand_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(merge_smem)));
-    merge_cfg = merge_smem;
-  }
-  knn_cand_merge_kernel<<<Q, 256, merge_smem, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, w.q_thr, a.NR, k, merge_cap, w.qn2, w.qexp, h,
-                                                        w.sel_idx, w.sel_T, w.sel_n);
+  knn_cand_merge_kernel<<<Q, 256, 0, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, w.q_thr, a.NR, k, w.qn2, w.qexp, h, w.sel_idx,
+                                               w.sel_T, w.sel_n);
   SCL_LAUNCH_CHECK();
   const long long pairs = (long long)Q * kKeep;
   knn_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, stream>>>(db, queries, D, w.sel_idx, pairs, w.d2);

@@ -128,6 +128,29 @@ __device__ __forceinline__ void tup_finish_loss(unsigned int* ws, int t, int T, 
   }
 }
 
+// The same for persistent CTAs that own many tuples: the per-tuple call only deposits the value (a plain store -- no
+// fence, no atomic round trip on the tuple's critical path); after its last tuple the CTA's depositing warp publishes
+// all of them with ONE fence + atomic and the last CTA to arrive reduces in the same fixed order.
+__device__ __forceinline__ void tup_deposit_loss(unsigned int* ws, int t, float v, int lane) {
+  if (lane == 0) reinterpret_cast<float*>(ws + 4)[t] = v;
+}
+__device__ __forceinline__ void tup_publish_losses(unsigned int* ws, int n_mine, int T, float* loss_out, int lane) {
+  float* stage = reinterpret_cast<float*>(ws + 4);
+  unsigned prev = 0;
+  if (lane == 0) {
+    __threadfence();
+    prev = atomicAdd(ws, unsigned(n_mine));
+  }
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev + unsigned(n_mine) == unsigned(T)) {
+    __threadfence();
+    float tot = 0.0f;
+    for (int k = lane; k < T; k += 32) tot += __ldcg(stage + k);
+    tot = warp_sum(tot);
+    if (lane == 0) loss_out[0] = tot / float(T);
+  }
+}
+
 // Host-side plan shared by the tuple kernels.
 struct TupPlan {
   int sg;        // 25, 30 or 35

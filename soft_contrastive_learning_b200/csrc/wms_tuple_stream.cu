@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
       float v = lane < S ? rowloss[lane] : 0.0f;
       v = warp_sum(v);
       if (lane == 0 && per_tuple != nullptr) per_tuple[t] = v;
-      tup_finish_loss(done_counter, t, T, v, loss_out, lane);
+      tup_deposit_loss(done_counter, t, v, lane);            // published once per CTA after the last tuple
     }
     consumer_sync<kSConsumers>();
 
@@ -475,6 +475,7 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
       }
     }
   }
+  if (warp == 0) tup_publish_losses(done_counter, int(iter), T, loss_out, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
