@@ -101,7 +101,10 @@ int scl_ms_flat_fwd_bwd(const float* emb, const int32_t* labels, int B, int D, c
  *   sq_d_dists [T,P] f32 squared metres anchor->positive (train.py:529-534), NULL when dist_term == NONE
  * ---------------------------------------------------------------------------------------------- */
 enum { SCL_TRIPLET = 0, SCL_LAZY_TRIPLET = 1, SCL_QUADRUPLET = 2, SCL_LAZY_QUADRUPLET = 3,
-       SCL_EVIL_TRIPLET = 4, SCL_EVIL_QUADRUPLET = 5 };
+       SCL_EVIL_TRIPLET = 4, SCL_EVIL_QUADRUPLET = 5,
+       /* distance_quadruplet_loss, model/losses.py:267-307 (calls train/train.py:729-763): distance_triplet_loss with
+        * triplet_loss / lazy_triplet_loss + the distance-term second hinge; needs dist_term != NONE and the `other` row */
+       SCL_DISTANCE_QUADRUPLET = 6, SCL_DISTANCE_LAZY_QUADRUPLET = 7 };
 enum { SCL_DIST_NONE = 0, SCL_DIST_SQUARED = 1, SCL_DIST_HUBER = 2 };
 
 typedef struct {
@@ -125,6 +128,15 @@ int scl_tuple_loss_fwd_bwd(const float* emb, int T, int P, int N, int D, const f
 int scl_logratio_fwd_bwd(const float* emb, int T, int P, int N, int D, const float* sq_pos, const float* sq_neg,
                          int strict_reference, float* loss, float* demb,
                          void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* pairwise_distance_loss, model/losses.py:627-646: all-pairs squared feature distances of
+ * [anchor, positives] (formula of :656-661) against all-pairs squared metres, squared (huber = 0) or Huber (huber = 1,
+ * labels = scaled_f, predictions = scaled_d, delta = 1), mean over T*n*n.
+ *   emb [T,n,D] f32 (n = 1+P <= 32), pairwise_sq_d [T,n,n] f32 (train.py:535-537), demb may be NULL.
+ * Workspace: scl_wms_tuple_workspace_bytes(T, n, D). */
+int scl_pairwise_distance_loss_fwd_bwd(const float* emb, const float* pairwise_sq_d, int T, int n, int D,
+                                       float d_max_squared, float f_max_squared, int huber, float* loss, float* demb,
+                                       void* workspace, size_t workspace_bytes, scl_stream_t stream);
 
 /* D1: _pairwise_squared_distances, model/losses.py:656-661:  out[t,i,j] = r_i - 2 x_i.x_j + r_j
  * (no clamp, diagonal not forced to zero).  x [T,n,D] -> out [T,n,n]. */

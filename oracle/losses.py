@@ -258,6 +258,48 @@ def distance_triplet_loss(a_feature, pos_features, neg_features, margin, lam, sq
     return trip + lam * distance_loss(a_feature, pos_features, squared_d_dists, d_max_squared, f_max_squared)
 
 
+def _best_distance(a_feature, pos_features, squared_d_dists, d_max_squared, f_max_squared):
+    """model/losses.py:664-668."""
+    sd, sf = scale_distances(a_feature, pos_features, squared_d_dists, d_max_squared, f_max_squared)
+    return ((sf - sd) ** 2).min(dim=1).values
+
+
+def _best_huber_distance(a_feature, pos_features, squared_d_dists, d_max_squared, f_max_squared):
+    """model/losses.py:671-675: huber_loss(labels=scaled_f, predictions=scaled_d, reduction=NONE), min over positives."""
+    sd, sf = scale_distances(a_feature, pos_features, squared_d_dists, d_max_squared, f_max_squared)
+    return huber(sf, sd, reduce=False).min(dim=1).values
+
+
+def distance_quadruplet_loss(a_feature, pos_features, neg_features, other_neg, m1, m2, lam, squared_d_dists,
+                             d_max_squared, f_max_squared, triplet_loss_name="triplet_loss",
+                             distance_loss_name="huber_distance_loss"):
+    """model/losses.py:267-307 (calls train/train.py:729-763): distance_triplet_loss + a second hinge in which the
+    "best positive" is the smallest distance-term element and the negative<->other distances are scaled by f_max;
+    the second hinge always takes the max over negatives (:301-305), whatever the triplet name."""
+    a_feature, pos_features, neg_features, other_neg, squared_d_dists = map(
+        _keep, (a_feature, pos_features, neg_features, other_neg, squared_d_dists))
+    trip = distance_triplet_loss(a_feature, pos_features, neg_features, m1, lam, squared_d_dists, d_max_squared,
+                                 f_max_squared, triplet_loss_name, distance_loss_name)
+    if "huber" in distance_loss_name:
+        best = _best_huber_distance(a_feature, pos_features, squared_d_dists, d_max_squared, f_max_squared)
+    else:
+        best = _best_distance(a_feature, pos_features, squared_d_dists, d_max_squared, f_max_squared)
+    d_on = _sqdist(other_neg, neg_features) / f_max_squared
+    second = torch.clamp(m2 + best[:, None] - d_on, min=0.0).max(dim=1).values.mean()
+    return trip + second
+
+
+def pairwise_distance_loss(anchor, positives, pairwise_squared_d_dists, d_max_squared, f_max_squared,
+                           distance_loss_name="distance_loss"):
+    """model/losses.py:627-646: all-pairs squared feature distances of [anchor, positives] (via :656-661) against the
+    all-pairs squared metres, squared or Huber (labels=scaled_f, predictions=scaled_d), mean over everything."""
+    anchor, positives, pairwise_squared_d_dists = map(_keep, (anchor, positives, pairwise_squared_d_dists))
+    f = pairwise_squared_distances(torch.cat([anchor, positives], dim=1)) / f_max_squared
+    d = pairwise_squared_d_dists / d_max_squared
+    el = huber(f, d, reduce=False) if "huber" in distance_loss_name else (f - d) ** 2
+    return el.mean(dim=2).mean(dim=1).mean(dim=0)
+
+
 # --------------------------------------------------------------------------------------
 # L6: logratio_loss (losses.py:125-135) -- literal broadcast, T=1 and P==N only
 # --------------------------------------------------------------------------------------

@@ -113,3 +113,42 @@ def recall_at_n(top_g_dists, rad=25.0, num=25):
     Y = np.array([[float(sum(top_n_[:, n] < x)) / float(len(top_n_[:, n])) * 100 for x in X]
                   for n in range(top_n_.shape[1])])
     return X, Y
+
+
+def localization_summary(nearest_latent_indices, nearest_d_dist, query_xy, ref_xy, rads=(50, 25, 10)):
+    """train/train.py:360-386 (evaluate_localization_thread) without the plotting, loops as written there."""
+    nq = nearest_latent_indices.shape[0]
+    d_to_nearest_latent = np.empty(nearest_latent_indices.shape)
+    for i in range(nq):                                                               # :364-367
+        for j in range(nearest_latent_indices.shape[1]):
+            other_index = nearest_latent_indices[i][j]
+            d_to_nearest_latent[i, j] = np.linalg.norm(query_xy[i, :] - ref_xy[other_index, :])
+    top_n_ = np.empty(nearest_latent_indices.shape)
+    for i in range(nq):                                                               # :369-371
+        for j in range(nearest_latent_indices.shape[1]):
+            top_n_[i, j] = min(d_to_nearest_latent[i, 0:(j + 1)])
+    from sklearn.metrics import auc
+    out = {"scalars": {}, "curves": {}}
+    for rad in rads:                                                                  # :372-386
+        X = np.linspace(0, rad, num=25)
+        Ys = []
+        for n in range(top_n_.shape[1]):
+            Y = [float(sum(top_n_[:, n] < x)) / float(len(top_n_[:, n])) * 100 for x in X]
+            Ys.append(Y)
+            if n == 0:
+                out["scalars"]["{}m-auc@Top1".format(rad)] = auc(X, Y)
+                out["scalars"]["%<{}m@Top1".format(rad)] = Y[-1]
+        Yo = [float(sum(np.array(nearest_d_dist).reshape(-1) < x)) / float(len(top_n_[:, 0])) * 100 for x in X]
+        out["curves"][rad] = {"X": X, "Y": np.array(Ys), "optimum": np.array(Yo)}
+    return out
+
+
+def mining_sorted_neighbours(cached_features, cached_indices, index, k):
+    """train/train.py:446-452: cache entries ordered by feature distance to image ``index`` (sklearn KDTree)."""
+    from sklearn.neighbors import KDTree
+    fis = np.where(cached_indices == index)[0]
+    if len(fis) == 0:
+        return None
+    tree = KDTree(cached_features)                                                    # :1066
+    sorted_ni = tree.query(cached_features[fis[0], :].reshape(1, -1), k=k, return_distance=False, sort_results=True)[0]
+    return [cached_indices[ni] for ni in sorted_ni]

@@ -29,7 +29,8 @@ class TupleParams(C.Structure):
 WF = {"exp": 0, "lin": 1, "tanh": 2}
 SUMF = {"ms": 0, "plain": 1}
 TUPLE_KIND = {"triplet_loss": 0, "lazy_triplet_loss": 1, "quadruplet_loss": 2, "lazy_quadruplet_loss": 3,
-              "evil_triplet_loss": 4, "evil_quadruplet_loss": 5}
+              "evil_triplet_loss": 4, "evil_quadruplet_loss": 5,
+              "distance_quadruplet_loss": 6, "distance_lazy_quadruplet_loss": 7}
 DIST_TERM = {"none": 0, "distance_loss": 1, "huber_distance_loss": 2}
 
 # name -> (restype, argtypes); mirrors include/scl_b200.h one to one
@@ -53,6 +54,8 @@ PROTOTYPES = {
     "scl_logratio_fwd_bwd": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr,
                                        c_ptr, C.c_size_t, c_ptr]),
     "scl_pairwise_sqdist": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "scl_pairwise_distance_loss_fwd_bwd": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                                     c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_netvlad_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _SIZE_P]),
     "scl_netvlad_fwd": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t,
                                   c_ptr]),

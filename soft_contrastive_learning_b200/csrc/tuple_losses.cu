@@ -4,6 +4,7 @@
 //   pointnetvlad_cls.{triplet,lazy_triplet,quadruplet,lazy_quadruplet}_loss  (train/train.py:700-712)
 //   evil_triplet_loss / evil_quadruplet_loss                                  (model/losses.py:63-73,197-214)
 //   distance_triplet_loss with distance_loss / huber_distance_loss            (model/losses.py:225-264,678-690)
+//   distance_quadruplet_loss, same two distance terms x {triplet, lazy}       (model/losses.py:267-307,664-675)
 //   logratio_loss                                                             (model/losses.py:125-135)
 //   _pairwise_squared_distances                                               (model/losses.py:656-661)
 //
@@ -56,8 +57,9 @@ __device__ float anchor_logic(const AnchorArgs& a, int t, int S, const float* da
   if (a.mode == kModeTriplet) {
     const int kind = a.tp.kind;
     const bool evil = kind == SCL_EVIL_TRIPLET || kind == SCL_EVIL_QUADRUPLET;
-    const bool lazy = kind == SCL_LAZY_TRIPLET || kind == SCL_LAZY_QUADRUPLET;
+    const bool lazy = kind == SCL_LAZY_TRIPLET || kind == SCL_LAZY_QUADRUPLET || kind == SCL_DISTANCE_LAZY_QUADRUPLET;
     const bool quad = kind == SCL_QUADRUPLET || kind == SCL_LAZY_QUADRUPLET || kind == SCL_EVIL_QUADRUPLET;
+    const bool dquad = kind == SCL_DISTANCE_QUADRUPLET || kind == SCL_DISTANCE_LAZY_QUADRUPLET;
     // best (min) / worst (max) positive distance, ties share the gradient evenly (tf.reduce_min/max)
     float dp = (lane < P) ? da[1 + lane] : (evil ? -INFINITY : INFINITY);
     float ref = evil ? warp_max(dp) : warp_min(dp);
@@ -117,6 +119,34 @@ __device__ float anchor_logic(const AnchorArgs& a, int t, int S, const float* da
         gamma[1 + lane] += g;
       }
       loss += a.tp.lam * warp_sum(term) / float(P);
+    }
+    // distance_quadruplet_loss (losses.py:267-307): the second hinge uses the smallest element of the distance term as
+    // "best positive" (losses.py:664-675), scales |neg - other|^2 by f_max and always takes the max over negatives
+    if (dquad) {
+      float el = INFINITY, gel = 0.0f;
+      if (lane < P) {
+        const float sd = a.sq_d_dists[size_t(t) * P + lane] / a.tp.d_max_squared;
+        const float e = da[1 + lane] / a.tp.f_max_squared - sd;
+        if (a.tp.dist_term == SCL_DIST_HUBER) {
+          const float ae = fabsf(e), q = fminf(ae, 1.0f);
+          el = 0.5f * q * q + (ae - q);
+          gel = (ae <= 1.0f) ? e : (e > 0.0f ? 1.0f : -1.0f);
+        } else {
+          el = e * e;
+          gel = 2.0f * e;
+        }
+      }
+      const float best = warp_min(el);
+      const unsigned btie = __ballot_sync(0xffffffffu, lane < P && el == best);
+      const float x = (lane < N) ? a.tp.m2 + best - dob[1 + P + lane] / a.tp.f_max_squared : -INFINITY;
+      const float hh = (lane < N) ? fmaxf(x, 0.0f) : -INFINITY;
+      const float hm = warp_max(hh);
+      const unsigned tm = __ballot_sync(0xffffffffu, lane < N && hh == hm);
+      const float coef = (lane < N && hh == hm && x >= 0.0f) ? 1.0f / float(__popc(tm)) : 0.0f;
+      loss += hm;
+      if (lane < N) omega[1 + P + lane] -= coef / a.tp.f_max_squared;
+      const float dbest = warp_sum(coef);
+      if (lane < P && el == best) gamma[1 + lane] += dbest * gel / (a.tp.f_max_squared * float(__popc(btie)));
     }
   } else {
     // logratio_loss, losses.py:125-135 (T=1 formula).  fr[n][p] = log(dpos_p / dneg_n).
@@ -379,11 +409,13 @@ extern "C" int scl_tuple_loss_fwd_bwd(const float* emb, int T, int P, int N, int
                                       const scl_tuple_params* p, float* loss, float* demb, void* workspace,
                                       size_t workspace_bytes, scl_stream_t stream) {
   if (!p) return SCL_ERR_BAD_ARG;
-  if (p->kind < SCL_TRIPLET || p->kind > SCL_EVIL_QUADRUPLET) return SCL_ERR_BAD_ARG;
+  if (p->kind < SCL_TRIPLET || p->kind > SCL_DISTANCE_LAZY_QUADRUPLET) return SCL_ERR_BAD_ARG;
   if (p->dist_term < SCL_DIST_NONE || p->dist_term > SCL_DIST_HUBER) return SCL_ERR_BAD_ARG;
   if (p->dist_term != SCL_DIST_NONE && !sq_d_dists) return SCL_ERR_BAD_ARG;
+  const bool dquad = p->kind == SCL_DISTANCE_QUADRUPLET || p->kind == SCL_DISTANCE_LAZY_QUADRUPLET;
+  if (dquad && p->dist_term == SCL_DIST_NONE) return SCL_ERR_BAD_ARG;      // its second hinge is built on the distance term
   if (P < 1 || N < 1 || P > 32 || N > 32) return SCL_ERR_BAD_SHAPE;
-  const bool quad = p->kind == SCL_QUADRUPLET || p->kind == SCL_LAZY_QUADRUPLET || p->kind == SCL_EVIL_QUADRUPLET;
+  const bool quad = dquad || p->kind == SCL_QUADRUPLET || p->kind == SCL_LAZY_QUADRUPLET || p->kind == SCL_EVIL_QUADRUPLET;
   scl::AnchorArgs a = {};
   a.mode = scl::kModeTriplet;
   a.P = P; a.N = N; a.has_other = quad ? 1 : 0;

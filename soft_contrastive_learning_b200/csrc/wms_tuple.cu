@@ -29,6 +29,8 @@ constexpr int kWmsThreads = kTupThreads;
 constexpr int kWmsWarps = kTupWarps;
 constexpr int kTileGrid = 5;                                   // 5 x 5 grid of TS x TS tiles
 constexpr int kNumTiles = kTileGrid * (kTileGrid + 1) / 2;     // 15 symmetric tiles
+// internal values of scl_ms_params::sumfunction that route the Gram skeleton to pairwise_distance_loss
+constexpr int kSumPairwiseSquared = 100, kSumPairwiseHuber = 101;
 
 template <int TS>
 struct WmsSmem {
@@ -160,74 +162,114 @@ __global__ void __launch_bounds__(kWmsThreads, (TS <= 6 ? 2 : 1)) wms_tuple_chun
   }
   __syncthreads();
 
+  float* Mraw = red + 2 * SG * SG;
+  if (p.sumfunction >= kSumPairwiseSquared) {
+    // ---------------- pairwise_distance_loss (model/losses.py:627-646) on the same Gram ----------------
+    // F_ij = r_i - 2 x_i.x_j + r_j (losses.py:656-661), e = F/f_max - d/d_max, squared or Huber(delta = 1), mean over
+    // all n*n pairs;  A_ij = dL_t/dF_ij,  dX = M X with M = 2 (diag(rowsum(A + A^T)) - (A + A^T)).
+    // p.alpha carries d_max_squared, p.beta f_max_squared (internal call, see scl_pairwise_distance_loss_fwd_bwd).
+    const float* dist_t = dist + size_t(t) * S * S;
+    const float inv_nn = 1.0f / float(S * S);
+    for (int i = warp; i < S; i += kWmsWarps) {
+      float el = 0.0f, g = 0.0f;
+      if (lane < S) {
+        const float F = Gf[i * (SG + 1) + i] - 2.0f * Gf[i * (SG + 1) + lane] + Gf[lane * (SG + 1) + lane];
+        const float e = F / p.beta - dist_t[i * S + lane] / p.alpha;
+        if (p.sumfunction == kSumPairwiseHuber) {
+          const float ae = fabsf(e), q = fminf(ae, 1.0f);
+          el = 0.5f * q * q + (ae - q);
+          g = (ae <= 1.0f) ? e : (e > 0.0f ? 1.0f : -1.0f);
+        } else {
+          el = e * e;
+          g = 2.0f * e;
+        }
+        red[i * SG + lane] = g * inv_nn / p.beta;
+      }
+      el = warp_sum(el);
+      if (lane == 0) rowloss[i] = el * inv_nn;
+    }
+    __syncthreads();
+    for (int i = warp; i < S; i += kWmsWarps) {
+      const float w = lane < S ? red[i * SG + lane] + red[lane * SG + i] : 0.0f;
+      const float rs = warp_sum(w);
+      if (lane == 0) cvec[i] = rs;
+    }
+    __syncthreads();
+    for (int k = tid; k < S * S; k += kWmsThreads) {
+      const int i = k / S, j = k - i * S;
+      const float w = red[i * SG + j] + red[j * SG + i];
+      Mraw[i * SG + j] = (i == j) ? 2.0f * (cvec[i] - w) : -2.0f * w;
+    }
+    __syncthreads();
+  } else {
   // ---------------- weights: one warp per anchor row ----------------
-  if (tid < SG) {
-    float n2 = tid < S ? Gf[tid * (SG + 1) + tid] : 1.0f;
-    // tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12))  (losses.py:7)
-    invn[tid] = rsqrtf(fmaxf(n2, 1e-12f));
-    nflag[tid] = n2 >= 1e-12f ? 1.0f : 0.0f;     // below the clamp the normalisation is a pure scale
-  }
-  __syncthreads();
-  const float* dist_t = dist + size_t(t) * S * S;
-  const float invS = 1.0f / float(S);
-  for (int i = warp; i < S; i += kWmsWarps) {
-    const int j = lane;
-    const bool valid = j < S;
-    float raw = 0.0f, s = 0.0f, wp = 0.0f, wn = 0.0f;
-    if (valid) {
-      raw = Gf[i * (SG + 1) + j] * invn[i] * invn[j];
-      s = fmaxf(raw, 0.0f);                                              // losses.py:26
-      wms_masks(dist_t[i * S + j], p.d_alpha, p.d_beta, p.wfunction, wp, wn);
-      if (i == j) wp -= 1.0f;                                            // losses.py:22
+    if (tid < SG) {
+      float n2 = tid < S ? Gf[tid * (SG + 1) + tid] : 1.0f;
+      // tf.nn.l2_normalize: x * rsqrt(max(sum x^2, 1e-12))  (losses.py:7)
+      invn[tid] = rsqrtf(fmaxf(n2, 1e-12f));
+      nflag[tid] = n2 >= 1e-12f ? 1.0f : 0.0f;     // below the clamp the normalisation is a pure scale
     }
-    MsRowStats st;
-    st.maxv = warp_max(valid ? s * wn : -INFINITY);
-    st.tmp = warp_max(valid ? s * wp : -INFINITY);
-    st.minv = warp_min(valid ? (s - st.tmp) * wp : INFINITY) + st.tmp;
-    bool kp = false, kn = false;
-    float ep = 0.0f, en = 0.0f;
-    if (valid) ms_elem(s, wp, wn, st, p, kp, kn, ep, en);
-    float A = warp_sum(ep), B = warp_sum(en);
-    float g = 0.0f;
-    if (valid) {
-      g = ms_elem_grad(wp, wn, kp, kn, ep, en, A, B, p) * invS;
-      if (!(raw >= 0.0f)) g = 0.0f;                                      // tf.maximum passes gradient when x >= 0
-    }
-    // Gf now holds similarities in the upper use; stash dL/ds into `red` (free again) as Gw[i][j]
-    if (valid) red[i * SG + j] = g;
-    if (valid) red[SG * SG + i * SG + j] = raw;
-    if (lane == 0) rowloss[i] = ms_row_loss(A, B, p) * invS;
-    if (kept != nullptr && crank == 0) {
-      unsigned mp = __ballot_sync(0xffffffffu, kp), mn = __ballot_sync(0xffffffffu, kn);
-      if (lane == 0) {
-        kept[(size_t(t) * S + i) * 2 + 0] = mp;
-        kept[(size_t(t) * S + i) * 2 + 1] = mn;
+    __syncthreads();
+    const float* dist_t = dist + size_t(t) * S * S;
+    const float invS = 1.0f / float(S);
+    for (int i = warp; i < S; i += kWmsWarps) {
+      const int j = lane;
+      const bool valid = j < S;
+      float raw = 0.0f, s = 0.0f, wp = 0.0f, wn = 0.0f;
+      if (valid) {
+        raw = Gf[i * (SG + 1) + j] * invn[i] * invn[j];
+        s = fmaxf(raw, 0.0f);                                              // losses.py:26
+        wms_masks(dist_t[i * S + j], p.d_alpha, p.d_beta, p.wfunction, wp, wn);
+        if (i == j) wp -= 1.0f;                                            // losses.py:22
+      }
+      MsRowStats st;
+      st.maxv = warp_max(valid ? s * wn : -INFINITY);
+      st.tmp = warp_max(valid ? s * wp : -INFINITY);
+      st.minv = warp_min(valid ? (s - st.tmp) * wp : INFINITY) + st.tmp;
+      bool kp = false, kn = false;
+      float ep = 0.0f, en = 0.0f;
+      if (valid) ms_elem(s, wp, wn, st, p, kp, kn, ep, en);
+      float A = warp_sum(ep), B = warp_sum(en);
+      float g = 0.0f;
+      if (valid) {
+        g = ms_elem_grad(wp, wn, kp, kn, ep, en, A, B, p) * invS;
+        if (!(raw >= 0.0f)) g = 0.0f;                                      // tf.maximum passes gradient when x >= 0
+      }
+      // Gf now holds similarities in the upper use; stash dL/ds into `red` (free again) as Gw[i][j]
+      if (valid) red[i * SG + j] = g;
+      if (valid) red[SG * SG + i * SG + j] = raw;
+      if (lane == 0) rowloss[i] = ms_row_loss(A, B, p) * invS;
+      if (kept != nullptr && crank == 0) {
+        unsigned mp = __ballot_sync(0xffffffffu, kp), mn = __ballot_sync(0xffffffffu, kn);
+        if (lane == 0) {
+          kept[(size_t(t) * S + i) * 2 + 0] = mp;
+          kept[(size_t(t) * S + i) * 2 + 1] = mn;
+        }
       }
     }
-  }
-  __syncthreads();
-  // M = diag(invn) (W - diag(c)) diag(invn), W = Gw + Gw^T, c_i = sum_j W_ij s_ij(raw)  (projection of l2norm)
-  const float* Gw = red;
-  const float* Sraw = red + SG * SG;
-  for (int i = warp; i < S; i += kWmsWarps) {
-    float w = 0.0f, part = 0.0f;
-    if (lane < S) {
-      w = Gw[i * SG + lane] + Gw[lane * SG + i];
-      part = w * Sraw[i * SG + lane];
+    __syncthreads();
+    // M = diag(invn) (W - diag(c)) diag(invn), W = Gw + Gw^T, c_i = sum_j W_ij s_ij(raw)  (projection of l2norm)
+    const float* Gw = red;
+    const float* Sraw = red + SG * SG;
+    for (int i = warp; i < S; i += kWmsWarps) {
+      float w = 0.0f, part = 0.0f;
+      if (lane < S) {
+        w = Gw[i * SG + lane] + Gw[lane * SG + i];
+        part = w * Sraw[i * SG + lane];
+      }
+      float c = warp_sum(part) * nflag[i];
+      if (lane == 0) cvec[i] = c;
     }
-    float c = warp_sum(part) * nflag[i];
-    if (lane == 0) cvec[i] = c;
+    __syncthreads();
+    // overwrite Gw in place with M (Gw/Sraw are not needed afterwards), then store it transposed for step 5
+    for (int k = tid; k < S * S; k += kWmsThreads) {
+      int i = k / S, j = k - i * S;
+      float w = Gw[i * SG + j] + Gw[j * SG + i];
+      if (i == j) w -= cvec[i];
+      Mraw[i * SG + j] = invn[i] * w * invn[j];
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // overwrite Gw in place with M (Gw/Sraw are not needed afterwards), then store it transposed for step 5
-  float* Mraw = red + 2 * SG * SG;
-  for (int k = tid; k < S * S; k += kWmsThreads) {
-    int i = k / S, j = k - i * S;
-    float w = Gw[i * SG + j] + Gw[j * SG + i];
-    if (i == j) w -= cvec[i];
-    Mraw[i * SG + j] = invn[i] * w * invn[j];
-  }
-  __syncthreads();
   tup_store_Mt<SG>(Mt, Mraw, SG, S);
 
   // ---------------- loss ----------------
@@ -327,6 +369,34 @@ int wms_resident_launch(const float* emb, const float* dist, int T, int S, int D
                         float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream);
 
 }  // namespace scl
+
+extern "C" int scl_pairwise_distance_loss_fwd_bwd(const float* emb, const float* pairwise_sq_d, int T, int n, int D,
+                                                  float d_max_squared, float f_max_squared, int huber, float* loss,
+                                                  float* demb, void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
+  if (!emb || !pairwise_sq_d || !loss || !workspace) return SCL_ERR_BAD_ARG;
+  if (T < 1 || !(d_max_squared > 0.0f) || !(f_max_squared > 0.0f)) return SCL_ERR_BAD_ARG;
+  if (!scl::aligned16(emb) || (demb && !scl::aligned16(demb)) || !scl::aligned16(workspace)) return SCL_ERR_ALIGN;
+  int rc = scl::check_device();
+  if (rc) return rc;
+  scl::WmsPlan pl;
+  rc = scl::wms_plan(n, D, &pl);
+  if (rc) return rc;
+  size_t need = 0;
+  scl_wms_tuple_workspace_bytes(T, n, D, &need);
+  if (workspace_bytes < need) return SCL_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  unsigned int* counter = static_cast<unsigned int*>(workspace);
+  SCL_CUDA_TRY(cudaMemsetAsync(counter, 0, 16, stream));
+  scl_ms_params p = {};
+  p.alpha = d_max_squared;
+  p.beta = f_max_squared;
+  p.sumfunction = huber ? scl::kSumPairwiseHuber : scl::kSumPairwiseSquared;
+  switch (pl.ts) {
+    case 5: return scl::wms_launch_chunked<5>(pl, emb, pairwise_sq_d, T, n, D, p, nullptr, demb, nullptr, loss, counter, stream);
+    case 6: return scl::wms_launch_chunked<6>(pl, emb, pairwise_sq_d, T, n, D, p, nullptr, demb, nullptr, loss, counter, stream);
+    default: return scl::wms_launch_chunked<7>(pl, emb, pairwise_sq_d, T, n, D, p, nullptr, demb, nullptr, loss, counter, stream);
+  }
+}
 
 extern "C" int scl_wms_tuple_workspace_bytes(int T, int S, int D, size_t* bytes) {
   if (!bytes || T < 1) return SCL_ERR_BAD_ARG;

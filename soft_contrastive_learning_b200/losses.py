@@ -317,6 +317,71 @@ def distance_triplet_loss(a_feature, pos_features, neg_features, margin, lam, sq
                        d_max_squared, f_max_squared, term)
 
 
+def distance_quadruplet_loss(a_feature, pos_features, neg_features, other_neg, m1, m2, lam, squared_d_dists,
+                             d_max_squared, f_max_squared, triplet_loss_name="triplet_loss",
+                             distance_loss_name="huber_distance_loss"):
+    """model/losses.py:267-307 (calls train/train.py:729-763): distance_triplet_loss + the distance-term second hinge."""
+    if triplet_loss_name not in ("triplet_loss", "lazy_triplet_loss"):
+        raise AttributeError(f"module 'pointnetvlad_cls' has no attribute {triplet_loss_name!r}")
+    kind = "distance_lazy_quadruplet_loss" if triplet_loss_name == "lazy_triplet_loss" else "distance_quadruplet_loss"
+    term = "huber_distance_loss" if "huber" in distance_loss_name else "distance_loss"     # losses.py:285,292
+    return _tuple_loss(kind, (a_feature, pos_features, neg_features, other_neg), m1, m2, lam, squared_d_dists,
+                       d_max_squared, f_max_squared, term)
+
+
+def _pairwise_distance_raw(emb3, sq_d3, d_max_squared, f_max_squared, huber, need_grad=True):
+    T, n, D = emb3.shape
+    L = lib()
+    nbytes = C.c_size_t()
+    check(L.scl_wms_tuple_workspace_bytes(T, n, D, C.byref(nbytes)), "scl_wms_tuple_workspace_bytes")
+    ws = _ws(nbytes.value, emb3.device)
+    loss = torch.empty(1, dtype=torch.float32, device=emb3.device)
+    grad = torch.empty_like(emb3) if need_grad else None
+    check(L.scl_pairwise_distance_loss_fwd_bwd(_p(emb3), _p(sq_d3), T, n, D, float(d_max_squared), float(f_max_squared),
+                                               int(huber), _p(loss), _p(grad), _p(ws), ws.numel(), _stream()),
+          "scl_pairwise_distance_loss_fwd_bwd")
+    return loss, grad
+
+
+class _PairwiseDistanceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sq_d, consts, anchor, positives):
+        emb3 = _f32(torch.cat([anchor.detach(), positives.detach()], dim=1))
+        loss, grad = _pairwise_distance_raw(emb3, sq_d, *consts, need_grad=True)
+        ctx.save_for_backward(grad)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        grad = grad * g
+        return None, None, grad[:, :1], grad[:, 1:]
+
+
+def pairwise_distance_loss(anchor, positives, pairwise_squared_d_dists, d_max_squared, f_max_squared,
+                           distance_loss_name="distance_loss"):
+    """model/losses.py:627-646: anchor [T,1,D], positives [T,P,D], pairwise_squared_d_dists [T,1+P,1+P] (squared
+    metres, DISTANCE_TYPE 'pairwise', train.py:535-537) -> scalar; squared or Huber element (name contains 'huber')."""
+    parts = [p if isinstance(p, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(p)) for p in (anchor, positives)]
+    parts = [p if p.is_cuda else p.to(_dev()) for p in parts]
+    n = 1 + parts[1].shape[1]
+    sq = _f32(pairwise_squared_d_dists).reshape(-1, n, n)
+    consts = (float(d_max_squared), float(f_max_squared), 1 if "huber" in distance_loss_name else 0)
+    if any(p.requires_grad for p in parts):
+        return _PairwiseDistanceFn.apply(sq, consts, *parts)
+    loss, _ = _pairwise_distance_raw(_f32(torch.cat(parts, dim=1)), sq, *consts, need_grad=False)
+    return loss.reshape(())
+
+
+def pairwise_distance_loss_value_and_grad(features, pairwise_squared_d_dists, d_max_squared=225.0, f_max_squared=2.0,
+                                          distance_loss_name="distance_loss"):
+    """Fused path on [T, 1+P, D] features (anchor first)."""
+    emb3 = _f32(features)
+    sq = _f32(pairwise_squared_d_dists).reshape(emb3.shape[0], emb3.shape[1], emb3.shape[1])
+    loss, grad = _pairwise_distance_raw(emb3, sq, d_max_squared, f_max_squared, 1 if "huber" in distance_loss_name else 0)
+    return _to_host(loss, grad, features)
+
+
 def tuple_loss_value_and_grad(name, output, tuples_per_batch, positives_per_tuple, negatives_per_tuple, m1=0.1, m2=0.2,
                               lam=0.5, squared_d_dists=None, d_max_squared=225.0, f_max_squared=2.0,
                               distance_loss_name="none"):
@@ -404,7 +469,8 @@ pairwise_squared_distances = _pairwise_squared_distances
 # ----------------------------------------------------------------------------------------------
 LOSS_NAMES = ("triplet", "lazy_triplet", "evil_triplet", "quadruplet", "lazy_quadruplet", "evil_quadruplet",
               "distance_triplet", "distance_lazy_triplet", "huber_distance_triplet", "huber_distance_lazy_triplet",
-              "ms_loss", "wms", "logratio")
+              "distance_quadruplet", "distance_lazy_quadruplet", "huber_distance_quadruplet",
+              "huber_distance_lazy_quadruplet", "ms_loss", "wms", "logratio")
 
 
 def split_outputs(output, tuples_per_batch, positives_per_tuple, negatives_per_tuple, other=False):
@@ -450,6 +516,12 @@ def get_loss(name):
             dl = "huber_distance_loss" if "huber" in name else "distance_loss"
             return distance_triplet_loss(outs[0], outs[1], outs[2], c["MARGIN_1"], c["LAM"], distances, d_max_squared,
                                          f_max_squared, trip, dl)
+        if name in ("distance_quadruplet", "distance_lazy_quadruplet", "huber_distance_quadruplet",
+                    "huber_distance_lazy_quadruplet"):                        # train.py:729-763
+            trip = "lazy_triplet_loss" if "lazy" in name else "triplet_loss"
+            dl = "huber_distance_loss" if "huber" in name else "distance_loss"
+            return distance_quadruplet_loss(outs[0], outs[1], outs[2], outs[3], c["MARGIN_1"], c["MARGIN_2"], c["LAM"],
+                                            distances, d_max_squared, f_max_squared, trip, dl)
         if name == "ms_loss":                                                 # train.py:821-827
             return ms_loss(ms_labels(T, P, N), output, ms_mining=c["MSMINING"])
         if name == "wms":                                                     # train.py:851-852

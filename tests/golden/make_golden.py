@@ -169,6 +169,13 @@ def make_tuple_losses():
             lambda e: ol.distance_triplet_loss(*spt(e)[:3], m1, lam, torch.as_tensor(sq64), dmax, fmax,
                                                "triplet_loss", "distance_loss")),
     }
+    # distance_quadruplet_loss, reference source (losses.py:267-307; dispatch train.py:729-763)
+    for tname, tl in (("", "triplet_loss"), ("lazy_", "lazy_triplet_loss")):
+        for dname, dl in (("distance", "distance_loss"), ("huber_distance", "huber_distance_loss")):
+            cases[f"{dname}_{tname}quadruplet"] = (
+                lambda e, tl=tl, dl=dl: ref.distance_quadruplet_loss(*sp(e), m1, m2, lam, A(sq64), dmax, fmax, tl, dl),
+                lambda e, tl=tl, dl=dl: ol.distance_quadruplet_loss(*spt(e), m1, m2, lam, torch.as_tensor(sq64), dmax,
+                                                                    fmax, tl, dl))
     for tag, (f_ref, f_or) in cases.items():
         v_ref = float(f_ref(e64))
         v_or, (g_or,) = ol.value_and_grad(f_or, [e64])
@@ -178,6 +185,31 @@ def make_tuple_losses():
         out["grad_" + tag] = g_or
         print(f"  {tag}: loss={v_ref:.10f} fd_err={err:.2e} nz_grad={int((g_or != 0).sum())}")
     save("tuple_losses_T3_P4_N6_D40", **out)
+
+
+def make_pairwise_distance_loss():
+    """pairwise_distance_loss (losses.py:627-646) on [anchor, positives] with all-pairs squared metres."""
+    rng = np.random.default_rng(8)
+    T, P, D = 3, 5, 40
+    xy = synth.tuple_xy(rng, T, P, 2)[:, :P + 1]
+    emb = (0.6 * synth.tuple_descriptors(rng, T, P, 2, D, pos_noise=1.2)[:, :P + 1]).astype(np.float32)
+    e64 = emb.astype(np.float64)
+    diff = xy[:, :, None, :] - xy[:, None, :, :]
+    sqd = (diff ** 2).sum(-1).astype(np.float32)                     # 'pairwise' DISTANCE_TYPE, train.py:535-537
+    sq64 = sqd.astype(np.float64)
+    dmax, fmax = 225.0, 2.0
+    out = {"emb": emb, "pairwise_sq_d": sqd, "P": P, "d_max_squared": dmax, "f_max_squared": fmax}
+    for tag, dl in (("squared", "distance_loss"), ("huber", "huber_distance_loss")):
+        f_ref = lambda e, dl=dl: ref.pairwise_distance_loss(A(e[:, :1]), A(e[:, 1:]), A(sq64), dmax, fmax, dl)
+        f_or = lambda e, dl=dl: ol.pairwise_distance_loss(e[:, :1], e[:, 1:], torch.as_tensor(sq64), dmax, fmax, dl)
+        v_ref = float(f_ref(e64))
+        v_or, (g_or,) = ol.value_and_grad(f_or, [e64])
+        assert abs(v_ref - v_or) < 1e-12 * max(1, abs(v_ref)), (tag, v_ref, v_or)
+        err = check_grad("pairwise_" + tag, f_ref, e64, g_or)
+        out["loss_" + tag] = v_ref
+        out["grad_" + tag] = g_or
+        print(f"  pairwise_distance_loss[{tag}]: loss={v_ref:.10f} fd_err={err:.2e}")
+    save("pairwise_distance_loss_T3_P5_D40", **out)
 
 
 def make_logratio():
@@ -226,3 +258,4 @@ if __name__ == "__main__":
     make_tuple_losses()
     make_logratio()
     make_pairwise()
+    make_pairwise_distance_loss()

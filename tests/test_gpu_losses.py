@@ -221,7 +221,9 @@ def test_flat_wms_and_ms_batch(cuda_lib):
 
 # ---------------- triplet family ----------------
 TUPLE_CASES = ["triplet", "lazy_triplet", "quadruplet", "lazy_quadruplet", "evil_triplet", "evil_quadruplet",
-               "huber_distance_triplet", "huber_distance_lazy_triplet", "distance_triplet"]
+               "huber_distance_triplet", "huber_distance_lazy_triplet", "distance_triplet",
+               "distance_quadruplet", "huber_distance_quadruplet", "distance_lazy_quadruplet",
+               "huber_distance_lazy_quadruplet"]
 
 
 def _run_named(losses, tag, emb_t, sq, P, N, m1, m2, lam, dmax, fmax):
@@ -240,6 +242,8 @@ def _run_named(losses, tag, emb_t, sq, P, N, m1, m2, lam, dmax, fmax):
         return losses.evil_quadruplet_loss(q, p, n, o, m1, m2)
     trip = "lazy_triplet_loss" if "lazy" in tag else "triplet_loss"
     dl = "huber_distance_loss" if "huber" in tag else "distance_loss"
+    if "quadruplet" in tag:
+        return losses.distance_quadruplet_loss(q, p, n, o, m1, m2, lam, sq, dmax, fmax, trip, dl)
     return losses.distance_triplet_loss(q, p, n, m1, lam, sq, dmax, fmax, trip, dl)
 
 
@@ -277,6 +281,64 @@ def test_tuple_losses_config3_shape(cuda_lib, name):
     ref, (rg,) = ol.value_and_grad(f, [emb.astype(np.float64)])
     assert ref > 0
     assert rel(loss, ref) < LOSS_TOL and grad_err(grad.reshape(emb.shape), rg) < GRAD_TOL
+
+
+@pytest.mark.parametrize("dl", ["distance_loss", "huber_distance_loss"])
+@pytest.mark.parametrize("trip", ["triplet_loss", "lazy_triplet_loss"])
+def test_distance_quadruplet_active_second_hinge(cuda_lib, trip, dl):
+    """distance_quadruplet_loss (losses.py:267-307) with the `other` negative close enough to the
+    negatives that the distance-term hinge is active in most tuples (the golden case only exercises it for 'distance')."""
+    from soft_contrastive_learning_b200 import losses
+    T, P, N, D = 16, 12, 11, 512
+    rng = np.random.default_rng(31)
+    xy = synth.tuple_xy(rng, T, P, N, other=True)
+    emb = (0.03 * synth.tuple_descriptors(rng, T, P, N, D, other=True, pos_noise=1.2)).astype(np.float32)
+    emb[:, -1] = emb[:, 1 + P] + 0.02 * rng.standard_normal((T, D)).astype(np.float32)     # other ~ first negative
+    sqd = synth.anchor_sq_dists(xy, P).astype(np.float32)
+    e = torch.tensor(emb, device="cuda", requires_grad=True)
+    q, p, n, o = e[:, 0:1], e[:, 1:1 + P], e[:, 1 + P:1 + P + N], e[:, 1 + P + N:]
+    loss = losses.distance_quadruplet_loss(q, p, n, o, 0.1, 0.2, 0.5, sqd, 225.0, 2.0, trip, dl)
+    loss.backward()
+
+    def f(x):
+        parts = ol.split_tuple(x, P, N, other=True)
+        return ol.distance_quadruplet_loss(*parts, 0.1, 0.2, 0.5, torch.as_tensor(sqd.astype(np.float64)), 225.0, 2.0,
+                                           trip, dl)
+    ref, (rg,) = ol.value_and_grad(f, [emb.astype(np.float64)])
+    base, _ = ol.value_and_grad(lambda x: ol.distance_triplet_loss(*ol.split_tuple(x, P, N, other=True)[:3], 0.1, 0.5,
+                                                                   torch.as_tensor(sqd.astype(np.float64)), 225.0, 2.0,
+                                                                   trip, dl), [emb.astype(np.float64)])
+    assert ref > base + 1e-3                                   # the second hinge contributes
+    assert rel(float(loss), ref) < LOSS_TOL and grad_err(e.grad.cpu().numpy(), rg) < GRAD_TOL
+    # the --loss name dispatch of train.py:729-763 reaches the same kernel
+    name = ("huber_" if "huber" in dl else "") + "distance_" + ("lazy_" if "lazy" in trip else "") + "quadruplet"
+    cfg = dict(TUPLES_PER_BATCH=T, POSITIVES_PER_TUPLE=P, NEGATIVES_PER_TUPLE=N, MARGIN_1=0.1, MARGIN_2=0.2, LAM=0.5)
+    with torch.no_grad():
+        l2 = losses.get_loss(name)(e.detach().reshape(T * (P + N + 2), D), sqd, cfg)
+    assert float(l2) == float(loss)
+
+
+@pytest.mark.parametrize("tag,dl", [("squared", "distance_loss"), ("huber", "huber_distance_loss")])
+def test_pairwise_distance_loss_golden_and_shapes(cuda_lib, golden, tag, dl):
+    """pairwise_distance_loss (losses.py:627-646): golden from the reference source, then a wider shape
+    (P = 12, D = 4096, T = 32) against the oracle."""
+    from soft_contrastive_learning_b200 import losses
+    g = golden("pairwise_distance_loss_T3_P5_D40")
+    e = torch.tensor(g["emb"], device="cuda", requires_grad=True)
+    loss = losses.pairwise_distance_loss(e[:, :1], e[:, 1:], g["pairwise_sq_d"], float(g["d_max_squared"]),
+                                         float(g["f_max_squared"]), dl)
+    (2.0 * loss).backward()
+    assert rel(float(loss), float(g["loss_" + tag])) < LOSS_TOL
+    assert grad_err(e.grad.cpu().numpy() / 2.0, g["grad_" + tag]) < GRAD_TOL
+    T, P, D = 32, 12, 4096
+    rng = np.random.default_rng(17)
+    xy = synth.tuple_xy(rng, T, P, 2)[:, :P + 1]
+    emb = (0.02 * synth.tuple_descriptors(rng, T, P, 2, D, pos_noise=1.2)[:, :P + 1]).astype(np.float32)
+    sqd = ((xy[:, :, None, :] - xy[:, None, :, :]) ** 2).sum(-1).astype(np.float32)
+    lv, gv = losses.pairwise_distance_loss_value_and_grad(emb, sqd, 225.0, 2.0, dl)
+    ref, (rg,) = ol.value_and_grad(lambda x: ol.pairwise_distance_loss(x[:, :1], x[:, 1:], torch.as_tensor(sqd.astype(np.float64)),
+                                                                       225.0, 2.0, dl), [emb.astype(np.float64)])
+    assert rel(lv, ref) < LOSS_TOL and grad_err(gv, rg) < GRAD_TOL
 
 
 def test_logratio_golden_and_tuples(cuda_lib, golden):

@@ -187,3 +187,88 @@ def test_full_size_properties_1M_x_4096(cuda_lib):
     d2, i2 = tree.query_device(qry[:12], k=25, force_path=1)       # exact scan on a subset
     assert torch.equal(i[:12], i2) and torch.equal(d[:12], d2)
     assert st["n_fallback"] <= Q // 20, st
+
+
+# ---------------------------------------------------------------------------------------------
+# the callers either side of the kernels (files in / pickles out, mining, localization)
+# ---------------------------------------------------------------------------------------------
+def _write_eval_files(tmp_path, R=1500, Q=40, D=96, seed=4):
+    from soft_contrastive_learning_b200 import formats
+    db, qry, ref_xy, query_xy, _ = synth.retrieval_problem(R=R, Q=Q, D=D, seed=seed, extent=200.0)
+    rng = np.random.default_rng(seed)
+    # drive along a path so that greedy subsampling by distance (top-n.py:91-94) actually drops references
+    order = np.argsort(ref_xy[:, 0])
+    db, ref_xy = db[order], ref_xy[order]
+    pca_f = db[rng.choice(R, 400, replace=False)] + 0.01 * rng.standard_normal((400, D)).astype(np.float32)
+    paths = {k: str(tmp_path / (k + ".x")) for k in ("pca", "ref", "query")}
+    formats.save_features(pca_f, paths["pca"] + ".pickle")
+    formats.save_features(db, paths["ref"] + ".pickle")
+    formats.save_features(qry, paths["query"] + ".v1.pickle")
+    for name, xy in (("ref", ref_xy), ("query", query_xy)):
+        formats.save_csv({"t": list(range(len(xy))), "easting": [repr(float(v)) for v in xy[:, 0]],
+                          "northing": [repr(float(v)) for v in xy[:, 1]]}, paths[name] + ".csv")
+    return paths, pca_f, db, qry, ref_xy, query_xy
+
+
+def test_get_top_n_files_in_pickles_out(cuda_lib, tmp_path):
+    from sklearn.decomposition import PCA
+    from soft_contrastive_learning_b200 import evaluation, formats, netvlad
+    paths, pca_f, db, qry, ref_xy, query_xy = _write_eval_files(tmp_path)
+    out_root = str(tmp_path / "top_n")
+    L, Dm = (0.0, 3.0), (32, 64)
+    written = evaluation.get_top_n(paths["pca"] + ".pickle", paths["query"] + ".v1.pickle", paths["ref"] + ".pickle",
+                                   paths["query"] + ".csv", paths["ref"] + ".csv", out_root, N=25, L=L, D=Dm,
+                                   log=lambda *_: None)
+    assert len(written) == 4
+    for d in Dm:
+        pca = PCA(whiten=True, n_components=d).fit(pca_f)                     # the reference's host pipeline, top-n.py:74-77
+        v, m, var = netvlad.pca_from_sklearn(pca)
+        pr, pq = netvlad.pca_project(db, v, m, var), netvlad.pca_project(qry, v, m, var)
+        # P1 eval twin: the device projection is sklearn's transform to fp32 rounding; the neighbour lists below are then
+        # compared on identical projected features, so that they must agree exactly (no near-tie reordering)
+        assert np.allclose(pr, pca.transform(db), rtol=0, atol=2e-5 * np.abs(pr).max())
+        for l in L:
+            f = os.path.join(out_root, "l{}_dim{}".format(l, d), "queryxv1.pickle")   # name rule of top-n.py:84
+            assert f in written
+            got = formats.load_pickle(f)
+            ref = orr.top_n(pr, pq, ref_xy, query_xy, N=25, l=l)
+            assert len(got) == 6 and got[5] == ref[5]
+            assert np.array_equal(np.asarray(got[0]), np.asarray(ref[0]))     # same neighbours, original indices
+            assert np.allclose(got[2], ref[2], rtol=1e-12)
+            assert np.allclose(np.asarray(got[1]), np.asarray(ref[1]), atol=1e-6)
+            assert np.array_equal(np.asarray(got[3]), np.asarray(ref[3])) and np.allclose(got[4], ref[4], atol=1e-6)
+    # second call: everything exists -> nothing recomputed (top-n.py:41-57)
+    assert evaluation.get_top_n(paths["pca"] + ".pickle", paths["query"] + ".v1.pickle", paths["ref"] + ".pickle",
+                                paths["query"] + ".csv", paths["ref"] + ".csv", out_root, N=25, L=L, D=Dm,
+                                log=lambda *_: None) == []
+
+
+def test_mining_cache_full_sort(cuda_lib):
+    from soft_contrastive_learning_b200 import evaluation
+    rng = np.random.default_rng(12)
+    feats = rng.standard_normal((1000, 256)).astype(np.float32)             # MINING_CACHE_SIZE images
+    idx = rng.permutation(50000)[:1000]
+    cache = evaluation.FeatureCache(feats, idx)
+    for index in (int(idx[0]), int(idx[517])):
+        got = cache.sorted_neighbours(index)
+        ref = orr.mining_sorted_neighbours(feats, idx, index, k=1000)
+        assert got[0] == index and [int(g) for g in got] == [int(r) for r in ref]
+    assert cache.sorted_neighbours(-5) is None                               # not cached: train.py:447
+
+
+def test_in_training_localization(cuda_lib):
+    from sklearn.neighbors import KDTree as SkKDTree
+    from soft_contrastive_learning_b200 import evaluation
+    db, qry, ref_xy, query_xy, _ = synth.retrieval_problem(R=3000, Q=100, D=128, seed=6, extent=400.0)
+    ld, li, gd, gi = evaluation.evaluate_localization(db, qry, ref_xy, query_xy, k=5)
+    rd, ri = SkKDTree(db).query(qry, k=5)                                    # train.py:1181-1182
+    od, oi = SkKDTree(ref_xy).query(query_xy, k=1)                           # train.py:1184-1185
+    assert np.array_equal(li, ri) and np.allclose(ld, rd, rtol=1e-12)
+    assert np.array_equal(gi, oi) and np.allclose(gd, od, rtol=1e-12)
+    got = evaluation.localization_summary(li, gd, query_xy, ref_xy)
+    ref = orr.localization_summary(ri, od, query_xy, ref_xy)
+    for rad in (50, 25, 10):
+        assert np.array_equal(got["curves"][rad]["Y"], ref["curves"][rad]["Y"])
+        assert np.array_equal(got["curves"][rad]["optimum"], ref["curves"][rad]["optimum"])
+    for tag, v in ref["scalars"].items():
+        assert abs(got["scalars"][tag] - v) <= 1e-9 * max(1.0, abs(v)), tag
