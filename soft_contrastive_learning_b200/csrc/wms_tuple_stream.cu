@@ -93,6 +93,24 @@ __device__ __forceinline__ void stg_hint(float4* ptr, const float4& v, uint64_t 
                "l"(policy)
                : "memory");
 }
+__device__ __forceinline__ void stg_hint2_if(bool on, float* ptr, float x, float y, uint64_t policy) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t@p st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;\n\t}" ::"l"(ptr),
+      "f"(x), "f"(y), "l"(policy), "r"(int(on))
+      : "memory");
+}
+// tf32 split for the tensor-core backward: hi = rn_tf32(x), lo = x - hi (exact in fp32; the tensor core drops the
+// bits of lo below tf32, 2^-22 of x).  hi*hi + lo*hi + hi*lo is fp32-grade (measured <= 4e-7 of the gradient's max-norm).
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 template <int N>
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
@@ -124,7 +142,7 @@ __device__ __forceinline__ void bwd_tile(const float* __restrict__ ecol, const f
   }
 }
 
-template <int TS, int NW, int CH, bool kPackedGram = true>
+template <int TS, int NW, int CH, bool kPackedGram = true, bool kMmaBwd = false>
 __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) wms_stream_kernel(
     const float* __restrict__ emb, const float* __restrict__ dist, int T, int S, int D, scl_ms_params p,
     float* __restrict__ per_tuple, float* __restrict__ demb, uint32_t* __restrict__ kept, float* __restrict__ loss_out,
@@ -432,7 +450,112 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
     consumer_sync<kSConsumers>();
 
     // ---------------- C. backward: demb = M * E, chunk pairs in descending order ----------------
-    if (need_bwd) {
+    if constexpr (kMmaBwd) { if (need_bwd) {
+      // Tensor-core variant: dE[32 x cols] = M[32 x 8*KT] E[8*KT x cols] on mma.sync.m16n8k8 tf32 with the 3-term
+      // hi/lo split (fp32-grade), which moves the backward's 2.56 M FMAs per tuple off the FP32 pipes (they keep the
+      // Gram of the SM's other CTA) and most of its operand traffic off the shared-memory pipe (7 loads per 8 columns
+      // instead of 25 vector loads per 4).  M's fragments (both 16-row halves, hi and lo) live in registers for the
+      // tuple; a warp owns 32-column groups of a stage: E is loaded and split once per 8 columns and feeds four
+      // independent accumulator chains (main = hi*hi and correction = lo*hi + hi*lo, per row half).
+      // S == 25: 24 rows of E go through the tensor core, row 24 is a rank-1 FFMA update.
+      constexpr int KT = (SG <= 25) ? 3 : 4;
+      const int g = lane >> 2, tg = lane & 3;
+      auto mval = [&](int i, int j) -> float {
+        return (i < S && j < S) ? Mt[j * (2 * HRP) + (i / HR) * HRP + (i % HR)] : 0.0f;
+      };
+      uint32_t ahi[2][KT][4], alo[2][KT][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v = mval(16 * mt + g + 8 * (e & 1), 8 * kt + tg + 4 * (e >> 1));
+            ahi[mt][kt][e] = to_tf32(v);
+            alo[mt][kt][e] = to_tf32(v - __uint_as_float(ahi[mt][kt][e]));
+          }
+      float m24[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) m24[e] = (KT == 3) ? mval(g + 8 * e, 24) : 0.0f;
+      int roff[KT][2];                                  // E rows of the B fragments (clamped into the stage: M is 0 there)
+#pragma unroll
+      for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) roff[kt][h] = min(8 * kt + 4 * h + tg, SG - 1) * kSPitch + g;
+      float* dbase = demb + size_t(t) * S * D + size_t(g) * D + 2 * tg;
+      const size_t D8 = size_t(8) * D;
+      bool stv[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) stv[e] = g + 8 * e < S;
+      auto load_b = [&](const float* Es, int c0, float (&b)[KT][2], float2& e24) {
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+          b[kt][0] = Es[roff[kt][0] + c0];
+          b[kt][1] = Es[roff[kt][1] + c0];
+        }
+        if (KT == 3) e24 = *reinterpret_cast<const float2*>(Es + 24 * kSPitch + c0 + 2 * tg);
+      };
+#pragma unroll 1
+      for (int pr = npairs - 1; pr >= 0; --pr) {
+        const bool hasB = 2 * pr + 1 < nchunks;
+#pragma unroll 1
+        for (int c = 0; c < (hasB ? 2 : 1); ++c) {
+          const int ch = 2 * pr + c;
+          const int stage = (pos + c) % kSStages;
+          const int ncols = min(kSChunk, D - ch * kSChunk);
+          const float* Es = ring + size_t(stage) * STAGE;
+          mbar_wait(&full[stage], ((pos + c) / kSStages) & 1);
+#pragma unroll 1
+          for (int c32 = warp * 32; c32 < ncols; c32 += NW * 32) {
+            const bool whole = c32 + 32 <= ncols;
+            float braw[KT][2];
+            float2 e24 = make_float2(0.0f, 0.0f);
+            load_b(Es, c32, braw, e24);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int c0 = c32 + 8 * u;
+              // round-to-nearest tf32 split on the integer pipe: hi = (b + 0x1000) & ~0x1fff, lo = b - hi
+              uint32_t bhi[KT][2], blo[KT][2];
+#pragma unroll
+              for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  bhi[kt][h] = (__float_as_uint(braw[kt][h]) + 0x1000u) & 0xffffe000u;
+                  blo[kt][h] = __float_as_uint(braw[kt][h] - __uint_as_float(bhi[kt][h]));
+                }
+              float accm[2][4], accc[2][4];
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                accm[mt][0] = m24[2 * mt] * e24.x; accm[mt][1] = m24[2 * mt] * e24.y;
+                accm[mt][2] = m24[2 * mt + 1] * e24.x; accm[mt][3] = m24[2 * mt + 1] * e24.y;
+                accc[mt][0] = accc[mt][1] = accc[mt][2] = accc[mt][3] = 0.0f;
+              }
+              if (u < 3) load_b(Es, c0 + 8, braw, e24);    // next 8 columns in flight behind this tile's MMAs
+#pragma unroll
+              for (int kt = 0; kt < KT; ++kt) {
+                mma_tf32(accc[0], alo[0][kt], bhi[kt][0], bhi[kt][1]);
+                mma_tf32(accc[1], alo[1][kt], bhi[kt][0], bhi[kt][1]);
+                mma_tf32(accm[0], ahi[0][kt], bhi[kt][0], bhi[kt][1]);
+                mma_tf32(accm[1], ahi[1][kt], bhi[kt][0], bhi[kt][1]);
+                mma_tf32(accc[0], ahi[0][kt], blo[kt][0], blo[kt][1]);
+                mma_tf32(accc[1], ahi[1][kt], blo[kt][0], blo[kt][1]);
+              }
+              {
+                const bool cv = whole || c0 + 2 * tg < ncols;
+                float* d = dbase + size_t(ch) * kSChunk + c0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  stg_hint2_if(cv && stv[e], d + e * D8, accm[e >> 1][2 * (e & 1)] + accc[e >> 1][2 * (e & 1)],
+                               accm[e >> 1][2 * (e & 1) + 1] + accc[e >> 1][2 * (e & 1) + 1], pol_drop);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+        }
+        pos += hasB ? 2 : 1;
+      }
+    } } else if (need_bwd) {
       float* dE_t = demb + size_t(t) * S * D;
 #pragma unroll 1
       for (int pr = npairs - 1; pr >= 0; --pr) {
@@ -479,11 +602,11 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int TS, int NW, int CH, bool kPackedGram = true>
+template <int TS, int NW, int CH, bool kPackedGram = true, bool kMmaBwd = false>
 static int stream_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p,
                          float* per_tuple, float* demb, uint32_t* kept, float* loss, unsigned int* counter,
                          cudaStream_t stream) {
-  auto kern = wms_stream_kernel<TS, NW, CH, kPackedGram>;
+  auto kern = wms_stream_kernel<TS, NW, CH, kPackedGram, kMmaBwd>;
   constexpr size_t smem = SSmem<TS, CH>::bytes;
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_relaxed)) {
@@ -507,6 +630,9 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   // keeps the re-read in L2 but leaves the FP32 pipes idle during the scalar phase and the barriers.
   const char* ce = getenv("SCL_WMS_STREAM_CFG");
   const int cfg = ce ? atoi(ce) : 2;
+  // 6: backward on the tensor cores (mma.sync tf32, 3-term split), any S <= 32
+  if (cfg == 6) return stream_launch<TS, 7, 224, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
+  if (cfg == 8) return stream_launch<TS, 8, 256, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   // the wider register tiles (S > 25) need more registers than 16+ warps leave per thread
   if constexpr (TS == 5) {
     if (cfg == 5) return stream_launch<TS, 8, 256, false>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
@@ -518,6 +644,9 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
 }
 
 // SCL_ERR_UNSUPPORTED: small batches go to the cluster kernels (more SMs per tuple).
+int wms_pipe_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
+                    float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream);
+
 int wms_stream_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
                       float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream) {
   const char* env = getenv("SCL_WMS_STREAM");          // 0: never, 1: always, unset: large batches
@@ -525,6 +654,11 @@ int wms_stream_launch(const float* emb, const float* dist, int T, int S, int D, 
   if (mode == 0) return SCL_ERR_UNSUPPORTED;
   if (S < 2 || S > 32 || D < 4 || (D & 3)) return SCL_ERR_UNSUPPORTED;
   if (mode != 1 && T < num_sms()) return SCL_ERR_UNSUPPORTED;
+  const char* ce = getenv("SCL_WMS_STREAM_CFG");
+  if (ce && atoi(ce) == 7) {                           // warp-specialised one-CTA-per-SM pipeline (S <= 25)
+    const int rc = wms_pipe_launch(emb, dist, T, S, D, p, loss, per_tuple, demb, kept, counter, stream);
+    if (rc != SCL_ERR_UNSUPPORTED) return rc;
+  }
   if (S <= 25) return stream_dispatch<5>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   if (S <= 30) return stream_dispatch<6>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   return stream_dispatch<7>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
