@@ -333,7 +333,7 @@ def bench_wms(args, torch, pk, T=4096):
             "dtype": "f32", "config": {"workload": f"wms tuple mode, T={T} S={S} D={D} fp32 (config 1 shape x{T // 32}; inputs 3.4 GB > L2)",
                                        "config1_T32_us_per_launch": ms32 * 1e3, "config1_T32_tuples_per_s": 32 / (ms32 * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                         "peak_source": pk["source"], "kernel": "wms_stream_kernel<5,8,256>",
+                         "peak_source": pk["source"], "kernel": "wms_stream_kernel<5,7,224,packed Gram,tensor-core backward>",
                          "algorithmic_bytes_per_tuple": 2 * S * D * 4 + S * S * 4,
                          # dram read + write of one launch (T=4096) from profiles/r1_ncu_wms.txt: 2.51 + 1.63 GB vs 3.37 GB
                          # algorithmic -- the backward's second read of the tuple misses L2 about half of the time

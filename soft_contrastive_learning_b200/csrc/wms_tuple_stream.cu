@@ -42,14 +42,17 @@ constexpr int kSRed = 4;                                   // cross-warp reducti
 //                                 allocated as 20, which caps the kernel at 96 registers per thread;
 //   <15, 480> one CTA per SM   -- the same with 16 warps in total: 128 registers per thread;
 //   <7, 224>  two CTAs per SM  -- 8 warps in total per CTA: 128 registers per thread instead of 96.
-template <int TS, int CH>
+constexpr int kMpStride = 36;                              // M for the tensor-core backward: [32][36] floats (bank = 4*row + col)
+template <int TS, int CH, bool kMma = false>
 struct SSmem {
-  static constexpr int kSPitch = CH + 4;                   // floats; rows 16 bytes apart in bank space
+  // floats; rows 16 bytes apart in bank space (FFMA2 paths), 48 bytes for the tensor-core backward (its scalar
+  // fragment loads, bank = 12*(lane%4) + lane/4, and the Gram's vector loads are both conflict-free)
+  static constexpr int kSPitch = CH + (kMma ? 12 : 4);
   static constexpr int SG = kSGrid * TS;
   static constexpr int NP = kSTiles * TS * TS;
   static constexpr int HR = (SG + 1) / 2;
   static constexpr int HRP = (HR + 3) / 4 * 4;
-  static constexpr int MT = SG * 2 * HRP;
+  static constexpr int MT = kMma ? 32 * kMpStride : SG * 2 * HRP;
   static constexpr int STAGE = SG * kSPitch;                                       // floats per ring stage
   static constexpr int GW = int(al4(SG * SG));
   static constexpr int WORK = (kSRed * NP > GW + MT) ? kSRed * NP : GW + MT;       // reduction, then Gw | Mt
@@ -99,13 +102,6 @@ __device__ __forceinline__ void stg_hint2_if(bool on, float* ptr, float x, float
       "f"(x), "f"(y), "l"(policy), "r"(int(on))
       : "memory");
 }
-// tf32 split for the tensor-core backward: hi = rn_tf32(x), lo = x - hi (exact in fp32; the tensor core drops the
-// bits of lo below tf32, 2^-22 of x).  hi*hi + lo*hi + hi*lo is fp32-grade (measured <= 4e-7 of the gradient's max-norm).
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -147,9 +143,9 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
     const float* __restrict__ emb, const float* __restrict__ dist, int T, int S, int D, scl_ms_params p,
     float* __restrict__ per_tuple, float* __restrict__ demb, uint32_t* __restrict__ kept, float* __restrict__ loss_out,
     unsigned int* __restrict__ done_counter) {
-  using L = SSmem<TS, CH>;
+  using L = SSmem<TS, CH, kMmaBwd>;
   constexpr int SG = L::SG, NP = L::NP, HR = L::HR, HRP = L::HRP, STAGE = L::STAGE;
-  constexpr int kSWarps = NW, kSConsumers = NW * 32, kSThreads = NW * 32 + 32, kSChunk = CH, kSPitch = CH + 4;
+  constexpr int kSWarps = NW, kSConsumers = NW * 32, kSThreads = NW * 32 + 32, kSChunk = CH, kSPitch = L::kSPitch;
   constexpr int RPW = (32 + NW - 1) / NW;            // anchor rows per warp in phase B (S <= 32)
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -433,8 +429,11 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
       for (int k = 0; k < RPW; ++k) {
         const int i = warp + kSWarps * k;
         const float c = cpart[k] * __shfl_sync(0xffffffffu, nflag_j, rvalid[k] ? i : 0);
-        if (rvalid[k] && jvalid) {
-          const float w = (i == lane) ? wij[k] - c : wij[k];
+        const float w = (i == lane) ? wij[k] - c : wij[k];
+        if constexpr (kMmaBwd) {
+          // plain [32][kMpStride] layout, zero outside S x S (the padded tensor-core tiles multiply it)
+          if (i < 32) Mt[i * kMpStride + lane] = (rvalid[k] && jvalid) ? invn_i[k] * w * invn_j * invT : 0.0f;
+        } else if (rvalid[k] && jvalid) {
           const int h = i / HR, r = i - h * HR;
           Mt[lane * (2 * HRP) + h * HRP + r] = invn_i[k] * w * invn_j * invT;
         }
@@ -451,18 +450,19 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
 
     // ---------------- C. backward: demb = M * E, chunk pairs in descending order ----------------
     if constexpr (kMmaBwd) { if (need_bwd) {
-      // Tensor-core variant: dE[32 x cols] = M[32 x 8*KT] E[8*KT x cols] on mma.sync.m16n8k8 tf32 with the 3-term
-      // hi/lo split (fp32-grade), which moves the backward's 2.56 M FMAs per tuple off the FP32 pipes (they keep the
-      // Gram of the SM's other CTA) and most of its operand traffic off the shared-memory pipe (7 loads per 8 columns
-      // instead of 25 vector loads per 4).  M's fragments (both 16-row halves, hi and lo) live in registers for the
-      // tuple; a warp owns 32-column groups of a stage: E is loaded and split once per 8 columns and feeds four
-      // independent accumulator chains (main = hi*hi and correction = lo*hi + hi*lo, per row half).
-      // S == 25: 24 rows of E go through the tensor core, row 24 is a rank-1 FFMA update.
+      // Tensor-core backward: dE[32 x cols] = M[32 x 8*KT] E[8*KT x cols] on mma.sync.m16n8k8 tf32 with the 3-term
+      // hi/lo split (hi*hi + lo*hi + hi*lo; the dropped lo*lo is 2^-22 of a product: fp32-grade).  It moves the
+      // backward's 2.56 M FMAs per tuple off the FP32 pipes (they keep the Gram of the SM's other CTA) and most of its
+      // operand traffic off the shared-memory pipe (7 loads per 8 columns instead of 25 vector loads per 4).  M's
+      // fragments (both 16-row halves, hi and lo) live in registers for the tuple; a warp owns 32-column groups of a
+      // stage: E is loaded and split once per 8 columns and feeds four independent accumulator chains (main = hi*hi
+      // and correction = lo*hi + hi*lo, per row half).  S == 25: 24 rows of E go through the tensor core, row 24 is
+      // a rank-1 FFMA update folded into the accumulator initialisation.
+      // Measured alternatives (B200, T = 4096): the transposed product (E^T as the 16-row operand, 27 instead of 36
+      // MMAs per 16 columns, 4-byte stores) 1.03 ms; interleaved even/odd column tiles with 16-byte stores 0.98 ms;
+      // this form 0.96 ms; the FFMA2 backward 1.07 ms.
       constexpr int KT = (SG <= 25) ? 3 : 4;
       const int g = lane >> 2, tg = lane & 3;
-      auto mval = [&](int i, int j) -> float {
-        return (i < S && j < S) ? Mt[j * (2 * HRP) + (i / HR) * HRP + (i % HR)] : 0.0f;
-      };
       uint32_t ahi[2][KT][4], alo[2][KT][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -470,13 +470,13 @@ __global__ void __launch_bounds__(NW * 32 + 32, ((TS == 5 && NW <= 8) ? 2 : 1)) 
         for (int kt = 0; kt < KT; ++kt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float v = mval(16 * mt + g + 8 * (e & 1), 8 * kt + tg + 4 * (e >> 1));
-            ahi[mt][kt][e] = to_tf32(v);
-            alo[mt][kt][e] = to_tf32(v - __uint_as_float(ahi[mt][kt][e]));
+            const float v = Mt[(16 * mt + g + 8 * (e & 1)) * kMpStride + 8 * kt + tg + 4 * (e >> 1)];
+            ahi[mt][kt][e] = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+            alo[mt][kt][e] = __float_as_uint(v - __uint_as_float(ahi[mt][kt][e]));
           }
       float m24[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) m24[e] = (KT == 3) ? mval(g + 8 * e, 24) : 0.0f;
+      for (int e = 0; e < 4; ++e) m24[e] = (KT == 3) ? Mt[(g + 8 * e) * kMpStride + 24] : 0.0f;
       int roff[KT][2];                                  // E rows of the B fragments (clamped into the stage: M is 0 there)
 #pragma unroll
       for (int kt = 0; kt < KT; ++kt)
@@ -607,7 +607,7 @@ static int stream_launch(const float* emb, const float* dist, int T, int S, int 
                          float* per_tuple, float* demb, uint32_t* kept, float* loss, unsigned int* counter,
                          cudaStream_t stream) {
   auto kern = wms_stream_kernel<TS, NW, CH, kPackedGram, kMmaBwd>;
-  constexpr size_t smem = SSmem<TS, CH>::bytes;
+  constexpr size_t smem = SSmem<TS, CH, kMmaBwd>::bytes;
   static std::atomic<int> configured{0};
   if (!configured.load(std::memory_order_relaxed)) {
     SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -625,14 +625,16 @@ template <int TS>
 static int stream_dispatch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p,
                            float* per_tuple, float* demb, uint32_t* kept, float* loss, unsigned int* counter,
                            cudaStream_t stream) {
-  // 1: <16,512>, 2: <8,256> x 2 CTAs/SM (default), 3: <15,480>.  Measured on B200, T = 4096, S = 25, D = 4096:
-  // cfg 2 1.04-1.08 ms (HBM reads 2.5 GB), cfg 3 1.13 ms (1.98 GB), cfg 1 1.30 ms (1.89 GB): one tuple pipeline per SM
-  // keeps the re-read in L2 but leaves the FP32 pipes idle during the scalar phase and the barriers.
+  // FFMA2 backward: 1: <16,512>, 2: <8,256> x 2 CTAs/SM, 3: <15,480>, 4: <7,224> x 2, 5: as 2 with a scalar-FFMA Gram.
+  // Tensor-core backward: 6: <7,224> x 2 CTAs/SM (default for S <= 25).  Measured on B200, T = 4096, S = 25, D = 4096:
+  // cfg 6 0.96 ms, cfg 2 1.04-1.08 ms (HBM reads 2.5 GB), cfg 4 1.12 ms, cfg 3 1.13 ms (1.98 GB), cfg 1 1.30 ms (1.89 GB):
+  // one tuple pipeline per SM keeps the re-read in L2 but leaves the pipes idle during the scalar phase and the barriers.
+  // Also measured and dropped: tensor-core backward with 6 warps x 192 columns x 5 stages 1.11 ms, with 8 warps x 256
+  // columns at 96 registers (spills) 1.08 ms; a one-CTA-per-SM warp-specialised pipeline (Gram warps / weight warps,
+  // 168 registers) 1.63 ms -- with this much register tile per warp, warps per SM are what hides the latencies.
   const char* ce = getenv("SCL_WMS_STREAM_CFG");
-  const int cfg = ce ? atoi(ce) : 2;
-  // 6: backward on the tensor cores (mma.sync tf32, 3-term split), any S <= 32
+  const int cfg = ce ? atoi(ce) : (TS == 5 ? 6 : 2);
   if (cfg == 6) return stream_launch<TS, 7, 224, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
-  if (cfg == 8) return stream_launch<TS, 8, 256, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   // the wider register tiles (S > 25) need more registers than 16+ warps leave per thread
   if constexpr (TS == 5) {
     if (cfg == 5) return stream_launch<TS, 8, 256, false>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
@@ -644,9 +646,6 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
 }
 
 // SCL_ERR_UNSUPPORTED: small batches go to the cluster kernels (more SMs per tuple).
-int wms_pipe_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
-                    float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream);
-
 int wms_stream_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
                       float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream) {
   const char* env = getenv("SCL_WMS_STREAM");          // 0: never, 1: always, unset: large batches
@@ -654,11 +653,6 @@ int wms_stream_launch(const float* emb, const float* dist, int T, int S, int D, 
   if (mode == 0) return SCL_ERR_UNSUPPORTED;
   if (S < 2 || S > 32 || D < 4 || (D & 3)) return SCL_ERR_UNSUPPORTED;
   if (mode != 1 && T < num_sms()) return SCL_ERR_UNSUPPORTED;
-  const char* ce = getenv("SCL_WMS_STREAM_CFG");
-  if (ce && atoi(ce) == 7) {                           // warp-specialised one-CTA-per-SM pipeline (S <= 25)
-    const int rc = wms_pipe_launch(emb, dist, T, S, D, p, loss, per_tuple, demb, kept, counter, stream);
-    if (rc != SCL_ERR_UNSUPPORTED) return rc;
-  }
   if (S <= 25) return stream_dispatch<5>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   if (S <= 30) return stream_dispatch<6>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   return stream_dispatch<7>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);

@@ -98,8 +98,6 @@ def test_wms_cluster_sizes_agree(cuda_lib, cluster, monkeypatch):
 # ring stage), odd S (distance block not 16-byte sized), S = 32 (widest register tile) and a forward-only call
 WMS_PATHS = {"stream": {"SCL_WMS_STREAM": "1", "SCL_WMS_STREAM_CFG": "2"}, "resident": {"SCL_WMS_STREAM": "0"},
              "stream_mma": {"SCL_WMS_STREAM": "1", "SCL_WMS_STREAM_CFG": "6"},
-             "stream_mma8": {"SCL_WMS_STREAM": "1", "SCL_WMS_STREAM_CFG": "8"},
-             "pipe": {"SCL_WMS_STREAM": "1", "SCL_WMS_STREAM_CFG": "7"},
              "chunked": {"SCL_WMS_STREAM": "0", "SCL_WMS_CHUNKED": "1"}}
 
 
@@ -139,10 +137,10 @@ def test_wms_kernel_paths_variants_and_forward_only(cuda_lib, monkeypatch, golde
     assert rel(float(l), float(g["loss_exp_ms_mine"])) < LOSS_TOL
 
 
-@pytest.mark.parametrize("cfg", ["2", "6", "7"])
+@pytest.mark.parametrize("cfg", ["2", "6"])
 def test_wms_stream_large_batch_matches_small_batch_kernels(cuda_lib, monkeypatch, cfg):
-    """T = 600 tuples (several per persistent CTA): the streaming kernels (FFMA2 backward, tensor-core backward,
-    warp-specialised pipeline) against the cluster kernel, per tuple."""
+    """T = 600 tuples (several per persistent CTA): the streaming kernels (FFMA2 backward, tensor-core backward)
+    against the cluster kernel, per tuple."""
     monkeypatch.setenv("SCL_WMS_STREAM_CFG", cfg)
     from soft_contrastive_learning_b200 import losses
     emb, dist, _ = synth.wms_batch(T=40, P=12, N=12, D=1024, seed=21)
