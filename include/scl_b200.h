@@ -167,6 +167,15 @@ int scl_pca_fwd(const float* x, const float* v, const float* m, const float* var
 int scl_pca_bwd(const float* dy, const float* v, const float* var, int B, int Din, int Dout,
                 float* dx, void* workspace, size_t workspace_bytes, scl_stream_t stream);
 
+/* P0: the data-sized steps of the PCA *fit*, `PCA(whiten=True, n_components=d).fit(pca_f)` at
+ * evaluation/top-n.py:74-75 (training twin: the incremental PCA of train/train.py:1039-1053, source absent upstream).
+ *   mean[D] = column means of x [n,D] (float64 accumulation, fixed order), xc [n,D] = x - mean (may be NULL).
+ * The fit's contractions (Gram xc xc^T when n <= D, covariance xc^T xc otherwise; back-projection xc^T U) are
+ * scl_gemm_tf32 calls; the caller solves the small symmetric eigenproblem in between (see netvlad.pca_fit). */
+int scl_pca_center_workspace_bytes(int n, int D, size_t* bytes);
+int scl_pca_center(const float* x, int n, int D, float* mean, float* xc, void* workspace, size_t workspace_bytes,
+                   scl_stream_t stream);
+
 /* Precision of the tensor-core contractions (PCA, flat-mode Gram and its backward): 0 = fp32-grade 3xTF32 (default:
  * meets the 1e-5 tolerance of the reference's fp32 graph), 1 = one TF32 pass (relative error ~1e-3, three times the
  * throughput).  Process-wide setting. */

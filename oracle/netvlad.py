@@ -49,6 +49,21 @@ def pca_project(x, v, m, var):
     return ((x - m) @ v.T) / torch.sqrt(var)
 
 
+def pca_fit(x, n_components):
+    """``PCA(whiten=True, n_components=d).fit(x)`` (evaluation/top-n.py:74-75) restated in float64 NumPy after
+    scikit-learn's exact solver (third-party, version unpinned by the reference; ``PCA._fit_full``): centre by the
+    column mean, thin SVD, ``svd_flip(u_based_decision=False)`` (largest-magnitude entry of every row of V^T made
+    positive), ``explained_variance_ = S**2 / (n - 1)``.  Returns (components_ [d,D], mean_ [D], explained_variance_ [d])."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.shape[0]
+    mean = x.mean(axis=0)
+    _, S, Vt = np.linalg.svd(x - mean, full_matrices=False)
+    idx = np.argmax(np.abs(Vt), axis=1)
+    Vt = Vt * np.sign(Vt[np.arange(Vt.shape[0]), idx])[:, None]
+    d = int(n_components)
+    return Vt[:d], mean, (S[:d] ** 2) / (n - 1)
+
+
 def sklearn_pca_params(pca):
     """Map a fitted sklearn PCA(whiten=True) (top-n.py:74-75) onto the (v, m, var) of the train-time op."""
     return (np.asarray(pca.components_), np.asarray(pca.mean_), np.asarray(pca.explained_variance_))

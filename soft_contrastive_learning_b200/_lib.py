@@ -64,6 +64,8 @@ PROTOTYPES = {
     "scl_pca_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, _SIZE_P]),
     "scl_pca_fwd": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_pca_bwd": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "scl_pca_center_workspace_bytes": (C.c_int, [C.c_int, C.c_int, _SIZE_P]),
+    "scl_pca_center": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_set_gemm_precision": (C.c_int, [C.c_int]),
     "scl_get_gemm_precision": (C.c_int, []),
     "scl_gemm_tf32": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -482,6 +482,78 @@ extern "C" int scl_pca_fwd(const float* x, const float* v, const float* m, const
   return gemm_launch(g, stream);
 }
 
+// ---------------------------------------------------------------------------------------------
+// P0: the data-sized steps of PCA(whiten=True).fit (evaluation/top-n.py:74-75): column means
+// and the centred copy.  The contractions of the fit (Gram X_c X_c^T or covariance X_c^T X_c, and the back-projection
+// X_c^T U) run on scl_gemm_tf32; the small symmetric eigenproblem stays with the caller.
+// Column sums are accumulated in float64 per row slice (coalesced: a warp reads 32 consecutive columns of a row) and
+// the slices are added in a fixed order: deterministic.
+constexpr int kPcaSlices = 16;
+__global__ void __launch_bounds__(256) pca_colsum_kernel(const float* __restrict__ x, int n, int D, double* __restrict__ part) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  const int rows = (n + kPcaSlices - 1) / kPcaSlices;
+  const int r0 = blockIdx.y * rows, r1 = min(n, r0 + rows);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    const float v0 = ldg_stream(x + size_t(r) * D + c), v1 = ldg_stream(x + size_t(r + 1) * D + c);
+    const float v2 = ldg_stream(x + size_t(r + 2) * D + c), v3 = ldg_stream(x + size_t(r + 3) * D + c);
+    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+  }
+  for (; r < r1; ++r) a0 += ldg_stream(x + size_t(r) * D + c);
+  part[size_t(blockIdx.y) * D + c] = (a0 + a1) + (a2 + a3);
+}
+__global__ void __launch_bounds__(256) pca_mean_kernel(const double* __restrict__ part, int n, int D, float* __restrict__ mean) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  double a = 0.0;
+#pragma unroll
+  for (int s = 0; s < kPcaSlices; ++s) a += part[size_t(s) * D + c];
+  mean[c] = float(a / double(n));
+}
+__global__ void __launch_bounds__(256) pca_center_any_kernel(const float* __restrict__ x, const float* __restrict__ m,
+                                                             long long total, int D, float* __restrict__ xc) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    xc[i] = ldg_stream(x + i) - __ldg(m + (i % D));
+}
+
+extern "C" int scl_pca_center_workspace_bytes(int n, int D, size_t* bytes) {
+  if (!bytes || n < 1 || D < 1) return SCL_ERR_BAD_ARG;
+  *bytes = carve_bytes(size_t(kPcaSlices) * D, sizeof(double));
+  return SCL_OK;
+}
+
+extern "C" int scl_pca_center(const float* x, int n, int D, float* mean, float* xc, void* workspace, size_t workspace_bytes,
+                              scl_stream_t stream_) {
+  if (!x || !mean) return SCL_ERR_BAD_ARG;
+  if (n < 1 || D < 1) return SCL_ERR_BAD_SHAPE;
+  int rc = check_device();
+  if (rc) return rc;
+  size_t need = 0;
+  scl_pca_center_workspace_bytes(n, D, &need);
+  if (!workspace || workspace_bytes < need) return SCL_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255u) return SCL_ERR_ALIGN;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  Carver c(workspace, workspace_bytes);
+  double* part = c.take<double>(size_t(kPcaSlices) * D);
+  pca_colsum_kernel<<<dim3((D + 255) / 256, kPcaSlices), 256, 0, stream>>>(x, n, D, part);
+  SCL_LAUNCH_CHECK();
+  pca_mean_kernel<<<(D + 255) / 256, 256, 0, stream>>>(part, n, D, mean);
+  SCL_LAUNCH_CHECK();
+  if (xc) {
+    const long long total = (long long)n * D;
+    if (D % 4 == 0 && aligned16(x) && aligned16(xc) && aligned16(mean)) {
+      const long long n4 = total / 4;
+      pca_center_kernel<<<unsigned(std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 16)), 256, 0, stream>>>(x, mean, n4, D / 4, xc);
+    } else {
+      pca_center_any_kernel<<<unsigned(std::min<long long>((total + 255) / 256, (long long)num_sms() * 16)), 256, 0, stream>>>(x, mean, total, D, xc);
+    }
+    SCL_LAUNCH_CHECK();
+  }
+  return SCL_OK;
+}
+
 extern "C" int scl_pca_bwd(const float* dy, const float* v, const float* var, int B, int Din, int Dout, float* dx,
                            void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
   if (!dy || !v || !var || !dx) return SCL_ERR_BAD_ARG;

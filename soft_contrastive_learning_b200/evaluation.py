@@ -6,8 +6,9 @@
 * ``localization_summary``  train/train.py:360-386       -- "% localized within x m" curves, AUC@Top1, %<rad@Top1
 
 The neighbour searches, the PCA projection, the geographic bookkeeping and the recall curves run on the GPU
-(``retrieval.KDTree``, ``netvlad.pca_project``, ``retrieval.geo_topn``, ``retrieval.recall_curves``); only file IO, the
-PCA *fit* (scikit-learn, exactly the reference's call) and list bookkeeping stay on the host.
+(``retrieval.KDTree``, ``netvlad.pca_project``, ``retrieval.geo_topn``, ``retrieval.recall_curves``), and so does the
+PCA *fit* (``netvlad.pca_fit``: one exact fit at max(D), every smaller d is a prefix of it; ``pca_solver="sklearn"``
+makes the reference's own library call instead); only file IO and list bookkeeping stay on the host.
 """
 from __future__ import annotations
 
@@ -17,7 +18,7 @@ import numpy as np
 import torch
 
 from . import formats
-from .netvlad import pca_from_sklearn, pca_project
+from .netvlad import pca_fit, pca_from_sklearn, pca_project
 from .retrieval import KDTree, geo_topn, recall_curves, top_n
 
 # top-n.py:34-39: the sweep used for the published checkpoints, and the default cell
@@ -32,7 +33,7 @@ def _cell_pickle(out_root, query_lv_pickle, l, d):
 
 
 def get_top_n(pca_lv_pickle, query_lv_pickle, ref_lv_pickle, query_csv, ref_csv, out_root, N=25, L=(0.0,), D=(256,),
-              log=print):
+              log=print, pca_solver="gpu"):
     """evaluation/top-n.py:23-119 for the sweep ``L`` x ``D`` (defaults: the reference's single cell l=0.0, d=256).
 
     Skips everything when all cells exist (:41-57) and single cells that exist (:87-89) or have fewer than N
@@ -40,7 +41,8 @@ def get_top_n(pca_lv_pickle, query_lv_pickle, ref_lv_pickle, query_csv, ref_csv,
     if all(os.path.exists(_cell_pickle(out_root, query_lv_pickle, l, d)[1]) for l in L for d in D):
         log("Skipping complete {}".format(query_lv_pickle))
         return []
-    from sklearn.decomposition import PCA                                              # the reference's fit, :74-75
+    if pca_solver not in ("gpu", "sklearn"):
+        raise ValueError("pca_solver must be 'gpu' or 'sklearn'")
 
     full_ref_xy = formats.get_xy(formats.load_csv(ref_csv))                            # :59-62
     full_query_xy = formats.get_xy(formats.load_csv(query_csv))
@@ -48,10 +50,15 @@ def get_top_n(pca_lv_pickle, query_lv_pickle, ref_lv_pickle, query_csv, ref_csv,
     full_ref_f = formats.load_features(ref_lv_pickle)
     full_query_f = formats.load_features(query_lv_pickle)
     written = []
+    if pca_solver == "gpu":                                                            # :74-75, exact, once for the sweep
+        v_all, m_all, var_all = pca_fit(pca_f, max(D))
     for d in D:
         log(d)
-        pca = PCA(whiten=True, n_components=d).fit(pca_f)                              # :74-75
-        v, m, var = pca_from_sklearn(pca)
+        if pca_solver == "gpu":
+            v, m, var = v_all[:d], m_all, var_all[:d]
+        else:
+            from sklearn.decomposition import PCA
+            v, m, var = pca_from_sklearn(PCA(whiten=True, n_components=d).fit(pca_f))  # the reference's call, :74-75
         with torch.no_grad():                                                          # :76-77 on the tcgen05 GEMM
             pca_ref_f = pca_project(full_ref_f, v, m, var)
             pca_query_f = pca_project(full_query_f, v, m, var)

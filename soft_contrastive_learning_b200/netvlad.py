@@ -115,6 +115,81 @@ def pca_project(full_out, v, m, var):
     return out.cpu().numpy() if isinstance(full_out, np.ndarray) else out
 
 
+def _gemm(A, B, M, N, K, a_mn, b_mn, precision=0):
+    """C[M,N] = A . B^T on the tcgen05 TF32 engine (csrc/tc_gemm.cu); leading dimensions from the tensors' strides."""
+    ldc = (N + 3) // 4 * 4
+    out = torch.empty((M, ldc), dtype=torch.float32, device=A.device)
+    check(lib().scl_gemm_tf32(_p(A), _p(B), _p(out), M, N, K, A.stride(0), B.stride(0), ldc, int(a_mn), int(b_mn), None,
+                              int(precision), _stream()), "scl_gemm_tf32")
+    return out[:, :N]
+
+
+def _pad_cols(t, mult=4):
+    """A copy of the 2-D tensor whose row pitch is a multiple of `mult` floats (zero padding), viewed at its own width."""
+    n, w = t.shape
+    wp = (w + mult - 1) // mult * mult
+    if wp == w and t.is_contiguous():
+        return t
+    buf = torch.zeros((n, wp), dtype=torch.float32, device=t.device)
+    buf[:, :w] = t
+    return buf[:, :w]
+
+
+def pca_fit(features, n_components, return_device=False):
+    """``PCA(whiten=True, n_components=d).fit(pca_f)`` of /root/reference/evaluation/top-n.py:74-75 on the GPU
+    (SURVEY 8f row 4), as the exact truncated decomposition (scikit-learn's ``svd_solver='full'`` result; the
+    reference's default ``'auto'`` resolves to the randomized solver with an unseeded RNG for these sizes, i.e. to an
+    approximation of what is computed here).  Returns ``(v, m, var)`` = (components_ [d,D], mean_ [D],
+    explained_variance_ [d]) ready for :func:`pca_project`.
+
+    mean and centring: ``scl_pca_center``; n <= D: Gram ``G = Xc Xc^T`` [n,n] and the back-projection
+    ``V = (U / sigma)^T Xc`` on the fp32-grade tcgen05 GEMM, with ``G = U diag(sigma^2) U^T``; n > D: covariance
+    ``Xc^T Xc`` [D,D] on the same GEMM.  Only the small symmetric eigenproblem (n x n or D x D, float64) is a
+    library call (``torch.linalg.eigh``).  Signs follow scikit-learn's ``svd_flip(u_based_decision=False)``: the
+    largest-magnitude entry of every component is positive.  ``explained_variance_ = sigma^2 / (n - 1)``."""
+    x = features if isinstance(features, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = _f32(x if x.is_cuda else x.to(dev))
+    n, D = x.shape
+    d = int(n_components)
+    if not 1 <= d <= min(n, D):
+        raise ValueError(f"n_components={d} must be between 1 and min(n_samples, n_features)={min(n, D)}")
+    nbytes = C.c_size_t()
+    check(lib().scl_pca_center_workspace_bytes(n, D, C.byref(nbytes)), "scl_pca_center_workspace_bytes")
+    ws = _ws(nbytes.value, x.device)
+    mean = torch.empty(D, dtype=torch.float32, device=x.device)
+    Dp = (D + 3) // 4 * 4
+    xc_buf = torch.zeros((n, Dp), dtype=torch.float32, device=x.device) if Dp != D else torch.empty((n, D), dtype=torch.float32, device=x.device)
+    if Dp == D:
+        check(lib().scl_pca_center(_p(x), n, D, _p(mean), _p(xc_buf), _p(ws), ws.numel(), _stream()), "scl_pca_center")
+        xc = xc_buf
+    else:                                         # ragged D: centre densely, then re-pitch for the TMA path
+        dense = torch.empty((n, D), dtype=torch.float32, device=x.device)
+        check(lib().scl_pca_center(_p(x), n, D, _p(mean), _p(dense), _p(ws), ws.numel(), _stream()), "scl_pca_center")
+        xc_buf[:, :D] = dense
+        xc = xc_buf[:, :D]
+    if n <= D:
+        G = _gemm(xc, xc, n, n, D, False, False)                           # Xc Xc^T
+        lam, U = torch.linalg.eigh(G.double())                             # ascending
+        lam = lam.flip(0)[:d].clamp_min(0.0)
+        U = U.flip(1)[:, :d]
+        sigma = lam.sqrt()
+        Us = _pad_cols((U / sigma.clamp_min(1e-300)).float())              # [n,d]
+        comps = _gemm(Us, xc, d, D, n, True, True)                         # A(m,k) = Us[k,m], B(j,k) = Xc[k,j]
+    else:
+        Cv = _gemm(xc, xc, D, D, n, True, True)                            # Xc^T Xc
+        lam, V = torch.linalg.eigh(Cv.double())
+        lam = lam.flip(0)[:d].clamp_min(0.0)
+        comps = V.flip(1)[:, :d].t().float()
+    comps = comps.contiguous()
+    idx = comps.abs().argmax(dim=1, keepdim=True)
+    comps = comps * torch.sign(torch.gather(comps, 1, idx))
+    var = (lam / max(n - 1, 1)).float()
+    if return_device:
+        return comps, mean, var
+    return comps.cpu().numpy(), mean.cpu().numpy(), var.cpu().numpy()
+
+
 def pca_from_sklearn(pca):
     """(v, m, var) of a fitted ``sklearn.decomposition.PCA(whiten=True)`` (evaluation/top-n.py:74-75):
     pca.transform(x) == pca_project(x, components_, mean_, explained_variance_)."""

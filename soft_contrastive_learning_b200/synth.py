@@ -98,3 +98,13 @@ def netvlad_problem(B=2, H=3, W=4, C=512, K=64, Dout=128, seed=42):
     m = (0.01 * rng.standard_normal(Din)).astype(np.float32)
     var = rng.uniform(0.5, 2.0, size=Dout).astype(np.float32)
     return x, aw, cc, V, m, var
+
+
+def pca_features(n, D, rank=40, seed=42, dtype=np.float64):
+    """Features for the PCA fit: `rank` orthogonal directions with geometrically decaying strength over
+    small isotropic noise and a non-zero mean, so the leading components are well separated."""
+    rng = np.random.default_rng(seed)
+    basis = np.linalg.qr(rng.standard_normal((D, rank)))[0].T
+    strength = 10.0 * 0.8 ** np.arange(rank)
+    x = (rng.standard_normal((n, rank)) * strength) @ basis + 0.05 * rng.standard_normal((n, D)) + rng.standard_normal(D)
+    return x.astype(dtype)

@@ -101,3 +101,23 @@ def test_pca_tensor_core_matches_simt_fallback(cuda_lib, monkeypatch):
     monkeypatch.setenv("SCL_GEMM_SIMT", "1")
     b = netvlad.pca_project(x, V, m, var)
     assert relmax(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("n,D,d", [(300, 1024, 16), (512, 130, 16), (200, 4096, 12)])
+def test_pca_fit_matches_oracle_and_sklearn(cuda_lib, n, D, d):
+    """PCA(whiten=True, n_components=d).fit on the GPU (Gram route n <= D, covariance route n > D,
+    ragged D) against the float64 oracle and scikit-learn's exact solver; the fitted triple then drives pca_project.
+    d stays inside the components that stand clear of the noise floor of the synthetic spectrum: below it the
+    eigen-gaps vanish and any two solvers rotate the basis differently."""
+    from sklearn.decomposition import PCA
+    from soft_contrastive_learning_b200 import netvlad
+    X = synth.pca_features(n, D, rank=40, seed=17, dtype=np.float32)
+    v, m, var = netvlad.pca_fit(X, d)
+    vo, mo, varo = onv.pca_fit(X, d)
+    assert v.shape == (d, D) and m.shape == (D,) and var.shape == (d,)
+    assert np.allclose(m, mo, rtol=1e-6, atol=1e-6)
+    assert np.allclose(var, varo, rtol=2e-5)
+    assert np.abs(v - vo).max() < 2e-4                      # unit-norm rows; eigenvector error ~ eps * |G| / gap
+    pca = PCA(whiten=True, n_components=d, svd_solver="full").fit(X.astype(np.float64))
+    got = netvlad.pca_project(X[:64], v, m, var)
+    assert np.allclose(got, pca.transform(X[:64].astype(np.float64)), rtol=1e-3, atol=1e-3)

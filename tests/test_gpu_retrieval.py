@@ -210,7 +210,8 @@ def _write_eval_files(tmp_path, R=1500, Q=40, D=96, seed=4):
     return paths, pca_f, db, qry, ref_xy, query_xy
 
 
-def test_get_top_n_files_in_pickles_out(cuda_lib, tmp_path):
+@pytest.mark.parametrize("pca_solver", ["sklearn", "gpu"])
+def test_get_top_n_files_in_pickles_out(cuda_lib, tmp_path, pca_solver):
     from sklearn.decomposition import PCA
     from soft_contrastive_learning_b200 import evaluation, formats, netvlad
     paths, pca_f, db, qry, ref_xy, query_xy = _write_eval_files(tmp_path)
@@ -218,15 +219,23 @@ def test_get_top_n_files_in_pickles_out(cuda_lib, tmp_path):
     L, Dm = (0.0, 3.0), (32, 64)
     written = evaluation.get_top_n(paths["pca"] + ".pickle", paths["query"] + ".v1.pickle", paths["ref"] + ".pickle",
                                    paths["query"] + ".csv", paths["ref"] + ".csv", out_root, N=25, L=L, D=Dm,
-                                   log=lambda *_: None)
+                                   log=lambda *_: None, pca_solver=pca_solver)
     assert len(written) == 4
+    if pca_solver == "gpu":
+        v_all, m_all, var_all = netvlad.pca_fit(pca_f, max(Dm))               # 8f row 4: one exact fit for the sweep
     for d in Dm:
-        pca = PCA(whiten=True, n_components=d).fit(pca_f)                     # the reference's host pipeline, top-n.py:74-77
-        v, m, var = netvlad.pca_from_sklearn(pca)
+        if pca_solver == "gpu":
+            v, m, var = v_all[:d], m_all, var_all[:d]
+            pca = PCA(whiten=True, n_components=d, svd_solver="full").fit(pca_f.astype(np.float64))
+            assert np.allclose(var, pca.explained_variance_, rtol=1e-4)
+        else:
+            pca = PCA(whiten=True, n_components=d).fit(pca_f)                 # the reference's host pipeline, top-n.py:74-77
+            v, m, var = netvlad.pca_from_sklearn(pca)
         pr, pq = netvlad.pca_project(db, v, m, var), netvlad.pca_project(qry, v, m, var)
         # P1 eval twin: the device projection is sklearn's transform to fp32 rounding; the neighbour lists below are then
         # compared on identical projected features, so that they must agree exactly (no near-tie reordering)
-        assert np.allclose(pr, pca.transform(db), rtol=0, atol=2e-5 * np.abs(pr).max())
+        if pca_solver == "sklearn":
+            assert np.allclose(pr, pca.transform(db), rtol=0, atol=2e-5 * np.abs(pr).max())
         for l in L:
             f = os.path.join(out_root, "l{}_dim{}".format(l, d), "queryxv1.pickle")   # name rule of top-n.py:84
             assert f in written
@@ -240,7 +249,7 @@ def test_get_top_n_files_in_pickles_out(cuda_lib, tmp_path):
     # second call: everything exists -> nothing recomputed (top-n.py:41-57)
     assert evaluation.get_top_n(paths["pca"] + ".pickle", paths["query"] + ".v1.pickle", paths["ref"] + ".pickle",
                                 paths["query"] + ".csv", paths["ref"] + ".csv", out_root, N=25, L=L, D=Dm,
-                                log=lambda *_: None) == []
+                                log=lambda *_: None, pca_solver=pca_solver) == []
 
 
 def test_mining_cache_full_sort(cuda_lib):

@@ -6,6 +6,7 @@ import torch
 from oracle import losses as ol
 from oracle import netvlad as onv
 from oracle import retrieval as orr
+from soft_contrastive_learning_b200 import synth
 
 WMS_VARIANTS = {
     "exp_ms_mine": dict(wfunction="exp", sumfunction="ms", ms_mining=True),
@@ -182,3 +183,16 @@ def test_wms_masks_are_float32_like_the_reference(golden):
     assert (mp64 > 0).all()            # which is why a float64 transcription of the masks would be a different loss
     g = golden("wms_flat_S25_D64")
     assert int(g["keptpos_exp_ms_nomine"].sum()) < 25 * 24
+
+
+@pytest.mark.parametrize("n,D", [(120, 40), (60, 200)])
+def test_pca_fit_oracle_matches_sklearn_full_solver(n, D):
+    """the oracle's PCA fit against the reference's library call with the exact solver."""
+    from sklearn.decomposition import PCA
+    X = synth.pca_features(n, D, rank=12, seed=5)
+    pca = PCA(whiten=True, n_components=10, svd_solver="full").fit(X)
+    v, m, var = onv.pca_fit(X, 10)
+    assert np.allclose(m, pca.mean_, rtol=1e-12, atol=1e-12)
+    assert np.allclose(var, pca.explained_variance_, rtol=1e-10)
+    assert np.allclose(v, pca.components_, rtol=1e-8, atol=1e-9)
+    assert np.allclose(onv.pca_project(X[:7], v, m, var).numpy(), pca.transform(X[:7]), rtol=1e-8, atol=1e-9)
