@@ -632,6 +632,8 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   // Also measured and dropped: tensor-core backward with 6 warps x 192 columns x 5 stages 1.11 ms, with 8 warps x 256
   // columns at 96 registers (spills) 1.08 ms; a one-CTA-per-SM warp-specialised pipeline (Gram warps / weight warps,
   // 168 registers) 1.63 ms -- with this much register tile per warp, warps per SM are what hides the latencies.
+  // Latency tweaks inside cfg 6 that did not pay: six instead of four accumulator chains in the backward 0.97 ms,
+  // Gram operands software-pipelined one column quad ahead 1.02 ms.
   const char* ce = getenv("SCL_WMS_STREAM_CFG");
   const int cfg = ce ? atoi(ce) : (TS == 5 ? 6 : 2);
   if (cfg == 6) return stream_launch<TS, 7, 224, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
