@@ -45,6 +45,26 @@ def knn_bruteforce(ref_f, query_f, k, chunk=256):
     return out_d, out_i
 
 
+def knn_sgemm_allcores(ref_f, query_f, k):
+    """The strongest plain-CPU form of top-n.py:103-106 (bench baseline only): float32 ``|r|^2 - 2 q.r`` through the
+    multi-threaded BLAS sgemm for a shortlist of 4k candidates, float64 direct-difference rescore, (dist, idx) order."""
+    ref = np.ascontiguousarray(ref_f, dtype=np.float32)
+    qry = np.ascontiguousarray(query_f, dtype=np.float32)
+    Q, R = qry.shape[0], ref.shape[0]
+    k = min(k, R)
+    kk = min(R, max(4 * k, k + 64))
+    approx = (ref * ref).sum(1)[None, :] - 2.0 * (qry @ ref.T)
+    cand = np.argpartition(approx, kk - 1, axis=1)[:, :kk]
+    out_d = np.empty((Q, k), dtype=np.float64)
+    out_i = np.empty((Q, k), dtype=np.int64)
+    for j in range(Q):
+        c = cand[j]
+        d2 = ((ref[c].astype(np.float64) - qry[j].astype(np.float64)) ** 2).sum(1)
+        order = np.lexsort((c, d2))[:k]
+        out_d[j], out_i[j] = np.sqrt(d2[order]), c[order]
+    return out_d, out_i
+
+
 def knn_bruteforce_exact(ref_f, query_f, k):
     """Tiny-problem version with no shortlist at all: full float64 direct differences."""
     ref = np.asarray(ref_f, dtype=np.float64)

@@ -161,6 +161,8 @@ def test_knn_oracle_matches_reference_kdtree_call():
     ex_d, ex_i = orr.knn_bruteforce_exact(ref, qry, 25)
     assert np.array_equal(kd_i, bf_i) and np.array_equal(kd_i, ex_i)
     assert np.allclose(kd_d, bf_d, rtol=1e-12) and np.allclose(kd_d, ex_d, rtol=1e-12)
+    sg_d, sg_i = orr.knn_sgemm_allcores(ref, qry, 25)         # the bench's all-core CPU baseline
+    assert np.array_equal(kd_i, sg_i) and np.allclose(kd_d, sg_d, rtol=1e-12)
 
 
 def test_recall_oracle():
