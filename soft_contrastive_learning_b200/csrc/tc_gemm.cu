@@ -13,9 +13,12 @@
 //       and write the lo tile next to it (same swizzled offsets, so no layout math); neither ever touches HBM.  The
 //       dropped lo_a lo_b term and the rounding of lo are each <= 2^-22 relative and unbiased.
 //
-// One 128 x BN output tile per CTA (cta_group::1, UMMA 128 x BN x 8), K swept in 32-float (128-byte, SWIZZLE_128B)
-// stages through an mbarrier ring: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
-// (tcgen05.ld 32x32b: one accumulator row per thread), warps 6-9 = splitters (x3 only).
+// Persistent CTAs (one per SM) walk the 128 x BN output tiles (cta_group::1, UMMA 128 x BN x 8), K swept in 32-float
+// (128-byte, SWIZZLE_128B) stages through an mbarrier ring that keeps running across tiles: warp 0 = TMA producer,
+// warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue (tcgen05.ld 32x32b: one accumulator row per thread),
+// warps 6-9 = splitters (x3 only).  The two TMEM accumulators alternate across flush groups AND tiles, so the loads and
+// MMAs of tile i+1 run under the global stores of tile i -- what the short-K, many-tile NetVLAD contractions
+// (K = 64, 10 240 tiles) are bound by.
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -69,11 +72,21 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GSmemTail* tail = reinterpret_cast<GSmemTail*>(smem + size_t(kStages) * Cfg::kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * kGBM, n0 = blockIdx.x * BN;
-  const int bz = int(blockIdx.z) / g.split_k, ks = int(blockIdx.z) - bz * g.split_k;      // batch index, K slice
   const int total_k = (g.K + kGBK - 1) / kGBK;
-  const int k_begin = (total_k * ks) / g.split_k, k_end = (total_k * (ks + 1)) / g.split_k;
-  const int num_k = k_end - k_begin;
+  const int ntiles = g.tiles_n * g.tiles_m * g.batch * g.split_k;
+  // tile -> (n tile, m tile, batch index, K slice); consecutive tiles share their A rows
+  struct Tile { int m0, n0, bz, k_begin, num_k; };
+  auto decode = [&](int tile) {
+    Tile t;
+    const int bx = tile % g.tiles_n, r = tile / g.tiles_n, by = r % g.tiles_m, z = r / g.tiles_m;
+    t.m0 = by * kGBM;
+    t.n0 = bx * BN;
+    t.bz = z / g.split_k;
+    const int ks = z - t.bz * g.split_k;
+    t.k_begin = (total_k * ks) / g.split_k;
+    t.num_k = (total_k * (ks + 1)) / g.split_k - t.k_begin;
+    return t;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -98,9 +111,13 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kc = 0; kc < num_k; ++kc) {
-        const int stage = kc % kStages;
-        mbar_wait(&tail->empty[stage], ((kc / kStages) & 1) ^ 1);
+      uint32_t kcg = 0;                                 // ring position, running across tiles
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const Tile t = decode(tile);
+      const int m0 = t.m0, n0 = t.n0, bz = t.bz, k_begin = t.k_begin;
+      for (int kc = 0; kc < t.num_k; ++kc, ++kcg) {
+        const int stage = kcg % kStages;
+        mbar_wait(&tail->empty[stage], ((kcg / kStages) & 1) ^ 1);
         uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
         uint8_t* sb = sa + kGABytes;
         mbar_arrive_expect_tx(&tail->full[stage], Cfg::kHiBytes);
@@ -119,6 +136,7 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
           tma_load_3d(sb, &tmB, &tail->full[stage], (k_begin + kc) * kGBK, n0, g.b_shared ? 0 : bz);
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -126,14 +144,18 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
       constexpr uint32_t idesc = make_idesc(kFmtTF32, kGBM, BN) | (kAMn ? (1u << 15) : 0u) | (kBMn ? (1u << 16) : 0u);
       // K advance of 8 tf32 inside a stage: K-major +32 bytes within the swizzle row, MN-major +1024 bytes (next atom)
       constexpr uint64_t stepA = kAMn ? (1024 >> 4) : (32 >> 4), stepB = kBMn ? (1024 >> 4) : (32 >> 4);
-      for (int kc = 0; kc < num_k; ++kc) {
-        const int stage = kc % kStages;
-        const int grp = kc / Cfg::kFlush, buf = grp & 1, in_grp = kc - grp * Cfg::kFlush;
+      uint32_t kcg = 0, grpg = 0;                       // ring position and flush-group count, running across tiles
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int num_k = decode(tile).num_k;
+      for (int kc = 0; kc < num_k; ++kc, ++kcg) {
+        const int stage = kcg % kStages;
+        const int in_grp = kc % Cfg::kFlush;
+        const uint32_t buf = grpg & 1;
         if (in_grp == 0) {
-          mbar_wait(&tail->acc_empty[buf], ((grp >> 1) & 1) ^ 1);       // the epilogue drained this accumulator
+          mbar_wait(&tail->acc_empty[buf], ((grpg >> 1) & 1) ^ 1);      // the epilogue drained this accumulator
           tc_fence_after();
         }
-        mbar_wait(kX3 ? &tail->split[stage] : &tail->full[stage], (kc / kStages) & 1);
+        mbar_wait(kX3 ? &tail->split[stage] : &tail->full[stage], (kcg / kStages) & 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(buf) * BN;
         const uint32_t sa = smem_u32(smem + size_t(stage) * Cfg::kStageBytes);
@@ -153,21 +175,30 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
           }
         }
         mma_commit(&tail->empty[stage]);              // frees the stage when these MMAs retire
-        if (in_grp == Cfg::kFlush - 1 || kc == num_k - 1) mma_commit(&tail->acc_full[buf]);
+        if (in_grp == Cfg::kFlush - 1 || kc == num_k - 1) {
+          mma_commit(&tail->acc_full[buf]);
+          ++grpg;
+        }
+      }
       }
     }
   } else if (warp < 6) {
     // ===================== epilogue: TMEM -> register accumulators (per flush group) -> global =====================
     const int lq = warp & 3;                            // TMEM lane quarter this warp may read
-    const int m = m0 + lq * 32 + lane;
+    uint32_t grpg = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const Tile t = decode(tile);
+    const int n0 = t.n0, bz = t.bz;
+    const int m = t.m0 + lq * 32 + lane;
     float acc[BN];
 #pragma unroll
     for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
-    const int ngroups = (num_k + Cfg::kFlush - 1) / Cfg::kFlush;
+    const int ngroups = (t.num_k + Cfg::kFlush - 1) / Cfg::kFlush;
 #pragma unroll 1
-    for (int grp = 0; grp < ngroups; ++grp) {
-      const int buf = grp & 1;
-      mbar_wait(&tail->acc_full[buf], (grp >> 1) & 1);
+    for (int grp = 0; grp < ngroups; ++grp, ++grpg) {
+      const uint32_t buf = grpg & 1;
+      mbar_wait(&tail->acc_full[buf], (grpg >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16) + uint32_t(buf) * BN;
 #pragma unroll
@@ -214,11 +245,14 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
         }
       }
     }
+    }
   } else if (kX3) {
     // ===================== splitters: lo = x - tf32_trunc(x), same swizzled offsets =====================
     const int st = threadIdx.x - 192;                   // 0..127
     constexpr int kVec = int(Cfg::kHiBytes / 16);       // float4s in the hi part of a stage
-    for (int kc = 0; kc < num_k; ++kc) {
+    uint32_t nk_all = 0;                                // stages this CTA sweeps over all its tiles
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) nk_all += uint32_t(decode(tile).num_k);
+    for (uint32_t kc = 0; kc < nk_all; ++kc) {
       const int stage = kc % kStages;
       mbar_wait(&tail->full[stage], (kc / kStages) & 1);
       float4* hi = reinterpret_cast<float4*>(smem + size_t(stage) * Cfg::kStageBytes);
@@ -278,7 +312,11 @@ static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
   g.batch = int(nb);
   g.b_shared = (nb > 1 && d.sB == 0) ? 1 : 0;
   g.split_k = (d.split_k == 2 && (d.K + kGBK - 1) / kGBK >= 2 && !d.accumulate) ? 2 : 1;
-  dim3 grid(unsigned((d.N + BN - 1) / BN), unsigned((d.M + kGBM - 1) / kGBM), unsigned(g.batch * g.split_k));
+  g.tiles_n = (d.N + BN - 1) / BN;
+  g.tiles_m = (d.M + kGBM - 1) / kGBM;
+  const long long ntiles = (long long)g.tiles_n * g.tiles_m * g.batch * g.split_k;
+  if (ntiles > 0x7fffffffLL) return SCL_ERR_BAD_SHAPE;
+  const unsigned grid = unsigned(ntiles < num_sms() ? ntiles : num_sms());      // persistent: one CTA per SM
   kern<<<grid, Cfg::kThreads, smem, stream>>>(tmA, tmB, g);
   SCL_LAUNCH_CHECK();
   return SCL_OK;

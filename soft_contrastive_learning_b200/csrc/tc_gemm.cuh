@@ -38,8 +38,9 @@ struct TcGemmArgs {
   const float* rowscale;
   long long rowscale_stride;
   int accumulate;
-  int batch;               // grid.z = batch * split_k
+  int batch;               // tiles = tiles_n * tiles_m * batch * split_k, walked by persistent CTAs
   int split_k;
+  int tiles_n, tiles_m;
   int b_shared;            // every batch reads B slice 0
 };
 
