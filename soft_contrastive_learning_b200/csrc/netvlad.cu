@@ -370,18 +370,14 @@ extern "C" int scl_netvlad_bwd(const float* x, const float* assign_w, const floa
   SCL_LAUNCH_CHECK();
   if (dx) {
     if (!aligned16(dx)) return SCL_ERR_ALIGN;
-    // dxh[b] = A[b] dV[b]^T (aggregation path)   M = HW, N = C, contraction over K
+    // dxh[b] = A[b] dV[b]^T (aggregation path) + dS[b] W^T (assignment path): ONE contraction over the concatenated
+    // K = 64 + 64 ([A | dS] . [dV[b] | W]^T), so dx is written once instead of written, re-read and written again
     TcGemmDesc e = {};
     e.A = w.a; e.B = w.dV; e.C = dx; e.M = HW; e.N = C; e.K = K; e.lda = K; e.ldb = K; e.ldc = C;
     e.a_mn = false; e.b_mn = false; e.precision = prec;
     e.batch = B; e.sA = (long long)HW * K; e.sB = (long long)C * K; e.sC = (long long)HW * C;
+    e.A2 = w.da; e.B2 = assign_w; e.K2 = K; e.sB2 = 0;
     rc = tc_gemm(e, stream);
-    if (rc) return rc;
-    // dxh += dS W^T (assignment path)
-    TcGemmDesc f = {};
-    f.A = w.da; f.B = assign_w; f.C = dx; f.M = int(P); f.N = C; f.K = K; f.lda = K; f.ldb = K; f.ldc = C;
-    f.a_mn = false; f.b_mn = false; f.accumulate = 1; f.precision = prec;
-    rc = tc_gemm(f, stream);
     if (rc) return rc;
     nv_l2norm_bwd_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(x, w.inv, P, C, dx);
     SCL_LAUNCH_CHECK();

@@ -65,7 +65,8 @@ __device__ __forceinline__ float tf32_rn(float x) {     // round to nearest tf32
 
 template <int BN, bool kX3, bool kAMn, bool kBMn>
 __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
-    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcGemmArgs g) {
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, TcGemmArgs g) {
   using Cfg = GCfg<BN, kX3>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -91,6 +92,10 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (g.k1_stages < total_k) {
+      prefetch_tmap(&tmA2);
+      prefetch_tmap(&tmB2);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&tail->full[s], 1);
       mbar_init(&tail->split[s], 4);
@@ -121,19 +126,24 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
         uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
         uint8_t* sb = sa + kGABytes;
         mbar_arrive_expect_tx(&tail->full[stage], Cfg::kHiBytes);
+        // K stages beyond k1_stages come from the second operand pair (K-concatenated problem)
+        const int ka = k_begin + kc;
+        const bool second = ka >= g.k1_stages;
+        const CUtensorMap* mA = second ? &tmA2 : &tmA;
+        const CUtensorMap* mB = second ? &tmB2 : &tmB;
+        const int kk = (second ? ka - g.k1_stages : ka) * kGBK;
+        const int bzb = (second ? g.b2_shared : g.b_shared) ? 0 : bz;
         if (kAMn) {
 #pragma unroll
-          for (int grp = 0; grp < kGBM / 32; ++grp)
-            tma_load_3d(sa + grp * 4096, &tmA, &tail->full[stage], m0 + 32 * grp, (k_begin + kc) * kGBK, bz);
+          for (int grp = 0; grp < kGBM / 32; ++grp) tma_load_3d(sa + grp * 4096, mA, &tail->full[stage], m0 + 32 * grp, kk, bz);
         } else {
-          tma_load_3d(sa, &tmA, &tail->full[stage], (k_begin + kc) * kGBK, m0, bz);
+          tma_load_3d(sa, mA, &tail->full[stage], kk, m0, bz);
         }
         if (kBMn) {
 #pragma unroll
-          for (int grp = 0; grp < BN / 32; ++grp)
-            tma_load_3d(sb + grp * 4096, &tmB, &tail->full[stage], n0 + 32 * grp, (k_begin + kc) * kGBK, g.b_shared ? 0 : bz);
+          for (int grp = 0; grp < BN / 32; ++grp) tma_load_3d(sb + grp * 4096, mB, &tail->full[stage], n0 + 32 * grp, kk, bzb);
         } else {
-          tma_load_3d(sb, &tmB, &tail->full[stage], (k_begin + kc) * kGBK, n0, g.b_shared ? 0 : bz);
+          tma_load_3d(sb, mB, &tail->full[stage], kk, n0, bzb);
         }
       }
       }
@@ -299,6 +309,21 @@ static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
   if (kBMn) rc = make_tmap_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.B, uint64_t(d.N), uint64_t(d.K), nbB, uint64_t(d.ldb) * 4, pB, 32, 32, 1);
   else rc = make_tmap_3d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.B, uint64_t(d.K), uint64_t(d.N), nbB, uint64_t(d.ldb) * 4, pB, 32, BN, 0);
   if (rc) return rc;
+  // optional second operand pair, K-concatenated behind the first
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  const bool dual = d.A2 != nullptr;
+  if (dual) {
+    if (!d.B2 || d.K2 < 1 || (d.K % kGBK) != 0 || d.split_k == 2 || !aligned16(d.A2) || !aligned16(d.B2)) return SCL_ERR_BAD_ARG;
+    const uint64_t pA2 = (nb > 1 ? uint64_t(d.sA) : uint64_t(d.lda) * (d.a_mn ? d.K2 : d.M)) * 4;
+    const uint64_t pB2 = ((nb > 1 && d.sB2) ? uint64_t(d.sB2) : uint64_t(d.ldb) * (d.b_mn ? d.K2 : d.N)) * 4;
+    const uint64_t nbB2 = (nb > 1 && d.sB2 == 0) ? 1 : nb;
+    if (kAMn) rc = make_tmap_3d(&tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.A2, uint64_t(d.M), uint64_t(d.K2), nb, uint64_t(d.lda) * 4, pA2, 32, 32, 1);
+    else rc = make_tmap_3d(&tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.A2, uint64_t(d.K2), uint64_t(d.M), nb, uint64_t(d.lda) * 4, pA2, 32, kGBM, 0);
+    if (rc) return rc;
+    if (kBMn) rc = make_tmap_3d(&tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.B2, uint64_t(d.N), uint64_t(d.K2), nbB2, uint64_t(d.ldb) * 4, pB2, 32, 32, 1);
+    else rc = make_tmap_3d(&tmB2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.B2, uint64_t(d.K2), uint64_t(d.N), nbB2, uint64_t(d.ldb) * 4, pB2, 32, BN, 0);
+    if (rc) return rc;
+  }
   auto kern = tc_gemm_kernel<BN, kX3, kAMn, kBMn>;
   const size_t smem = 1024 + size_t(Cfg::kStages) * Cfg::kStageBytes + sizeof(GSmemTail);
   static bool configured = false;
@@ -307,7 +332,9 @@ static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
     configured = true;
   }
   TcGemmArgs g;
-  g.M = d.M; g.N = d.N; g.K = d.K; g.colscale = d.colscale; g.C = d.C; g.ldc = d.ldc;
+  g.M = d.M; g.N = d.N; g.K = d.K + (dual ? d.K2 : 0); g.colscale = d.colscale; g.C = d.C; g.ldc = d.ldc;
+  g.k1_stages = dual ? d.K / kGBK : 0x7fffffff;
+  g.b2_shared = (dual && nb > 1 && d.sB2 == 0) ? 1 : 0;
   g.sC = d.sC; g.rowscale = d.rowscale; g.rowscale_stride = d.rowscale_stride; g.accumulate = d.accumulate;
   g.batch = int(nb);
   g.b_shared = (nb > 1 && d.sB == 0) ? 1 : 0;
@@ -317,7 +344,7 @@ static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
   const long long ntiles = (long long)g.tiles_n * g.tiles_m * g.batch * g.split_k;
   if (ntiles > 0x7fffffffLL) return SCL_ERR_BAD_SHAPE;
   const unsigned grid = unsigned(ntiles < num_sms() ? ntiles : num_sms());      // persistent: one CTA per SM
-  kern<<<grid, Cfg::kThreads, smem, stream>>>(tmA, tmB, g);
+  kern<<<grid, Cfg::kThreads, smem, stream>>>(tmA, tmB, tmA2, tmB2, g);
   SCL_LAUNCH_CHECK();
   return SCL_OK;
 }

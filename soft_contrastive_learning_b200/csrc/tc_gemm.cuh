@@ -27,6 +27,12 @@ struct TcGemmDesc {
   int accumulate;          // C += result
   int split_k;             // 0/1: off; 2: two CTAs per tile, each half of K, combined with atomicAdd (C zeroed by the caller;
                            //       two addends commute, so the result stays deterministic)
+  // optional second operand pair, concatenated along K:  C = [A | A2] . [B | B2]^T  (one pass over C instead of a second,
+  // accumulating GEMM).  Same majorness, leading dimensions and batch stride of A as the first pair; K a multiple of 32.
+  const float* A2;
+  const float* B2;
+  int K2;
+  long long sB2;           // batch stride of B2 in elements; 0 = shared by every batch
 };
 
 struct TcGemmArgs {
@@ -42,6 +48,8 @@ struct TcGemmArgs {
   int split_k;
   int tiles_n, tiles_m;
   int b_shared;            // every batch reads B slice 0
+  int k1_stages;           // K stages served by the first operand pair (the rest come from the second pair)
+  int b2_shared;
 };
 
 int tc_gemm(const TcGemmDesc& d, cudaStream_t stream);
