@@ -8,7 +8,7 @@
 // Precision modes
 //   x1  one kind::tf32 MMA per product: operands are read as fp32 and truncated to tf32 by the tensor core
 //       (10-bit mantissa, relative error ~1e-3 per product; stated tolerance of callers: 2e-3 of the result norm);
-//   x3  fp32-grade "3xTF32": hi = rn_tf32(x), lo = rn_tf32(x - hi) (x - hi is exact in fp32),
+//   x3  fp32-grade "3xTF32": hi = rn_tf32(x), lo = x - hi (exact in fp32; the tensor core truncates it to tf32),
 //       D += hi_a hi_b + hi_a lo_b + lo_a hi_b.  Four "splitter" warps rewrite the TMA-landed fp32 tile in place as hi
 //       and write the lo tile next to it (same swizzled offsets, so no layout math); neither ever touches HBM.  The
 //       dropped lo_a lo_b term and the rounding of lo are each <= 2^-22 relative and unbiased.
@@ -57,11 +57,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr) {
          (uint64_t(1) << 46) | (uint64_t(1) << 61);
 }
 
-__device__ __forceinline__ float tf32_rn(float x) {     // round to nearest tf32 (10-bit mantissa), result as fp32 bits
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// Round to nearest tf32 (10-bit mantissa), result as fp32 bits.  cvt.rna.tf32.f32 has no native SASS form on sm_100 (it
+// expands to five instructions with an Inf/NaN guard); the integer form below is two, and the splitter warps are on the
+// critical path of the 3xTF32 mode.  Ties round away from zero like .rna; Inf stays Inf, NaN stays NaN.
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 template <int BN, bool kX3, bool kAMn, bool kBMn>
 __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
@@ -271,10 +270,12 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
       for (int i = st; i < kVec; i += 128) {
         const float4 x = hi[i];
         float4 h, l;
-        h.x = tf32_rn(x.x); l.x = tf32_rn(x.x - h.x);
-        h.y = tf32_rn(x.y); l.y = tf32_rn(x.y - h.y);
-        h.z = tf32_rn(x.z); l.z = tf32_rn(x.z - h.z);
-        h.w = tf32_rn(x.w); l.w = tf32_rn(x.w - h.w);
+        // lo = x - hi is exact in fp32 and is handed over unrounded: the tensor core drops its bits below tf32
+        // (2^-22 of x, sign-symmetric like the residual itself)
+        h.x = tf32_rn(x.x); l.x = x.x - h.x;
+        h.y = tf32_rn(x.y); l.y = x.y - h.y;
+        h.z = tf32_rn(x.z); l.z = x.z - h.z;
+        h.w = tf32_rn(x.w); l.w = x.w - h.w;
         hi[i] = h;                                      // tf32-representable: whatever rounding the MMA applies is a no-op
         lo[i] = l;
       }
