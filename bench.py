@@ -409,6 +409,10 @@ def bench_netvlad_pca(args, torch, pk, B=256, H=30, W=40, Cc=512, K=64, Dout=409
     t0 = out["fp32-grade 3xTF32"]
     tot_flops = sum(flops.values())
     ach = tot_flops / (t0["total"] * 1e-3) / 1e12
+    # algorithmic HBM bytes of the step: X read by the forward and by the backward, dX written, V read by
+    # both PCA passes, the [B,32768] VLAD / gradient and the [B,4096] outputs once each
+    hbm_bytes = 4.0 * (3 * B * HW * Cc + 2 * Dout * Din + 4 * B * Din + 2 * B * Dout)
+    hbm_gbs = hbm_bytes / (t0["total"] * 1e-3) / 1e9
     return {"metric": "NetVLAD head + PCA fwd+bwd images/s", "value": B / (t0["total"] * 1e-3), "unit": "images/s",
             "ms_per_step": t0["total"], "dtype": "tf32 x3 (fp32-grade) on tcgen05, fp32 accumulate",
             "config": {"workload": f"BASELINE config 2: B={B}, {H}x{W}x{Cc} conv5 maps, K={K}, PCA {Din}->{Dout}, fwd+bwd",
@@ -416,8 +420,11 @@ def bench_netvlad_pca(args, torch, pk, B=256, H=30, W=40, Cc=512, K=64, Dout=409
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                          "frac": ach / pk["tf_sustained"], "peak_source": pk["source"] + " cuBLAS bf16 sustained (no tf32 peak measured; "
                          "kind::tf32 is nominally half the bf16 rate and the fp32-grade mode issues 3 MMAs per product)",
-                         "algorithmic_flops_per_step": tot_flops, "kernel": "tc_gemm_kernel", "traffic": None},
-            "gpu_launches": 5 * (6 + 12 + 4 + 2)}
+                         "algorithmic_flops_per_step": tot_flops, "kernel": "tc_gemm_kernel", "traffic": None,
+                         "hbm_view": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_gbs, "peak_gbs": pk["hbm_gbs"],
+                                      "frac": hbm_gbs / pk["hbm_gbs"],
+                                      "note": "with fp32 X the step is HBM-bound, not tensor-bound (SURVEY 8d): this is the binding roofline"}},
+            "gpu_launches": 5 * (6 + 11 + 4 + 2)}
 
 
 def bench_losses_cfg3(args, torch, pk, T=32, P=15, N=16, D=D_FULL):
