@@ -15,6 +15,8 @@
 #include <cuda_fp16.h>
 
 #include "knn_internal.cuh"
+#include <atomic>
+
 #include "tc_common.cuh"
 
 namespace scl {
@@ -519,10 +521,10 @@ static int tc_tile_n(int variant) { return variant == 3 ? 2 * kBN : kBN; }
 template <bool kPair, int kNSub>
 static int tc_launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
   auto kern = knn_tc_kernel<kPair, kNSub>;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<bool> configured{false};          // idempotent attribute: a race between host threads is benign
+  if (!configured.load(std::memory_order_acquire)) {
     SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tc_smem_bytes<kPair, kNSub>())));
-    configured = true;
+    configured.store(true, std::memory_order_release);
   }
   const int sms = num_sms();
   const int m_units = kPair ? (a.num_m_blocks + 1) / 2 : a.num_m_blocks;

@@ -19,6 +19,8 @@
 // warps 6-9 = splitters (x3 only).  The two TMEM accumulators alternate across flush groups AND tiles, so the loads and
 // MMAs of tile i+1 run under the global stores of tile i -- what the short-K, many-tile NetVLAD contractions
 // (K = 64, 10 240 tiles) are bound by.
+#include <atomic>
+
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -327,10 +329,10 @@ static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
   }
   auto kern = tc_gemm_kernel<BN, kX3, kAMn, kBMn>;
   const size_t smem = 1024 + size_t(Cfg::kStages) * Cfg::kStageBytes + sizeof(GSmemTail);
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<bool> configured{false};          // idempotent attribute: a race between host threads is benign
+  if (!configured.load(std::memory_order_acquire)) {
     SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = true;
+    configured.store(true, std::memory_order_release);
   }
   TcGemmArgs g;
   g.M = d.M; g.N = d.N; g.K = d.K + (dual ? d.K2 : 0); g.colscale = d.colscale; g.C = d.C; g.ldc = d.ldc;
