@@ -366,6 +366,33 @@ def _time_ms(torch, fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
+def bench_wms_sharded(args, torch, dist_mod, rank, world, pk, T_local=4096):
+    """SURVEY 8e row 2 (N > 1): tuples sharded over the ranks, T_local per GPU (weak scaling), no data-path collective;
+    each step ends with the scalar all-reduce of sharded.combine_tuple_shards.  value = tuples of ALL ranks / max time."""
+    from soft_contrastive_learning_b200 import losses, sharded, synth
+    S, D = 25, D_FULL
+    emb_s, dist_s, _ = synth.wms_batch(T=64, P=12, N=12, D=D, seed=42 + rank)
+    emb = torch.tensor(emb_s, device="cuda").repeat(T_local // 64, 1, 1).contiguous()
+    dmat = torch.tensor(dist_s, device="cuda").repeat(T_local // 64, 1, 1).contiguous()
+    emb += 1e-3 * torch.randn_like(emb)
+    params = losses._ms_params(0.8, 15.0)
+
+    def step():
+        loss, grad, _, _ = losses._wms_tuple_raw(emb, dmat, params, need_grad=True)
+        sharded.combine_tuple_shards(loss.reshape(()), None, T_local)       # gradients stay local: only the scalar travels
+
+    ms = timed(torch, step, max(args.steps, 10), max(args.warmup, 3), dist_mod)
+    bytes_alg = world * T_local * (2 * S * D * 4 + S * S * 4)
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    return {"metric": "wms loss fwd+bwd tuples/s", "value": world * T_local / (ms * 1e-3), "unit": "tuples/s", "ms_per_step": ms,
+            "n_gpus": world, "scaling": "weak", "dtype": "f32",
+            "config": {"workload": f"wms tuple mode sharded by tuples, T={T_local} per GPU x {world} GPUs, S={S} D={D}; "
+                                   "one scalar all-reduce per step, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"] * world, "unit": "GB/s",
+                         "frac": gbs / (pk["hbm_gbs"] * world), "peak_source": pk["source"] + f" x {world} GPUs"},
+            "gpu_launches": max(args.steps, 10)}
+
+
 def bench_netvlad_pca(args, torch, pk, B=256, H=30, W=40, Cc=512, K=64, Dout=4096):
     """BASELINE config 2: NetVLAD head K=64 over 30x40x512 maps + PCA 32768->4096, forward and backward, batch 256."""
     import ctypes as C
@@ -527,6 +554,24 @@ def main():
                         line["secondary"].append(fn(args, torch, pk))
                     except Exception as e:          # a secondary line must never cost the headline
                         line["secondary"].append({"metric": fn.__name__, "error": repr(e)[:300]})
+        if world > 1 and not args.no_secondary:
+            # a secondary line must never cost the headline: if a rank fails and the others wait in a collective, a
+            # watchdog prints the headline alone and ends the process
+            def bail():
+                if rank == 0:
+                    line["secondary"] = [{"metric": "bench_wms_sharded", "error": "timed out"}]
+                    print(json.dumps(line), file=real_stdout, flush=True)
+                os._exit(0)
+            dog = threading.Timer(120.0, bail)
+            dog.daemon = True
+            dog.start()
+            torch.cuda.empty_cache()
+            try:
+                sec = bench_wms_sharded(args, torch, dist_mod, rank, world, pk)
+            except Exception as e:
+                sec = {"metric": "bench_wms_sharded", "error": repr(e)[:300]}
+            dog.cancel()
+            line["secondary"] = [sec]
     if rank == 0:
         print(json.dumps(line), file=real_stdout, flush=True)
     if dist_mod is not None:

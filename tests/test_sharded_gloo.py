@@ -78,3 +78,44 @@ def test_sharded_protocol_world2(tmp_path, R, k):
     got = np.load(out)
     assert np.array_equal(got["i"], ref_i)
     assert np.allclose(got["d"], ref_d, rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# tuple-mode losses shard by tuples; only the scalar mean is exchanged
+# ---------------------------------------------------------------------------------------------
+def _tuple_worker(rank, world, port, counts, out):
+    import torch.distributed as dist
+    from oracle import losses as ol
+    from soft_contrastive_learning_b200 import sharded, synth
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        emb, dmat, _ = synth.wms_batch(T=sum(counts), P=4, N=5, D=32, seed=7)
+        lo = sum(counts[:rank])
+        e = torch.tensor(emb[lo:lo + counts[rank]], dtype=torch.float64, requires_grad=True)
+        d = torch.tensor(dmat[lo:lo + counts[rank]], dtype=torch.float64)
+        local = ol.wms_loss_tuples(d, e, 0.8, 15.0)                 # the oracle stands in for the CUDA kernel on CPU
+        (g,) = torch.autograd.grad(local, e)
+        loss, grad = sharded.combine_tuple_shards(local.detach(), g, counts[rank])
+        torch.save({"loss": loss, "grad": grad}, out + f".{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [(3, 3), (5, 2)])
+def test_tuple_shards_reproduce_the_single_call(tmp_path, counts):
+    """world_size 2 over gloo: the combined mean and the re-weighted local gradients equal one call over all tuples,
+    also when the ranks hold different numbers of tuples."""
+    import torch.multiprocessing as mp
+    from oracle import losses as ol
+    from soft_contrastive_learning_b200 import synth
+    out = str(tmp_path / "tuple_shard")
+    mp.spawn(_tuple_worker, args=(2, _free_port(), counts, out), nprocs=2, join=True)
+    emb, dmat, _ = synth.wms_batch(T=sum(counts), P=4, N=5, D=32, seed=7)
+    e = torch.tensor(emb, dtype=torch.float64, requires_grad=True)
+    whole = ol.wms_loss_tuples(torch.tensor(dmat, dtype=torch.float64), e, 0.8, 15.0)
+    (g,) = torch.autograd.grad(whole, e)
+    parts = [torch.load(out + f".{r}") for r in range(2)]
+    for p in parts:
+        assert abs(float(p["loss"]) - float(whole)) <= 1e-12 * abs(float(whole))
+    got = torch.cat([p["grad"] for p in parts])
+    assert torch.allclose(got, g, rtol=1e-12, atol=1e-15)
