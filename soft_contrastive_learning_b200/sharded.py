@@ -24,9 +24,8 @@ def combine_tuple_shards(local_loss, local_grad, t_local, group=None):
                         torch.tensor(float(t_local), dtype=torch.float64, device=loss.device)))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(pair, op=dist.ReduceOp.SUM, group=group)
-    t_global = float(pair[1])
-    scale = float(t_local) / t_global
-    grad = None if local_grad is None else local_grad * scale
+    # everything stays on the device: no host synchronisation inside a training step
+    grad = None if local_grad is None else local_grad * (float(t_local) / pair[1]).to(local_grad.dtype)
     return (pair[0] / pair[1]).to(loss.dtype), grad
 
 
