@@ -633,7 +633,10 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   // columns at 96 registers (spills) 1.08 ms; a one-CTA-per-SM warp-specialised pipeline (Gram warps / weight warps,
   // 168 registers) 1.63 ms -- with this much register tile per warp, warps per SM are what hides the latencies.
   // Latency tweaks inside cfg 6 that did not pay: six instead of four accumulator chains in the backward 0.97 ms,
-  // Gram operands software-pipelined one column quad ahead 1.02 ms.
+  // Gram operands software-pipelined one column quad ahead 1.02 ms; the backward on mma.sync.m16n8k16 f16 (hi/lo split
+  // into fp16 with exact power-of-two scaling per tuple: 12 instead of 18 MMAs per 8 columns at the same instruction rate,
+  // tools/ubench/mma_f16.cu) passed every parity test and ran 0.956 ms -- the backward is not bound by the tensor pipe
+  // but by what each of the 7 warps can keep in flight.
   const char* ce = getenv("SCL_WMS_STREAM_CFG");
   const int cfg = ce ? atoi(ce) : (TS == 5 ? 6 : 2);
   if (cfg == 6) return stream_launch<TS, 7, 224, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
