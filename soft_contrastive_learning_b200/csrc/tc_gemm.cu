@@ -227,6 +227,20 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
     if (m < g.M) {
       float* crow = g.C + size_t(bz) * g.sC + size_t(m) * g.ldc;
       const float rs = g.rowscale ? __ldg(g.rowscale + size_t(bz) * g.rowscale_stride + m) : 1.0f;
+      // Whole tiles of a plain store go out as 32-byte (one full sector) stores: the accumulator layout is one row per
+      // thread, so a warp's store touches 32 rows -- 16-byte pieces would write every sector in two halves.
+      const bool wide = n0 + BN <= g.N && g.split_k == 1 && !g.accumulate && !g.colscale && (g.ldc & 7) == 0 &&
+                        (g.sC & 7) == 0 && (reinterpret_cast<uintptr_t>(g.C) & 31) == 0;
+      if (wide) {
+#pragma unroll
+        for (int j8 = 0; j8 < BN / 8; ++j8) {
+          const float* a8 = acc + 8 * j8;
+          asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(crow + n0 + 8 * j8), "f"(a8[0] * rs),
+                       "f"(a8[1] * rs), "f"(a8[2] * rs), "f"(a8[3] * rs), "f"(a8[4] * rs), "f"(a8[5] * rs), "f"(a8[6] * rs),
+                       "f"(a8[7] * rs)
+                       : "memory");
+        }
+      } else
 #pragma unroll
       for (int j4 = 0; j4 < BN / 4; ++j4) {
         const int n = n0 + 4 * j4;
