@@ -172,6 +172,13 @@ static int flat_run(const float* emb, const float* dist, const int32_t* labels, 
     TcGemmDesc d = {};
     d.A = emb; d.B = emb; d.C = w.G; d.M = B; d.N = B; d.K = D; d.lda = D; d.ldb = D; d.ldc = B;
     d.a_mn = false; d.b_mn = false; d.colscale = nullptr; d.precision = tc_gemm_precision();
+    // few output tiles and a long K (B = 1024: 64 tiles, K = 4096): two CTAs per tile fill the machine; the two halves
+    // meet in one atomicAdd per element (two addends commute: deterministic)
+    const int tiles = ((B + 127) / 128) * ((B + 127) / 128);
+    if (2 * tiles <= num_sms() && D >= 2048) {
+      d.split_k = 2;
+      SCL_CUDA_TRY(cudaMemsetAsync(w.G, 0, size_t(B) * B * sizeof(float), stream));
+    }
     rc = tc_gemm(d, stream);
   } else {
     GemmArgs g = gemm_args(emb, emb, w.G, B, B, D, D, D, B, 0, 1);       // G = E E^T
