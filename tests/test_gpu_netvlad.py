@@ -121,3 +121,32 @@ def test_pca_fit_matches_oracle_and_sklearn(cuda_lib, n, D, d):
     pca = PCA(whiten=True, n_components=d, svd_solver="full").fit(X.astype(np.float64))
     got = netvlad.pca_project(X[:64], v, m, var)
     assert np.allclose(got, pca.transform(X[:64].astype(np.float64)), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(2500, 1300, 96),       # 20 x 11 = 220 tiles > #SMs: the persistent tile loop wraps
+                                   (130, 68, 1000),        # ragged M, N, K (K not a multiple of the 32-float stage)
+                                   (64, 36, 40)])          # narrow output (BN = 64), single partial stage
+@pytest.mark.parametrize("precision", [0, 1])
+def test_gemm_engine_all_layouts(cuda_lib, M, N, K, a_mn, b_mn, precision):
+    """scl_gemm_tf32 (csrc/tc_gemm.cu) directly: K-major / MN-major operands, ragged shapes, more tiles than SMs."""
+    import ctypes as C
+    from soft_contrastive_learning_b200._lib import check, lib
+    g = torch.Generator(device="cuda").manual_seed(M + 7 * N + 13 * K)
+    pad = lambda n: (n + 3) // 4 * 4
+    A = torch.randn((K, pad(M)) if a_mn else (M, pad(K)), generator=g, device="cuda")
+    Bm = torch.randn((K, pad(N)) if b_mn else (N, pad(K)), generator=g, device="cuda")
+    Ad = (A[:, :M].t() if a_mn else A[:, :K]).double()
+    Bd = (Bm[:, :N].t() if b_mn else Bm[:, :K]).double()
+    ref = Ad @ Bd.t()
+    out = torch.full((M, pad(N)), float("nan"), device="cuda")
+    scale = torch.rand(pad(N), generator=g, device="cuda") + 0.5
+    check(lib().scl_gemm_tf32(C.c_void_p(A.data_ptr()), C.c_void_p(Bm.data_ptr()), C.c_void_p(out.data_ptr()), M, N, K,
+                              A.stride(0), Bm.stride(0), out.stride(0), a_mn, b_mn, C.c_void_p(scale.data_ptr()), precision,
+                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "scl_gemm_tf32")
+    got = out[:, :N].double()
+    ref = ref * scale[:N].double()
+    tol = 2e-6 if precision == 0 else 2e-3                 # fp32-grade 3xTF32 vs one TF32 pass, relative to the result norm
+    assert float((got - ref).abs().max() / ref.abs().max()) < tol
+    if pad(N) != N:
+        assert torch.isnan(out[:, N:]).all()               # nothing written past the logical width
