@@ -24,6 +24,7 @@ def launch_list(tag):
     hdr = rows[start]
     ix = {h: i for i, h in enumerate(hdr)}
     tot, cnt = collections.Counter(), collections.Counter()
+    seq = []
     for r in rows[start + 1:]:
         if len(r) < len(hdr) or r[ix["Metric Name"]] != "gpu__time_duration.sum":
             continue
@@ -31,6 +32,7 @@ def launch_list(tag):
         ms = v / 1e3 if u in ("us", "usecond") else v / 1e6 if u in ("ns", "nsecond") else v * 1e3 if u in ("s", "second") else v
         tot[r[ix["Kernel Name"]]] += ms
         cnt[r[ix["Kernel Name"]]] += 1
+        seq.append((r[ix["Kernel Name"]], ms))
     total = sum(tot.values())
     with open(os.path.join(PROF, f"{tag}_launch_list_summary.txt"), "w") as f:
         f.write("ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n")
@@ -38,6 +40,14 @@ def launch_list(tag):
                 f"{sum(cnt.values())} launches\n\n  total ms  count     avg ms   share  kernel\n")
         for k, v in tot.most_common(25):
             f.write(f"{v:10.3f} {cnt[k]:6d} {v / cnt[k]:10.4f} {100 * v / total:6.1f}%  {k[:110]}\n")
+        # one retrieval step in isolation: the launches between two consecutive query-prep kernels
+        prep = [i for i, (n, _) in enumerate(seq) if "knn_query_prep" in n]
+        if len(prep) >= 2:
+            step = seq[prep[-2]:prep[-1]]
+            st = sum(ms for _, ms in step)
+            f.write(f"\none retrieval step (10 000 queries vs the 1M-row shard), {len(step)} launches, {st:.3f} ms device time:\n")
+            for n, ms in step:
+                f.write(f"{ms:10.4f} ms {100 * ms / st:6.1f}%  {n[:110]}\n")
 
 
 def clocks(tag):
