@@ -55,7 +55,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -249,7 +249,17 @@ def bench_retrieval(args, torch, dist_mod, rank, world, pk):
     L.scl_knn_timing(1, None, None)
     sampler.start()
     ms = timed(torch, step_dev, args.steps, args.warmup, dist_mod)
+    # nvidia-smi needs a few hundred ms to deliver samples: when the timed region is shorter than that (small shards at
+    # N = 8: 5 steps x 10 ms), the same step keeps running untimed under the sampler until ~0.8 s of load has been seen
+    # (ms is the max over ranks, so every rank runs the same number of extra steps and the collectives stay matched)
+    loaded_s = ms * 1e-3 * (args.steps + args.warmup)
+    n_extra = int(np.ceil((0.8 - loaded_s) / (ms * 1e-3))) if loaded_s < 0.8 else 0
+    for _ in range(n_extra):
+        step_dev()
+    torch.cuda.synchronize()
     clocks = sampler.stop()
+    if n_extra:
+        clocks["untimed_steps_under_sampler"] = n_extra
     tc_ms, tc_calls = C.c_double(), C.c_int()
     L.scl_knn_timing(0, C.byref(tc_ms), C.byref(tc_calls))
     tc_avg_ms = tc_ms.value / max(1, tc_calls.value)
