@@ -93,8 +93,8 @@ def test_wms_cluster_sizes_agree(cuda_lib, cluster, monkeypatch):
     assert rel(loss, ref) < LOSS_TOL and grad_err(grad, rg) < GRAD_TOL
 
 
-# the three tuple-mode kernels: streaming (large batches), cluster-resident (small batches), cluster-chunked (slice too
-# large for shared memory); each is forced through the same shapes, incl. ragged D (not a multiple of the 256-column
+# the tuple-mode kernels: streaming with the FFMA2 backward and with the tensor-core backward (large batches),
+# cluster-resident (small batches), cluster-chunked (slice too large for shared memory); each is forced through the same shapes, incl. ragged D (not a multiple of the 256-column
 # ring stage), odd S (distance block not 16-byte sized), S = 32 (widest register tile) and a forward-only call
 WMS_PATHS = {"stream": {"SCL_WMS_STREAM": "1", "SCL_WMS_STREAM_CFG": "2"}, "resident": {"SCL_WMS_STREAM": "0"},
              "stream_mma": {"SCL_WMS_STREAM": "1", "SCL_WMS_STREAM_CFG": "6"},
