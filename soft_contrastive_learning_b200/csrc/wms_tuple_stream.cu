@@ -638,6 +638,8 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   // tools/ubench/mma_f16.cu) passed every parity test and ran 0.956 ms -- the backward is not bound by the tensor pipe
   // but by what each of the 7 warps can keep in flight.  Trading registers for warps does not help either: the fp16
   // backward with 10 consumer warps x 160 columns x 5 stages at 80 registers (2 CTAs per SM) ran 1.24-1.26 ms.
+  // cp.async.bulk.prefetch.L2 of the chunks 4 / 8 positions beyond the ring: 1.07 / 1.09 ms (the prefetched lines push
+  // the tuples waiting for their re-read out of L2).
   const char* ce = getenv("SCL_WMS_STREAM_CFG");
   const int cfg = ce ? atoi(ce) : (TS == 5 ? 6 : 2);
   if (cfg == 6) return stream_launch<TS, 7, 224, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
