@@ -24,6 +24,7 @@ def _free_port():
 class _OracleLocal:
     def __init__(self, X, index_offset=0):
         self.X, self.off = np.asarray(X), index_offset
+        self.db = torch.zeros(1)                 # the device the shard lives on (CPU in this test)
 
     def query_device(self, q, k=1, force_path=0):
         from oracle import retrieval as orr
@@ -60,6 +61,9 @@ def _worker(rank, world, port, R, D, Q, k, out):
         retrieval.topk_merge = _numpy_merge
         tree = retrieval.ShardedKDTree(db[lo:hi], index_offset=lo)
         d, i = tree.query_device(qry, k)
+        # queries in host memory: every rank copies its 1/G slice (ragged: Q = 9 over 2 ranks) and the slices are all-gathered
+        d2, i2 = tree.query_from_host(torch.from_numpy(qry), k)
+        assert torch.equal(i2, i) and torch.equal(d2, d)
         if rank == 0:
             np.savez(out, d=d.numpy(), i=i.numpy())
     finally:
