@@ -635,8 +635,9 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   // Latency tweaks inside cfg 6 that did not pay: six instead of four accumulator chains in the backward 0.97 ms,
   // Gram operands software-pipelined one column quad ahead 1.02 ms; the backward on mma.sync.m16n8k16 f16 (hi/lo split
   // into fp16 with exact power-of-two scaling per tuple: 12 instead of 18 MMAs per 8 columns at the same instruction rate,
-  // tools/ubench/mma_f16.cu) passed every parity test and ran 0.956 ms -- the backward is not bound by the tensor pipe
-  // but by what each of the 7 warps can keep in flight.  Trading registers for warps does not help either: the fp16
+  // tools/ubench/mma_f16.cu) passed every parity test and ran 0.956 ms -- the backward is not bound by the tensor pipe:
+  // the unit at its limit is the L1/shared-memory data pipe (71 % of peak over the whole kernel: Gram operand loads,
+  // one wavefront per 32-byte sector of these accumulator-layout stores, fragment loads; profiles/r1_wms_l1_analysis.txt).  Trading registers for warps does not help either: the fp16
   // backward with 10 consumer warps x 160 columns x 5 stages at 80 registers (2 CTAs per SM) ran 1.24-1.26 ms.
   // cp.async.bulk.prefetch.L2 of the chunks 4 / 8 positions beyond the ring: 1.07 / 1.09 ms (the prefetched lines push
   // the tuples waiting for their re-read out of L2).
