@@ -36,6 +36,28 @@ R_FULL, D_FULL, K_TOP = 1_000_000, 4096, 25
 Q_STEP = 10_000
 
 
+def workload_config(rows, queries, shards):
+    """The workload both arms (ours and --impl reference) are measured on: identical dict, identical wording."""
+    return {"workload": f"top-{K_TOP} exact retrieval, {queries} queries/step vs {rows}x{D_FULL} fp32 db (BASELINE config 4)",
+            "rows": rows, "queries_per_step": queries, "dim": D_FULL, "k": K_TOP, "db_shards": shards}
+
+
+def profile_traffic(fname):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, parsed from the committed `ncu --set full` digest
+    under profiles/ (tools/ncu_digest.py writes 'dram read  <x> Mbyte|Gbyte').  None when the digest is absent."""
+    import re
+    p = os.path.join(ROOT, "profiles", fname)
+    if not os.path.exists(p):
+        return None
+    tot, seen = 0.0, 0
+    for ln in open(p):
+        m = re.match(r"\s*dram (read|write)\s+([0-9.]+)\s+([KMG]?)byte", ln)
+        if m:
+            tot += float(m.group(2)) * {"": 1.0, "K": 1e3, "M": 1e6, "G": 1e9}[m.group(3)]
+            seen += 1
+    return tot if seen >= 2 else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -170,7 +192,7 @@ def run_reference(args, out):
         line = {"impl": "reference", "metric": "top-25 queries/s vs 1Mx4096 db", "value": cb["value"], "unit": "queries/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb.pop("ms_per_step"),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "top-25 retrieval, 1Mx4096 fp32 db (BASELINE config 4), bounded CPU sample scaled to 1M rows"},
+                "config": workload_config(R_FULL, Q_STEP, args.gpus),
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=out, flush=True)
@@ -200,31 +222,68 @@ def timed(torch, fn, steps, warmup, dist_mod=None):
     return ms / steps
 
 
-def bench_retrieval(args, torch, dist_mod, rank, world, pk):
-    from soft_contrastive_learning_b200 import _lib, retrieval
-    L = _lib.lib()
-    R, D, Q, k = args.rows, D_FULL, args.queries, K_TOP
-    lo, hi = retrieval.shard_bounds(R, world, rank)
+def make_database(torch, synth, data, lo, hi, R, D, Q, rank, dist_mod):
+    """This rank's rows [lo, hi) of the synthetic database and the (replicated) queries, generated on the device.
+    data = "gaussian": iid N(0,1) rows, queries = perturbed random rows (planted neighbours).
+    data = "clustered": synth.trajectory_* -- consecutive frames of one drive (near-duplicates) with stops where hundreds
+    of frames coincide up to sensor noise; queries = frames of a second drive (perturbed database frames)."""
+    n = hi - lo
+    db = torch.empty((n, D), dtype=torch.float32, device="cuda")
     g = torch.Generator(device="cuda").manual_seed(42 + rank)
-    db = torch.empty((hi - lo, D), dtype=torch.float32, device="cuda")
     chunk = 65536
-    for r0 in range(0, hi - lo, chunk):          # chunked: randn's temporaries stay small
-        r1 = min(hi - lo, r0 + chunk)
-        db[r0:r1] = torch.randn((r1 - r0, D), generator=g, device="cuda")
+    info = {}
+    if data == "gaussian":
+        for r0 in range(0, n, chunk):          # chunked: randn's temporaries stay small
+            r1 = min(n, r0 + chunk)
+            db[r0:r1] = torch.randn((r1 - r0, D), generator=g, device="cuda")
+        qnoise = 0.5
+    else:
+        rng = np.random.default_rng(1234)      # the layout of the WHOLE drive is the same on every rank
+        s_all, stopped_all = synth.trajectory_layout(R, rng, stop_frac=0.06, stop_len=(100, 300))
+        seg_len = 64
+        n_anchor = int(s_all[-1] // seg_len) + 2
+        ga = torch.Generator(device="cuda").manual_seed(99)
+        anchors = torch.randn((n_anchor, D), generator=ga, device="cuda")
+        s_t = torch.tensor(s_all[lo:hi], device="cuda")
+        st_t = torch.tensor(stopped_all[lo:hi], device="cuda")
+        for r0 in range(0, n, chunk):
+            r1 = min(n, r0 + chunk)
+            noise = torch.randn((r1 - r0, D), generator=g, device="cuda")
+            db[r0:r1] = synth.trajectory_rows(s_t[r0:r1], st_t[r0:r1], anchors, seg_len, 0.05, 2e-3, noise)
+        del anchors
+        qnoise = 0.05
+        info["stopped_frac"] = float(stopped_all.mean())
+        info["stopped"] = stopped_all
     # queries = perturbed database rows (planted neighbours), identical on every rank
     gq = torch.Generator(device="cuda").manual_seed(7)
     src = torch.randint(0, R, (Q,), generator=gq, device="cuda")
-    noise = 0.5 * torch.randn((Q, D), generator=gq, device="cuda")
+    noise = qnoise * torch.randn((Q, D), generator=gq, device="cuda")
     mine = (src >= lo) & (src < hi)
     qry = torch.zeros((Q, D), dtype=torch.float32, device="cuda")
     qry[mine] = db[(src[mine] - lo)] + noise[mine]
     if dist_mod is not None:
         dist_mod.all_reduce(qry)
     del noise
+    if data == "clustered":
+        info["stopped_src"] = info.pop("stopped")[src.cpu().numpy()]
+        info["queries_on_stops"] = int(info["stopped_src"].sum())
+    return db, qry, src, info
+
+
+def retrieval_run(args, torch, dist_mod, rank, world, R, Q, data="gaussian", steps=None, warmup=None, e2e=True,
+                  time_build=False, clocks=True):
+    """One retrieval measurement: R database rows split contiguously over the ranks, Q replicated queries per step."""
+    from soft_contrastive_learning_b200 import _lib, retrieval, synth
+    L = _lib.lib()
+    D, k = D_FULL, K_TOP
+    steps = steps or args.steps
+    warmup = warmup or args.warmup
+    lo, hi = retrieval.shard_bounds(R, world, rank)
+    db, qry, src, info = make_database(torch, synth, data, lo, hi, R, D, Q, rank, dist_mod)
 
     # index build from HOST memory (H2D of the shard + shadow build), timed once
     t_build_h2d = None
-    if args.time_build and world == 1:
+    if time_build and world == 1:
         host = torch.empty((hi - lo, D), dtype=torch.float32, pin_memory=True)
         host.copy_(db)
         torch.cuda.synchronize()
@@ -239,7 +298,6 @@ def bench_retrieval(args, torch, dist_mod, rank, world, pk):
     else:
         tree = retrieval.KDTree(db, index_offset=lo)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
     if dist_mod is not None:
         index = retrieval.ShardedKDTree.__new__(retrieval.ShardedKDTree)
         index.group, index.world, index.local = None, world, tree
@@ -251,77 +309,151 @@ def bench_retrieval(args, torch, dist_mod, rank, world, pk):
     def step_dev():
         out["d"], out["i"] = index.query_device(qry, k)
 
-    # correctness guard inside the bench: planted neighbour must be rank 1
+    # correctness guard inside the bench: the planted neighbour must be rank 1 (clustered data: its distance must be the
+    # smallest, the frame itself may tie with frames of the same stop)
     step_dev()
     torch.cuda.synchronize()
-    assert bool((out["i"][:, 0] == src).all()), "planted neighbours not recovered"
-    stats = tree.stats()
-
-    sampler = ClockSampler(torch.cuda.current_device())
-    L.scl_knn_timing(1, None, None)
-    sampler.start()
-    ms = timed(torch, step_dev, args.steps, args.warmup, dist_mod)
-    # nvidia-smi needs a few hundred ms to deliver samples: when the timed region is shorter than that (small shards at
-    # N = 8: 5 steps x 10 ms), the same step keeps running untimed under the sampler until ~0.8 s of load has been seen
-    # (ms is the max over ranks, so every rank runs the same number of extra steps and the collectives stay matched)
-    loaded_s = ms * 1e-3 * (args.steps + args.warmup)
-    n_extra = int(np.ceil((0.8 - loaded_s) / (ms * 1e-3))) if loaded_s < 0.8 else 0
-    for _ in range(n_extra):
+    if data == "gaussian":
+        assert bool((out["i"][:, 0] == src).all()), "planted neighbours not recovered"
+    else:
+        # frames of one stop tie up to sensor noise, so the planted frame need not be rank 1: hold the first queries that
+        # fall on stops (and the first 32 overall) to the exact float64 scan instead, bit for bit
+        on_stop = torch.tensor(np.nonzero(info["stopped_src"])[0][:32], device="cuda", dtype=torch.long)
+        sel = torch.cat((torch.arange(32, device="cuda"), on_stop))
+        d1, i1 = tree.query_device(qry[sel], k, force_path=1)
+        assert torch.equal(i1, out["i"][sel]) and torch.equal(d1, out["d"][sel]), "clustered: tensor path != exact scan"
+    stats = tree.stats() if data == "gaussian" else None
+    if stats is None:
         step_dev()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    if n_extra:
-        clocks["untimed_steps_under_sampler"] = n_extra
+        torch.cuda.synchronize()
+        stats = tree.stats()
+    info.pop("stopped_src", None)
+
+    sampler = ClockSampler(torch.cuda.current_device()) if clocks else None
+    L.scl_knn_timing(1, None, None)
+    if sampler:
+        sampler.start()
+    ms = timed(torch, step_dev, steps, warmup, dist_mod)
+    clk = None
+    if sampler:
+        # nvidia-smi needs a few hundred ms to deliver samples: when the timed region is shorter than that (small shards at
+        # N = 8: 5 steps x 10 ms), the same step keeps running untimed under the sampler until ~0.8 s of load has been seen
+        # (ms is the max over ranks, so every rank runs the same number of extra steps and the collectives stay matched)
+        loaded_s = ms * 1e-3 * (steps + warmup)
+        n_extra = int(np.ceil((0.8 - loaded_s) / (ms * 1e-3))) if loaded_s < 0.8 else 0
+        for _ in range(n_extra):
+            step_dev()
+        torch.cuda.synchronize()
+        clk = sampler.stop()
+        if n_extra:
+            clk["untimed_steps_under_sampler"] = n_extra
     tc_ms, tc_calls = C.c_double(), C.c_int()
     L.scl_knn_timing(0, C.byref(tc_ms), C.byref(tc_calls))
     tc_avg_ms = tc_ms.value / max(1, tc_calls.value)
 
-    # end to end: pinned host queries in, host results out, every step
-    q_host = torch.empty((Q, D), dtype=torch.float32, pin_memory=True)
-    q_host.copy_(qry)
-    d_host = torch.empty((Q, k), dtype=torch.float64, pin_memory=True)
-    i_host = torch.empty((Q, k), dtype=torch.int64, pin_memory=True)
+    ms_e2e = None
+    if e2e:
+        # end to end: pinned host queries in, host results out, every step
+        q_host = torch.empty((Q, D), dtype=torch.float32, pin_memory=True)
+        q_host.copy_(qry)
+        d_host = torch.empty((Q, k), dtype=torch.float64, pin_memory=True)
+        i_host = torch.empty((Q, k), dtype=torch.int64, pin_memory=True)
 
-    def step_e2e():
-        if dist_mod is not None:
-            d, i = index.query_from_host(q_host, k)      # 1/N of the queries per rank over PCIe, all-gather over NVLink
-        else:
-            qd = q_host.to("cuda", non_blocking=True)
-            d, i = index.query_device(qd, k)
-        d_host.copy_(d, non_blocking=True)
-        i_host.copy_(i, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        def step_e2e():
+            if dist_mod is not None:
+                d, i = index.query_from_host(q_host, k)      # 1/N of the queries per rank over PCIe, all-gather over NVLink
+            else:
+                qd = q_host.to("cuda", non_blocking=True)
+                d, i = index.query_device(qd, k)
+            d_host.copy_(d, non_blocking=True)
+            i_host.copy_(i, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
-    ms_e2e = timed(torch, step_e2e, args.steps, args.warmup, dist_mod)
-    assert np.array_equal(i_host.numpy()[:, 0], src.cpu().numpy())
-
-    flops = 2.0 * Q * (hi - lo) * D
-    achieved = flops / (tc_avg_ms * 1e-3) / 1e12 if tc_avg_ms > 0 else 0.0
+        ms_e2e = timed(torch, step_e2e, steps, warmup, dist_mod)
+        if data == "gaussian":
+            assert np.array_equal(i_host.numpy()[:, 0], src.cpu().numpy())
+    rows_local = hi - lo
+    del tree, index, db, qry
+    torch.cuda.empty_cache()
+    flops = 2.0 * Q * rows_local * D
+    # launches of this repo's kernels per step: prep + per chunk (tensor pass, candidate merge, rescore, certificate) +
+    # stats (+ shard merge); refused queries add the second stage (gather, tensor pass, rescore, select)
     nf = stats["n_fallback"]
-    launches_per_step = 5 + (0 if nf == 0 else (-(-nf // 6) + -(-nf // 16))) + (1 if world > 1 else 0)
+    launches = 1 + 4 * max(1, stats["chunks"]) + 1 + (1 if world > 1 else 0) + (4 * -(-nf // 2048) if nf else 0)
+    return {"ms": ms, "ms_e2e": ms_e2e, "tc_ms": tc_avg_ms, "flops_per_launch": flops, "stats": stats, "clocks": clk,
+            "rows_local": rows_local, "build_s": t_build_h2d, "launches_per_step": launches, "info": info, "steps": steps,
+            "warmup": warmup}
+
+
+def bench_retrieval(args, torch, dist_mod, rank, world, pk):
+    R, D, Q, k = args.rows, D_FULL, args.queries, K_TOP
+    m = retrieval_run(args, torch, dist_mod, rank, world, R, Q, data=args.data, e2e=True, time_build=args.time_build)
+    ms, ms_e2e, tc_avg_ms, stats = m["ms"], m["ms_e2e"], m["tc_ms"], m["stats"]
+    achieved = m["flops_per_launch"] / (tc_avg_ms * 1e-3) / 1e12 if tc_avg_ms > 0 else 0.0
+    cfg = workload_config(R, Q, world)
+    cfg.update({"data_kind": args.data, "rows_per_gpu": m["rows_local"],
+                "l2": "inputs larger than L2 (db shard fp32+fp16 >> 126 MB); no flush",
+                "merge": "one packed NCCL all-gather of [dist|idx] + merge kernel" if world > 1 else "single shard",
+                "n_certified": stats["n_certified"], "n_refused_first_pass": stats["n_fallback"],
+                "n_resolved_by_stage2": stats["n_stage2"], "n_exact_scan": stats["n_scan"],
+                "pipeline_chunks": stats["chunks"], "index_build_from_host_s": m["build_s"]})
     line = {
         "metric": "top-25 queries/s vs 1Mx4096 db", "value": Q / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f16 x f16 -> f32 (tcgen05 candidate pass) + f64 exact rescore", "data": "synthetic",
-        "config": {"workload": f"top-{k} exact retrieval, {Q} queries/step vs {R}x{D} fp32 db (BASELINE config 4), "
-                               f"db row-sharded over {world} GPU(s), NCCL all-gather + merge",
-                   "rows_per_gpu": hi - lo, "l2": "inputs larger than L2 (db shard fp32+fp16 >> 126 MB); no flush",
-                   "exactness": stats, "index_build_from_host_s": t_build_h2d},
+        "config": cfg,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tf_sustained"], "frac_of_burst_peak": achieved / pk["tf_burst"],
                      "peak_source": f"{pk['source']} cuBLAS bf16 sustained (kernel runs ~{tc_avg_ms:.0f} ms back to back under the power cap)",
                      "kernel": "knn_tc_kernel", "kernel_ms": tc_avg_ms, "kernel_share_of_step": tc_avg_ms / ms,
-                     "algorithmic_flops_per_launch": flops,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at the full 1M-row size, from the committed
-                     # `ncu --set full` capture profiles/r1_ncu_knn_tc.txt (35.05 GB + 0.77 GB); tensor-bound kernel, so this
-                     # is context (the fp16 shard is streamed ~4x per launch), not the roofline numerator
-                     "traffic": 35.82e9 if (hi - lo) == R_FULL and Q == Q_STEP else None},
+                     "whole_step_frac": m["flops_per_launch"] / (ms * 1e-3) / 1e12 / pk["tf_sustained"],
+                     "algorithmic_flops_per_launch": m["flops_per_launch"],
+                     # dram__bytes_read.sum + dram__bytes_write.sum over the launches of one step at the full 1M-row size,
+                     # parsed from the committed `ncu --set full` digest (tensor-bound kernel: this is context -- the fp16
+                     # shard is streamed ~4x per step -- not the roofline numerator)
+                     "traffic": profile_traffic("r2_ncu_knn_tc.txt") if (m["rows_local"] == R_FULL and Q == Q_STEP) else None},
         "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": Q * D * 4 // world if world > 1 else Q * D * 4,
                 "d2h_bytes_per_step": Q * k * 16, "ms_per_step": ms_e2e},
-        "gpu_launches": launches_per_step * args.steps,
-        "clocks": clocks,
+        "gpu_launches": m["launches_per_step"] * args.steps,
+        "clocks": m["clocks"],
     }
     return line
+
+
+def bench_config5(args, torch, dist_mod, rank, world, pk):
+    """BASELINE config 5 (the north-star target): the database grows with the machine -- 1M x 4096 fp32 rows PER GPU, i.e.
+    8M rows on 8 GPUs (16.4 GB fp32 + 8.2 GB fp16 shadow per GPU; one GPU cannot hold 8M x 4096 fp32 = 131 GB plus a
+    65.5 GB shadow in 180 GB) -- and every query meets every row: queries replicated, per-shard exact top-25, one packed
+    NCCL all-gather, merge.  A subset of the 100k queries is timed (10 000 per step; throughput is linear in Q)."""
+    R5 = R_FULL * world
+    m = retrieval_run(args, torch, dist_mod, rank, world, R5, Q_STEP, data="gaussian", e2e=True, clocks=False)
+    ach = m["flops_per_launch"] / (m["tc_ms"] * 1e-3) / 1e12 if m["tc_ms"] > 0 else 0.0
+    step = m["flops_per_launch"] / (m["ms"] * 1e-3) / 1e12
+    return {"metric": f"top-25 queries/s vs {R5}x4096 db (config 5, db sharded over {world} GPUs)", "value": Q_STEP / (m["ms"] * 1e-3),
+            "unit": "queries/s", "n_gpus": world, "ms_per_step": m["ms"], "scaling": "weak (rows per GPU fixed)",
+            "config": dict(workload_config(R5, Q_STEP, world), rows_per_gpu=m["rows_local"], exactness=m["stats"],
+                           query_subset=f"{Q_STEP} of config 5's 100k queries per step"),
+            "roofline": {"bound": "tensor", "achieved_per_gpu": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / pk["tf_sustained"], "whole_step_frac_per_gpu": step / pk["tf_sustained"],
+                         "kernel": "knn_tc_kernel", "kernel_ms": m["tc_ms"], "kernel_share_of_step": m["tc_ms"] / m["ms"]},
+            "e2e": {"value": Q_STEP / (m["ms_e2e"] * 1e-3), "unit": "queries/s", "ms_per_step": m["ms_e2e"]},
+            "gpu_launches": m["launches_per_step"] * m["steps"]}
+
+
+def bench_clustered(args, torch, pk, gaussian_ms):
+    """Retrieval on clustered descriptors (consecutive frames + stops, synth.trajectory_*): how many queries the first
+    tensor pass refuses, who resolves them (second tensor stage vs float64 scan) and what the step costs next to the
+    Gaussian headline."""
+    m = retrieval_run(args, torch, None, 0, 1, R_FULL, Q_STEP, data="clustered", e2e=False, clocks=False,
+                      steps=max(3, min(args.steps, 5)), warmup=3)
+    st = m["stats"]
+    return {"metric": "top-25 queries/s vs 1Mx4096 db, clustered descriptors", "value": Q_STEP / (m["ms"] * 1e-3), "unit": "queries/s",
+            "ms_per_step": m["ms"], "step_time_vs_gaussian": m["ms"] / gaussian_ms,
+            "config": {"workload": "as the headline, db = 1M consecutive frames of one drive (great-circle path between random "
+                                   "anchors every 64 frames, 6 % of the frames in stops of 100-300 near-identical frames), queries = "
+                                   "perturbed frames", "exactness": st, **m["info"]},
+            "roofline": {"bound": "tensor", "kernel_ms_first_pass": m["tc_ms"]},
+            "gpu_launches": m["launches_per_step"] * m["steps"]}
 
 
 def bench_wms(args, torch, pk, T=4096):
@@ -343,6 +475,23 @@ def bench_wms(args, torch, pk, T=4096):
     # config 1 exactly (T=32): latency of one fused launch
     e32, d32 = emb[:32].contiguous(), dist[:32].contiguous()
     ms32 = timed(torch, lambda: losses._wms_tuple_raw(e32, d32, params, need_grad=True), 50, 10)
+    # the same launch replayed from a CUDA graph (20 launches per graph): what a captured training step pays
+    ms32_graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                losses._wms_tuple_raw(e32, d32, params, need_grad=True)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(20):
+                keep = losses._wms_tuple_raw(e32, d32, params, need_grad=True)
+        ms32_graph = timed(torch, graph.replay, 20, 5) / 20
+        del graph, keep
+    except Exception as e:                 # never cost the line
+        print("cuda graph replay failed:", repr(e)[:200], file=sys.stderr)
     # end to end from pinned host buffers
     eh = torch.empty(emb.shape, dtype=torch.float32, pin_memory=True)
     eh.copy_(emb)
@@ -363,13 +512,15 @@ def bench_wms(args, torch, pk, T=4096):
     cb = wms_cpu_port()
     return {"metric": "wms loss fwd+bwd tuples/s", "value": T / (ms * 1e-3), "unit": "tuples/s", "ms_per_step": ms,
             "dtype": "f32", "config": {"workload": f"wms tuple mode, T={T} S={S} D={D} fp32 (config 1 shape x{T // 32}; inputs 3.4 GB > L2)",
-                                       "config1_T32_us_per_launch": ms32 * 1e3, "config1_T32_tuples_per_s": 32 / (ms32 * 1e-3)},
+                                       "config1_T32_us_per_launch": ms32 * 1e3, "config1_T32_tuples_per_s": 32 / (ms32 * 1e-3),
+                                       "config1_T32_us_per_launch_cuda_graph": None if ms32_graph is None else ms32_graph * 1e3,
+                                       "config1_T32_hbm_frac_cuda_graph": None if ms32_graph is None else
+                                       32 * (2 * S * D * 4 + S * S * 4) / (ms32_graph * 1e-3) / 1e9 / pk["hbm_gbs"]},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                          "peak_source": pk["source"], "kernel": "wms_stream_kernel<5,7,224,packed Gram,tensor-core backward>",
                          "algorithmic_bytes_per_tuple": 2 * S * D * 4 + S * S * 4,
-                         # dram read + write of one launch (T=4096) from profiles/r1_ncu_wms.txt: 2.51 + 1.63 GB vs 3.37 GB
-                         # algorithmic -- the backward's second read of the tuple misses L2 about half of the time
-                         "traffic": 4.14e9 if T == 4096 else None},
+                         # dram read + write of one launch (T=4096), parsed from the committed `ncu --set full` digest
+                         "traffic": profile_traffic("r2_ncu_wms.txt") if T == 4096 else None},
             "e2e": {"value": T / (ms_e2e * 1e-3), "unit": "tuples/s", "h2d_bytes_per_step": int(emb.numel() * 4 + dist.numel() * 4),
                     "d2h_bytes_per_step": int(emb.numel() * 4 + 4)},
             "cpu_baseline": cb, "gpu_launches": max(args.steps, 10)}
@@ -412,6 +563,33 @@ def bench_wms_sharded(args, torch, dist_mod, rank, world, pk, T_local=4096):
                                    "one scalar all-reduce per step, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"] * world, "unit": "GB/s",
                          "frac": gbs / (pk["hbm_gbs"] * world), "peak_source": pk["source"] + f" x {world} GPUs"},
+            "gpu_launches": max(args.steps, 10)}
+
+
+def bench_netvlad_sharded(args, torch, dist_mod, rank, world, pk, B_local=32, H=30, W=40, Cc=512, K=64):
+    """SURVEY 8e row 4 (N > 1): the images of the batch split over the ranks (B_local per GPU, weak scaling), weights
+    replicated, forward + backward per rank and ONE NCCL all-reduce of the packed [dW | dC]."""
+    from soft_contrastive_learning_b200 import sharded
+    g = torch.Generator(device="cuda").manual_seed(42 + rank)
+    x = torch.randn((B_local, H * W, Cc), generator=g, device="cuda")
+    gw = torch.Generator(device="cuda").manual_seed(1)
+    aw = 0.05 * torch.randn((Cc, K), generator=gw, device="cuda")
+    cc = 0.05 * torch.randn((Cc, K), generator=gw, device="cuda")
+    dout = torch.randn((B_local, Cc * K), generator=g, device="cuda") / (B_local * world)
+    out = {}
+
+    def step():
+        out["r"] = sharded.netvlad_step_sharded(x, aw, cc, lambda v: dout)
+
+    ms = timed(torch, step, max(args.steps, 10), 3, dist_mod)
+    dw = out["r"][2]
+    chk = dw.clone()
+    dist_mod.all_reduce(chk, op=dist_mod.ReduceOp.MAX)
+    same = bool(torch.equal(chk, dw))
+    return {"metric": "NetVLAD head fwd+bwd images/s, batch-parallel", "value": world * B_local / (ms * 1e-3), "unit": "images/s",
+            "ms_per_step": ms, "n_gpus": world, "scaling": "weak",
+            "config": {"workload": f"B={B_local} images per GPU x {world} GPUs, {H}x{W}x{Cc} maps, K={K}; one all-reduce of [dW|dC] "
+                                   f"({2 * Cc * K * 4} bytes) per step", "grads_identical_on_all_ranks": same},
             "gpu_launches": max(args.steps, 10)}
 
 
@@ -533,6 +711,7 @@ def main():
     ap.add_argument("--workload", default="retrieval", choices=["retrieval", "wms", "netvlad", "losses"])
     ap.add_argument("--rows", type=int, default=R_FULL)
     ap.add_argument("--queries", type=int, default=Q_STEP)
+    ap.add_argument("--data", default="gaussian", choices=["gaussian", "clustered"])
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--time-build", action="store_true", default=True)
@@ -563,37 +742,86 @@ def main():
                      "scaling": "weak", "vs_baseline": None, "data": "synthetic"})
     else:
         line = bench_retrieval(args, torch, dist_mod, rank, world, pk)
+        cfg = line["config"]          # flat scalar keys: the driver's parser keeps them (it drops `secondary`)
         if rank == 0 and world == 1:
             if not args.no_cpu_baseline:
                 line["cpu_baseline"] = kdtree_reference(steps=1, warmup=0)
                 line["cpu_baseline"].pop("ms_per_step", None)
             if not args.no_secondary:
-                torch.cuda.empty_cache()
-                line["secondary"] = [bench_wms(args, torch, pk)]
-                for fn in (bench_netvlad_pca, bench_losses_cfg3):
+                line["secondary"] = []
+
+                def secondary(fn, *a):
                     torch.cuda.empty_cache()
                     try:
-                        line["secondary"].append(fn(args, torch, pk))
+                        r = fn(*a)
                     except Exception as e:          # a secondary line must never cost the headline
-                        line["secondary"].append({"metric": fn.__name__, "error": repr(e)[:300]})
+                        r = {"metric": fn.__name__, "error": repr(e)[:300]}
+                    line["secondary"].append(r)
+                    return r
+                w = secondary(bench_wms, args, torch, pk)
+                if "error" not in w:
+                    cfg.update({"wms_t4096_tuples_per_s": w["value"], "wms_t4096_ms": w["ms_per_step"],
+                                "wms_t4096_hbm_frac": w["roofline"]["frac"],
+                                "wms_config1_t32_us_per_launch": w["config"]["config1_T32_us_per_launch"],
+                                "wms_config1_t32_us_cuda_graph": w["config"]["config1_T32_us_per_launch_cuda_graph"],
+                                "wms_e2e_tuples_per_s": w["e2e"]["value"], "wms_cpu_port_tuples_per_s": w["cpu_baseline"]["value"]})
+                nv = secondary(bench_netvlad_pca, args, torch, pk)
+                if "error" not in nv:
+                    t = nv["config"]["ms"]["fp32-grade 3xTF32"]
+                    cfg.update({"cfg2_netvlad_pca_ms_per_step": nv["ms_per_step"], "cfg2_netvlad_fwd_ms": t["netvlad_fwd"],
+                                "cfg2_netvlad_bwd_ms": t["netvlad_bwd"], "cfg2_pca_fwd_ms": t["pca_fwd"], "cfg2_pca_bwd_ms": t["pca_bwd"],
+                                "cfg2_hbm_frac": nv["roofline"]["hbm_view"]["frac"], "cfg2_images_per_s": nv["value"]})
+                ls = secondary(bench_losses_cfg3, args, torch, pk)
+                if "error" not in ls:
+                    cfg.update({"cfg3_all_losses_sweep_ms": ls["ms_per_step"],
+                                "cfg3_triplet_us": ls["config"]["ms_per_loss"]["triplet"] * 1e3,
+                                "cfg3_wms_flat_b1024_us": ls["config"]["ms_per_loss"]["wms (flat, B=1024)"] * 1e3})
+                if args.data == "gaussian" and args.rows == R_FULL:
+                    cl = secondary(bench_clustered, args, torch, pk, line["ms_per_step"])
+                    if "error" not in cl:
+                        st = cl["config"]["exactness"]
+                        cfg.update({"clustered_queries_per_s": cl["value"], "clustered_ms_per_step": cl["ms_per_step"],
+                                    "clustered_step_time_vs_gaussian": cl["step_time_vs_gaussian"],
+                                    "clustered_n_refused_first_pass": st["n_fallback"], "clustered_n_resolved_by_stage2": st["n_stage2"],
+                                    "clustered_n_exact_scan": st["n_scan"]})
         if world > 1 and not args.no_secondary:
             # a secondary line must never cost the headline: if a rank fails and the others wait in a collective, a
             # watchdog prints the headline alone and ends the process
+            line["secondary"] = []
+
             def bail():
                 if rank == 0:
-                    line["secondary"] = [{"metric": "bench_wms_sharded", "error": "timed out"}]
+                    line["secondary"].append({"metric": "secondary", "error": "timed out"})
                     print(json.dumps(line), file=real_stdout, flush=True)
                 os._exit(0)
-            dog = threading.Timer(120.0, bail)
+            dog = threading.Timer(300.0, bail)
             dog.daemon = True
             dog.start()
             torch.cuda.empty_cache()
             try:
+                c5 = bench_config5(args, torch, dist_mod, rank, world, pk)
+                cfg.update({"cfg5_rows": R_FULL * world, "cfg5_queries_per_s": c5["value"], "cfg5_ms_per_step": c5["ms_per_step"],
+                            "cfg5_tensor_frac_per_gpu": c5["roofline"]["frac"],
+                            "cfg5_whole_step_frac_per_gpu": c5["roofline"]["whole_step_frac_per_gpu"],
+                            "cfg5_kernel_share_of_step": c5["roofline"]["kernel_share_of_step"],
+                            "cfg5_e2e_queries_per_s": c5["e2e"]["value"], "cfg5_n_refused": c5["config"]["exactness"]["n_fallback"]})
+            except Exception as e:
+                c5 = {"metric": "bench_config5", "error": repr(e)[:300]}
+            line["secondary"].append(c5)
+            torch.cuda.empty_cache()
+            try:
                 sec = bench_wms_sharded(args, torch, dist_mod, rank, world, pk)
+                cfg.update({"wms_sharded_tuples_per_s": sec["value"], "wms_sharded_hbm_frac": sec["roofline"]["frac"]})
             except Exception as e:
                 sec = {"metric": "bench_wms_sharded", "error": repr(e)[:300]}
+            line["secondary"].append(sec)
+            try:
+                nvs = bench_netvlad_sharded(args, torch, dist_mod, rank, world, pk)
+                cfg.update({"netvlad_dp_images_per_s": nvs["value"], "netvlad_dp_ms_per_step": nvs["ms_per_step"]})
+            except Exception as e:
+                nvs = {"metric": "bench_netvlad_sharded", "error": repr(e)[:300]}
+            line["secondary"].append(nvs)
             dog.cancel()
-            line["secondary"] = [sec]
     if rank == 0:
         print(json.dumps(line), file=real_stdout, flush=True)
     if dist_mod is not None:

@@ -10,8 +10,12 @@
  *    row-major, contiguous, 16-byte aligned; outputs are pre-allocated by the caller;
  *  - scalar results (losses) are written to device memory: no entry point synchronises the stream
  *    except where stated (scl_knn_query);
- *  - no global mutable state: workspace and stream are per call, so concurrent calls from several host
- *    threads are safe when they use different workspaces (train.py runs up to three threads per session);
+ *  - workspace and stream are per call, so concurrent calls from several host threads are safe when they use
+ *    different workspaces (train.py runs up to three threads per session).  The ONLY process-wide mutable state is
+ *    the explicitly documented set of knobs below -- scl_set_tuning (initialised once from SCL_* environment
+ *    variables when the library is loaded; no entry point calls getenv), scl_set_gemm_precision and the
+ *    scl_knn_timing measurement hook (mutex-guarded) -- set them before concurrent use.  Per-device attributes
+ *    (dynamic shared-memory limits) are cached per device ordinal, so one process may drive several GPUs;
  *  - return value 0 on success, a negative scl_status otherwise; never throws, never exits;
  *  - there is no CPU fallback: on a device that is not compute capability 10.x every compute entry point
  *    returns SCL_ERR_ARCH.
@@ -43,6 +47,15 @@ int scl_version(void);
 const char* scl_strerror(int status);
 const char* scl_last_error(void); /* thread-local detail string of the last SCL_ERR_CUDA */
 int scl_device_ok(void);          /* 0 when the current device is compute capability 10.x */
+
+/* Process-wide tuning / test knobs, by the name of the environment variable that initialises them at load time:
+ *   SCL_WMS_STREAM, SCL_WMS_STREAM_CFG, SCL_WMS_CLUSTER, SCL_WMS_CHUNKED, SCL_TUPLE_CLUSTER, SCL_KNN_TC_VARIANT,
+ *   SCL_KNN_SYNC, SCL_KNN_SYNC_WINDOW, SCL_KNN_SYNC_SUBS, SCL_KNN_RANGES, SCL_KNN_GROUP_M, SCL_KNN_CHUNK_Q,
+ *   SCL_KNN_STAGE2, SCL_GEMM_SIMT, SCL_NV_FUSED.
+ * value = INT32_MIN restores "unset" (the built-in choice).  They select between kernels that compute the same result
+ * (the parity tests force each one); unknown names return SCL_ERR_BAD_ARG. */
+int scl_set_tuning(const char* name, int value);
+int scl_get_tuning(const char* name, int* value);
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-similarity family parameters.
@@ -178,7 +191,8 @@ int scl_pca_center(const float* x, int n, int D, float* mean, float* xc, void* w
 
 /* Precision of the tensor-core contractions (PCA, flat-mode Gram and its backward): 0 = fp32-grade 3xTF32 (default:
  * meets the 1e-5 tolerance of the reference's fp32 graph), 1 = one TF32 pass (relative error ~1e-3, three times the
- * throughput).  Process-wide setting. */
+ * throughput).  PROCESS-WIDE setting (one of the documented knobs, see the conventions at the top): set it before
+ * concurrent use; scl_gemm_tf32 takes the precision per call. */
 int scl_set_gemm_precision(int mode);
 int scl_get_gemm_precision(void);
 /* The contraction engine itself: C[M,N] = A . B^T (* colscale[n]) on tcgen05 kind::tf32.
@@ -197,12 +211,20 @@ int scl_gemm_tf32(const float* A, const float* B, float* C, int M, int N, int K,
  *   scl_knn_shadow_bytes   size of the shadow for R rows
  *   scl_knn_build          fills the shadow from db [R,D] f32 (one pass over the database)
  *   scl_knn_query          dist [Q,k] f64 Euclidean ascending, idx [Q,k] i64 = local row + idx_offset,
- *                          ties ordered by index; exact (every query is either certified against the
- *                          fp16 rounding bound or recomputed by the exact fp32->fp64 path).
- *                          stats (optional, device i32[4]): {n_queries, n_certified, n_fallback, path}
- *   force_path: 0 auto, 1 exact scan only, 2 tensor pass (+fallback), 3 tensor pass with every query
- *               forced through the fallback as well (test hook).
- * Requires D % 4 == 0, k <= 1024 (tensor pass used when k <= 32 and the problem is large enough). */
+ *                          ties ordered by index; exact: every query is either certified against the fp16 rounding
+ *                          bound, or resolved by the second tensor stage (all rows inside the bound collected and
+ *                          rescored), or recomputed by the exact fp32->fp64 scan.
+ *                          stats (optional, device i32[8]): {n_queries, n_certified, n_refused by the first pass,
+ *                          path, n_resolved_by_stage2, n_exact_scan, pipeline_chunks, 0}
+ *   force_path: 0 auto, 1 exact scan only, 2 tensor pass (+ stage 2 / scan as needed), 3 tensor pass with every query
+ *               forced through the exact scan as well, 4 ... through stage 2 as well (test hooks).
+ * Requires D % 4 == 0, k <= 1024.  The tensor pass keeps k' = 64 candidates per query and needs slack above k: it is
+ * used for k <= 32 (top-n.py N = 25, train.py k = 5) when Q*R >= 2^22 and R >= 4096; larger k -- the hard-negative
+ * mining cache of train.py:451, k = MINING_CACHE_SIZE = 1000 -- always takes the exact float64 scan.  k > R pads the
+ * tail with (inf, -1) where sklearn raises.
+ * Synchronisation: a fully certified call synchronises the stream once (to learn that nothing was refused); a call
+ * with refused queries synchronises a second time.  Queries are processed in chunks; the merge / rescore / certificate
+ * of one chunk run on an internal helper stream under the tensor pass of the next (joined before the call returns). */
 int scl_knn_shadow_bytes(int64_t R, int D, size_t* bytes);
 int scl_knn_build(const float* db, int64_t R, int D, void* shadow, size_t shadow_bytes, scl_stream_t stream);
 int scl_knn_query_workspace_bytes(int64_t R, int D, int Q, int k, size_t* bytes);
@@ -210,14 +232,20 @@ int scl_knn_query(const float* db, const void* shadow, int64_t R, int D, const f
                   int64_t idx_offset, int force_path, double* dist, int64_t* idx, int32_t* stats,
                   void* workspace, size_t workspace_bytes, scl_stream_t stream);
 
-/* Measurement hook (bench.py): returns the accumulated device time (CUDA events on the launching stream) and the
+/* Test hook: when set (per host thread) and capacity_floats >= Q*R, the tensor pass of the following scl_knn_query
+ * calls on this thread also writes its raw fp16-pass scores [Q,R] there.  NULL switches it off. */
+int scl_knn_set_debug_scores(float* scores, size_t capacity_floats);
+
+/* Measurement hook (bench.py), process-wide and mutex-guarded: returns the accumulated device time (CUDA events on the launching stream) and the
  * number of launches of the tensor-pass kernel since the last reset, then, if enable >= 0, resets the counters and
  * switches the timing on (1) or off (0).  Pass enable = -1 to read without resetting. */
 int scl_knn_timing(int enable, double* tensor_pass_ms_sum, int* tensor_pass_calls);
 
-/* Merge of G per-shard sorted top-k lists (after an all-gather): d_all [G,Q,k] f64, i_all [G,Q,k] i64
- * -> d [Q,k], i [Q,k], ordered by (distance, index).  SURVEY.md section 8(e). */
-int scl_topk_merge(const double* d_all, const int64_t* i_all, int G, int Q, int k,
+/* Merge of G per-shard sorted top-k lists (after an all-gather) -> d [Q,k], i [Q,k], ordered by (distance, index).
+ * Shard g's lists are d_all + g*shard_stride and i_all + g*shard_stride (elements; 0 = Q*k, i.e. dense [G,Q,k]
+ * arrays): a packed per-rank message [dist Q*k | idx Q*k] gathered ONCE is merged in place with
+ * d_all = buf, i_all = buf + Q*k, shard_stride = 2*Q*k.  SURVEY.md section 8(e). */
+int scl_topk_merge(const double* d_all, const int64_t* i_all, int G, int Q, int k, int64_t shard_stride,
                    double* d, int64_t* i, scl_stream_t stream);
 
 /* R2: geographic bookkeeping of evaluation/top-n.py:69,110-113 without materialising the [Q,R] matrix:

@@ -40,6 +40,8 @@ PROTOTYPES = {
     "scl_strerror": (C.c_char_p, [C.c_int]),
     "scl_last_error": (C.c_char_p, []),
     "scl_device_ok": (C.c_int, []),
+    "scl_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
+    "scl_get_tuning": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "scl_wms_tuple_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, _SIZE_P]),
     "scl_wms_tuple_fwd_bwd": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.POINTER(MsParams), c_ptr, c_ptr,
                                         c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
@@ -76,7 +78,8 @@ PROTOTYPES = {
     "scl_knn_query": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int64, C.c_int, c_ptr,
                                 c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_knn_timing": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
-    "scl_topk_merge": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "scl_knn_set_debug_scores": (C.c_int, [c_ptr, C.c_size_t]),
+    "scl_topk_merge": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int64, c_ptr, c_ptr, c_ptr]),
     "scl_geo_topn": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int64, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "scl_recall_curves": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr]),
 }
@@ -103,6 +106,38 @@ def lib():
                     fn.argtypes = args
                 _lib = handle
     return _lib
+
+
+TUNING_UNSET = -2 ** 31
+
+
+def set_tuning(name: str, value=None) -> None:
+    """Process-wide kernel-selection knob (include/scl_b200.h: scl_set_tuning); ``None`` restores the built-in choice."""
+    check(lib().scl_set_tuning(name.encode(), TUNING_UNSET if value is None else int(value)), f"scl_set_tuning({name})")
+
+
+def get_tuning(name: str):
+    v = C.c_int()
+    check(lib().scl_get_tuning(name.encode(), C.byref(v)), f"scl_get_tuning({name})")
+    return None if v.value == TUNING_UNSET else v.value
+
+
+class tuning:
+    """``with tuning(SCL_WMS_STREAM=1, SCL_WMS_STREAM_CFG=2): ...`` -- set knobs, restore the previous values on exit."""
+
+    def __init__(self, **knobs):
+        self.knobs = knobs
+
+    def __enter__(self):
+        self.saved = {k: get_tuning(k) for k in self.knobs}
+        for k, v in self.knobs.items():
+            set_tuning(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.saved.items():
+            set_tuning(k, v)
+        return False
 
 
 def check(status: int, what: str = "") -> None:

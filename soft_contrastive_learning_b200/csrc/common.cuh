@@ -1,6 +1,8 @@
 // common.cuh -- shared helpers for libscl_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -12,6 +14,36 @@ namespace scl {
 void set_last_error(const char* what, cudaError_t e);
 int check_device();  // SCL_OK or SCL_ERR_ARCH / SCL_ERR_CUDA
 int num_sms();
+int device_slot();   // ordinal of the current device, clamped to [0, kMaxDevices)
+constexpr int kMaxDevices = 64;
+
+// Process-wide tuning knobs (include/scl_b200.h: scl_set_tuning / scl_get_tuning).  Each knob is read from its SCL_*
+// environment variable ONCE, when the library is loaded; afterwards only scl_set_tuning changes it.  No entry point calls
+// getenv.
+enum Knob {
+  KNOB_WMS_STREAM = 0,      // 0 never / 1 always use the streaming wms kernel (unset: batches >= #SMs tuples)
+  KNOB_WMS_STREAM_CFG,      // streaming kernel variant (wms_tuple_stream.cu)
+  KNOB_WMS_CLUSTER,         // CTAs per tuple of the cluster kernels (1, 2, 4, 8)
+  KNOB_WMS_CHUNKED,         // 1: skip the resident kernel
+  KNOB_TUPLE_CLUSTER,       // CTAs per tuple of the triplet-family kernel
+  KNOB_KNN_TC_VARIANT,      // 1 single CTA, 2 CTA pair (default), 3 CTA pair 256x512
+  KNOB_KNN_SYNC, KNOB_KNN_SYNC_WINDOW, KNOB_KNN_SYNC_SUBS, KNOB_KNN_RANGES, KNOB_KNN_GROUP_M,
+  KNOB_KNN_CHUNK_Q,         // queries per pipelined chunk of scl_knn_query (0: one chunk)
+  KNOB_KNN_STAGE2,          // 0: uncertified queries go straight to the exact scan (skip the split-fp16 second stage)
+  KNOB_GEMM_SIMT,           // 1: FP32 FFMA GEMM instead of tcgen05
+  KNOB_NV_FUSED,            // 0: NetVLAD through the generic GEMM engine instead of the fused kernels
+  KNOB_COUNT
+};
+constexpr int kKnobUnset = -2147483647 - 1;
+int knob(Knob k);                                    // kKnobUnset when not set
+static inline int knob_or(Knob k, int dflt) { const int v = knob(k); return v == kKnobUnset ? dflt : v; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: the cache of "already raised
+// to X bytes" is keyed by the device ordinal.  Idempotent; a race between host threads is benign.
+struct SmemAttrCache {
+  std::atomic<size_t> bytes[kMaxDevices];
+};
+int ensure_dyn_smem(const void* func, size_t bytes, SmemAttrCache* cache);
 
 #define SCL_CUDA_TRY(expr)                                   \
   do {                                                       \

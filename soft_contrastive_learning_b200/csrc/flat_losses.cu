@@ -167,7 +167,7 @@ static int flat_run(const float* emb, const float* dist, const int32_t* labels, 
 
   // G = E E^T and dE = M E run on the tcgen05 GEMM (fp32-grade 3xTF32 unless scl_set_gemm_precision(1)); shapes
   // whose row pitch TMA cannot address (B or D not a multiple of 4) use the FP32 FFMA GEMM
-  const bool tc = (B % 4 == 0) && (D % 4 == 0) && aligned16(emb) && (!demb || aligned16(demb)) && !getenv("SCL_GEMM_SIMT");
+  const bool tc = (B % 4 == 0) && (D % 4 == 0) && aligned16(emb) && (!demb || aligned16(demb)) && knob_or(KNOB_GEMM_SIMT, 0) == 0;
   if (tc) {
     TcGemmDesc d = {};
     d.A = emb; d.B = emb; d.C = w.G; d.M = B; d.N = B; d.K = D; d.lda = D; d.ldb = D; d.ldc = B;

@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 
 #include "knn_internal.cuh"
 
@@ -350,9 +352,10 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __res
                                                            const double* __restrict__ d2, const float* __restrict__ sel_T,
                                                            const int* __restrict__ sel_n, const double* __restrict__ qn2,
                                                            const int* __restrict__ qexp, const ShadowHeader* __restrict__ h,
-                                                           int Q, int k, long long idx_offset, int force_all,
+                                                           int Q, int k, long long idx_offset, int force_all, int q0,
                                                            double* __restrict__ out_d, long long* __restrict__ out_i,
-                                                           int* __restrict__ flag_list, int* __restrict__ stats) {
+                                                           double* __restrict__ kth_d2, int* __restrict__ flag_list,
+                                                           int* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
@@ -394,11 +397,12 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __res
       ok = kth < double(sel_T[q]) + qn2[q] - eps;
     }
     if (force_all) ok = false;
+    kth_d2[q] = kth;                                // k-th smallest exact d^2 among the rescored candidates (inf: fewer than k)
     if (ok) {
       atomicAdd(&stats[1], 1);
     } else {
       const int slot = atomicAdd(&stats[2], 1);
-      flag_list[slot] = q;
+      flag_list[slot] = q0 + q;                     // all pointers of this launch are chunk-relative; the list is global
     }
   }
 }
@@ -554,22 +558,24 @@ __device__ __forceinline__ bool pair_less(double d0, long long i0, double d1, lo
   return d0 < d1 || (d0 == d1 && i0 < i1);
 }
 
+// shard g's lists start at d_all + g*stride / i_all + g*stride (elements): lets one packed all-gather buffer
+// [G][dist Q*k | idx Q*k] feed the merge without a repack
 __global__ void __launch_bounds__(256) topk_merge_kernel(const double* __restrict__ d_all, const long long* __restrict__ i_all,
-                                                         int G, int Q, int k, double* __restrict__ d,
+                                                         int G, int Q, int k, long long stride, double* __restrict__ d,
                                                          long long* __restrict__ i) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)G * Q * k) return;
   const int g = int(e / ((long long)Q * k));
   const long long rem = e - (long long)g * Q * k;
   const int q = int(rem / k), j = int(rem - (long long)q * k);
-  const double md = d_all[e];
-  const long long mi = i_all[e];
+  const double md = d_all[(size_t)g * stride + rem];
+  const long long mi = i_all[(size_t)g * stride + rem];
   // rank = number of entries, over all shard lists of this query, that order before (md, mi)
   int rank = j;    // entries before it in its own (sorted) list
   for (int g2 = 0; g2 < G; ++g2) {
     if (g2 == g) continue;
-    const double* ld = d_all + ((size_t)g2 * Q + q) * k;
-    const long long* li = i_all + ((size_t)g2 * Q + q) * k;
+    const double* ld = d_all + (size_t)g2 * stride + (size_t)q * k;
+    const long long* li = i_all + (size_t)g2 * stride + (size_t)q * k;
     int lo = 0, hi = k;                 // first position whose entry is NOT less than mine
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
@@ -645,31 +651,175 @@ __global__ void recall_scale_kernel(double* curves, int n, int Q) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// stage 2 (tensor pass, "collect" mode): queries the first pass could not certify
+// ---------------------------------------------------------------------------------------------
+// The first pass refuses a query when more than k' = 64 rows lie within the fp16 rounding bound of its k-th neighbour
+// (near-duplicate descriptors: consecutive frames of a standing vehicle).  Its k rescored candidates still give an
+// UPPER bound e_k on the exact k-th squared distance, and every true top-k row r satisfies
+//     score16(r) <= exact(r) + eps <= (e_k - |q|^2) + eps.
+// Stage 2 reruns the tensor pass for the refused queries only, with that fixed threshold, and keeps EVERY row below it
+// (up to kCollectCap); all of them are rescored exactly and the k best are emitted.  Exact unless the list overflows
+// (more than kCollectCap rows inside the bound), in which case the query goes to the float64 scan.
+__global__ void __launch_bounds__(256) knn_stage2_gather_kernel(const int* __restrict__ flag_list, int f0, int n2, int Dp,
+                                                                const __half* __restrict__ qh, const float* __restrict__ qmul,
+                                                                const double* __restrict__ qn2, const int* __restrict__ qexp,
+                                                                const double* __restrict__ kth_d2,
+                                                                const ShadowHeader* __restrict__ h, __half* __restrict__ qh2,
+                                                                float* __restrict__ qmul2, float* __restrict__ thr2,
+                                                                int* __restrict__ cnt2) {
+  const int f = blockIdx.x;
+  if (f >= n2) return;
+  const int q = flag_list[f0 + f];
+  const uint4* src = reinterpret_cast<const uint4*>(qh + size_t(q) * Dp);
+  uint4* dst = reinterpret_cast<uint4*>(qh2 + size_t(f) * Dp);
+  for (int c = threadIdx.x; c < (Dp >> 3); c += blockDim.x) dst[c] = src[c];
+  if (threadIdx.x == 0) {
+    qmul2[f] = qmul[q];
+    cnt2[f] = 0;
+    const double bound = kth_d2[q] - qn2[q] + knn_eps(sqrt(qn2[q]), qexp[q], h);
+    // the kernel tests score < thr: round the bound up and step once more so that equality passes
+    float t = isfinite(bound) ? __double2float_ru(bound) : INFINITY;
+    if (isfinite(t)) t = nextafterf(t, INFINITY);
+    thr2[f] = t;
+  }
+}
+
+// exact squared distances of the collected rows: one warp per (refused query, list slot); same arithmetic as
+// knn_rescore_kernel / knn_scan_kernel (bit-identical d^2)
+__global__ void __launch_bounds__(256) knn_stage2_rescore_kernel(const float* __restrict__ db, const float* __restrict__ q,
+                                                                 int D, const int* __restrict__ flag_list, int f0,
+                                                                 const uint32_t* __restrict__ coll_idx,
+                                                                 const int* __restrict__ cnt2, long long pairs,
+                                                                 double* __restrict__ d2) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= pairs) return;
+  const int f = int(p / kCollectCap), e = int(p - (long long)f * kCollectCap);
+  const int n = cnt2[f];
+  if (n > kCollectCap || e >= n) return;
+  const int qi = flag_list[f0 + f];
+  const uint32_t r = coll_idx[p];
+  const float4* qr = reinterpret_cast<const float4*>(q + size_t(qi) * D);
+  const float4* rr = reinterpret_cast<const float4*>(db + size_t(r) * D);
+  double acc = 0.0;
+  for (int c = lane; c < (D >> 2); c += 32) {
+    const float4 a = __ldg(qr + c);
+    const float4 b = ldg_stream(rr + c);
+    double d;
+    d = double(a.x) - double(b.x); acc = fma(d, d, acc);
+    d = double(a.y) - double(b.y); acc = fma(d, d, acc);
+    d = double(a.z) - double(b.z); acc = fma(d, d, acc);
+    d = double(a.w) - double(b.w); acc = fma(d, d, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) d2[p] = acc;
+}
+
+// one CTA per refused query: order the collected rows by (d^2, idx), emit the top-k; overflowed lists go to the scan
+__global__ void __launch_bounds__(256) knn_stage2_select_kernel(const int* __restrict__ flag_list, int f0,
+                                                                const uint32_t* __restrict__ coll_idx,
+                                                                const int* __restrict__ cnt2, const double* __restrict__ d2,
+                                                                int k, long long idx_offset, double* __restrict__ out_d,
+                                                                long long* __restrict__ out_i, int* __restrict__ flag2_list,
+                                                                int* __restrict__ stats) {
+  extern __shared__ unsigned char sel2_smem[];
+  SelKey* keys = reinterpret_cast<SelKey*>(sel2_smem);      // [kCollectCap]
+  const int f = blockIdx.x;
+  const int q = flag_list[f0 + f];
+  const int n = cnt2[f];
+  if (n > kCollectCap || n < k) {                            // overflow (or an unusable bound): exact scan
+    if (threadIdx.x == 0) flag2_list[atomicAdd(&stats[5], 1)] = q;
+    return;
+  }
+  int n_pow2 = 32;
+  while (n_pow2 < n) n_pow2 <<= 1;
+  for (int e = threadIdx.x; e < n_pow2; e += blockDim.x) {
+    SelKey key;
+    if (e < n) {
+      key.d = (unsigned long long)__double_as_longlong(d2[size_t(f) * kCollectCap + e]);
+      key.i = coll_idx[size_t(f) * kCollectCap + e];
+    } else {
+      key.d = ~0ull; key.i = ~0ull;
+    }
+    keys[e] = key;
+  }
+  bitonic_sort_smem(keys, n_pow2);
+  for (int e = threadIdx.x; e < k; e += blockDim.x) {
+    out_d[size_t(q) * k + e] = sqrt(__longlong_as_double((long long)keys[e].d));
+    out_i[size_t(q) * k + e] = (long long)keys[e].i + idx_offset;
+  }
+  if (threadIdx.x == 0) atomicAdd(&stats[4], 1);
+}
+
+// stats out: {n_queries, n_certified, n_refused by the first pass, path, n_stage2, n_scan, chunks, 0}
+struct StatsOut { int v[8]; };
+__global__ void knn_stats_out_kernel(int* __restrict__ out, StatsOut s) {
+  if (threadIdx.x < 8) out[threadIdx.x] = s.v[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
 // orchestration
 // ---------------------------------------------------------------------------------------------
+// Measurement hook state (scl_knn_timing): process-wide, guarded by a mutex.
 static std::atomic<int> g_knn_timing{0};
-static std::atomic<double> g_knn_tc_ms_sum{0.0};
-static std::atomic<int> g_knn_tc_calls{0};
+static std::mutex g_knn_timing_mu;
+static double g_knn_tc_ms_sum = 0.0;
+static int g_knn_tc_calls = 0;
+
+// test hook (scl_knn_set_debug_scores): per host thread, size-checked
+static thread_local float* t_dbg_scores = nullptr;
+static thread_local size_t t_dbg_capacity = 0;
+
+// Per host thread and device: the helper stream on which the candidate merge / exact rescore / certificate of query chunk
+// i run while the tensor pass of chunk i+1 occupies the launching stream, and the events that order the two.
+struct HelperCtx {
+  cudaStream_t h = nullptr;
+  std::vector<cudaEvent_t> ev;          // ordering events (timing disabled)
+  std::vector<cudaEvent_t> tev;         // timing events (scl_knn_timing)
+  int get(std::vector<cudaEvent_t>& pool, size_t i, unsigned flags, cudaEvent_t* out) {
+    while (pool.size() <= i) {
+      cudaEvent_t e;
+      SCL_CUDA_TRY(cudaEventCreateWithFlags(&e, flags));
+      pool.push_back(e);
+    }
+    *out = pool[i];
+    return SCL_OK;
+  }
+};
+static thread_local HelperCtx t_helper[kMaxDevices];
 
 struct QueryWs {
+  // per query (all Q)
   __half* qh;
   float* qmul;
   double* qn2;
   int* qexp;
-  float* cand_s;
-  uint32_t* cand_i;
-  int* cand_cnt;
   unsigned int* q_thr;
-  unsigned int* sync_ctr;
   uint32_t* sel_idx;
   float* sel_T;
   int* sel_n;
   double* d2;
+  double* kth_d2;
   int* flag_list;
+  int* flag2_list;
   int* stats;
+  // per pipeline slot (two chunks in flight)
+  float* cand_s[2];
+  uint32_t* cand_i[2];
+  int* cand_cnt[2];
+  unsigned int* sync_ctr[2];
+  // stage 2
+  __half* qh2;
+  float* qmul2;
+  float* thr2;
+  int* cnt2;
+  uint32_t* coll_idx;
+  double* coll_d2;
+  // exact scan
   double* scan_d2;
   SelKey* sel_scratch;
   int scan_qb;
+  int chunk_q, nchunks, nr_max, q2max;
 };
 
 static int scan_batch(int64_t R) {
@@ -693,28 +843,69 @@ static bool use_tensor_pass(int64_t R, int D, int Q, int k, int force_path) {
   return double(Q) * double(R) >= double(1 << 22) && R >= 4096;
 }
 
+// Queries per pipelined chunk: the tensor kernel's own L2 group (knn_tc_tiling: ~40 MB of fp16 query blocks, 5120 queries
+// at D = 4096), so that splitting a call at chunk boundaries does not change how the database ranges are streamed.
+static int chunk_queries(int Q, int64_t R, int Dp) {
+  int forced = knob(KNOB_KNN_CHUNK_Q);
+  if (forced == 0) return Q;
+  int mb, nt, NR, tpr, gm;
+  knn_tc_tiling(Q, R, Dp, &mb, &nt, &NR, &tpr, &gm);
+  const int unit = knob_or(KNOB_KNN_TC_VARIANT, 2) >= 2 ? 256 : 128;
+  long long cq = forced > 0 ? (long long)(forced + unit - 1) / unit * unit : (long long)gm * unit;
+  if (cq < unit) cq = unit;
+  if (cq >= Q) return Q;
+  // equal-sized chunks (multiples of the tile unit)
+  const int n = int((Q + cq - 1) / cq);
+  cq = ((Q + n - 1) / n + unit - 1) / unit * unit;
+  return int(cq);
+}
+
 static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* base, size_t bytes) {
   Carver c(base, bytes);
   const int Dp = pad64(D);
-  int mb, nt, NR, tpr, gm;
-  knn_tc_tiling(Q, R, Dp, &mb, &nt, &NR, &tpr, &gm);
   QueryWs tmp;
   QueryWs* o = w ? w : &tmp;
+  o->chunk_q = chunk_queries(Q, R, Dp);
+  o->nchunks = (Q + o->chunk_q - 1) / o->chunk_q;
+  int mb, nt, NR, tpr, gm;
+  knn_tc_tiling(o->chunk_q, R, Dp, &mb, &nt, &NR, &tpr, &gm);
+  o->nr_max = NR;
+  const int q_last = Q - (o->nchunks - 1) * o->chunk_q;
+  knn_tc_tiling(q_last, R, Dp, &mb, &nt, &NR, &tpr, &gm);
+  if (NR > o->nr_max) o->nr_max = NR;
+  o->q2max = Q < 2048 ? Q : 2048;
+  knn_tc_tiling(o->q2max, R, Dp, &mb, &nt, &NR, &tpr, &gm);      // stage 2 runs in batches of <= q2max queries
   o->stats = c.take<int>(8);
   o->qh = c.take<__half>(size_t(Q) * Dp);
   o->qmul = c.take<float>(Q);
   o->qn2 = c.take<double>(Q);
   o->qexp = c.take<int>(Q);
-  o->cand_s = c.take<float>(size_t(Q) * NR * kCandCap);
-  o->cand_i = c.take<uint32_t>(size_t(Q) * NR * kCandCap);
-  o->cand_cnt = c.take<int>(size_t(Q) * NR);
   o->q_thr = c.take<unsigned int>(Q);
-  o->sync_ctr = c.take<unsigned int>(kSyncMax);
   o->sel_idx = c.take<uint32_t>(size_t(Q) * kKeep);
   o->sel_T = c.take<float>(Q);
   o->sel_n = c.take<int>(Q);
   o->d2 = c.take<double>(size_t(Q) * kKeep);
+  o->kth_d2 = c.take<double>(Q);
   o->flag_list = c.take<int>(Q);
+  o->flag2_list = c.take<int>(Q);
+  const int slots = o->nchunks > 1 ? 2 : 1;
+  for (int sl = 0; sl < 2; ++sl) {
+    if (sl < slots) {
+      o->cand_s[sl] = c.take<float>(size_t(o->chunk_q) * o->nr_max * kCandCap);
+      o->cand_i[sl] = c.take<uint32_t>(size_t(o->chunk_q) * o->nr_max * kCandCap);
+      o->cand_cnt[sl] = c.take<int>(size_t(o->chunk_q) * o->nr_max);
+      o->sync_ctr[sl] = c.take<unsigned int>(kSyncMax);
+    } else {
+      o->cand_s[sl] = o->cand_s[0]; o->cand_i[sl] = o->cand_i[0]; o->cand_cnt[sl] = o->cand_cnt[0];
+      o->sync_ctr[sl] = o->sync_ctr[0];
+    }
+  }
+  o->qh2 = c.take<__half>(size_t(o->q2max) * Dp);
+  o->qmul2 = c.take<float>(o->q2max);
+  o->thr2 = c.take<float>(o->q2max);
+  o->cnt2 = c.take<int>(o->q2max);
+  o->coll_idx = c.take<uint32_t>(size_t(o->q2max) * kCollectCap);
+  o->coll_d2 = c.take<double>(size_t(o->q2max) * kCollectCap);
   o->scan_qb = scan_batch(R);
   o->scan_d2 = c.take<double>(size_t(o->scan_qb) * R);
   o->sel_scratch = c.take<SelKey>(size_t(o->scan_qb) * kTieCap);
@@ -727,11 +918,9 @@ static int run_exact(const float* db, int64_t R, int D, const float* queries, co
                      int64_t idx_offset, double* dist, int64_t* idx, const QueryWs& w, cudaStream_t stream) {
   const int qt = scan_qt(D);
   const size_t scan_smem = size_t(qt) * D * sizeof(float);
-  static size_t scan_cfg = 0;
-  if (scan_smem > 48 * 1024 && scan_cfg < scan_smem) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(scan_smem)));
-    scan_cfg = scan_smem;
-  }
+  static SmemAttrCache scan_cfg;                        // per device
+  int rc = ensure_dyn_smem(reinterpret_cast<const void*>(knn_scan_kernel), scan_smem, &scan_cfg);
+  if (rc) return rc;
   int kpow2 = 1;
   const int kk = int(k < R ? k : R);
   while (kpow2 < kk) kpow2 <<= 1;
@@ -751,6 +940,23 @@ static int run_exact(const float* db, int64_t R, int D, const float* queries, co
     SCL_LAUNCH_CHECK();
   }
   return SCL_OK;
+}
+
+// tiling + launch of the tensor pass for `nq` queries whose per-query arrays start at qh / qmul / q_thr
+static int launch_tensor(const QueryWs& w, int slot, const __half* qh, const float* qmul, unsigned int* q_thr, int nq,
+                         int64_t R, int Dp, const float* rn, const __half* dbh, float* dbg, bool collect,
+                         cudaStream_t stream) {
+  TcArgs a = {};
+  a.rn = rn; a.qmul = qmul; a.Q = nq; a.R = int(R); a.Dp = Dp;
+  knn_tc_tiling(nq, R, Dp, &a.num_m_blocks, &a.num_n_tiles, &a.NR, &a.tiles_per_range, &a.group_m);
+  a.cand_s = w.cand_s[slot]; a.cand_i = w.cand_i[slot]; a.cand_cnt = w.cand_cnt[slot]; a.q_thr = q_thr;
+  a.sync_ctr = w.sync_ctr[slot];
+  SCL_CUDA_TRY(cudaMemsetAsync(a.sync_ctr, 0, size_t(kSyncMax) * sizeof(unsigned int), stream));
+  a.dbg_scores = dbg;
+  if (collect) {
+    a.collect = 1; a.fixed_thr = w.thr2; a.coll_idx = w.coll_idx; a.coll_cnt = w.cnt2; a.coll_cap = kCollectCap;
+  }
+  return knn_tc_launch(a, qh, dbh, stream);
 }
 
 }  // namespace scl
@@ -796,6 +1002,12 @@ extern "C" int scl_knn_query_workspace_bytes(int64_t R, int D, int Q, int k, siz
   return SCL_OK;
 }
 
+extern "C" int scl_knn_set_debug_scores(float* scores, size_t capacity_floats) {
+  t_dbg_scores = scores;
+  t_dbg_capacity = scores ? capacity_floats : 0;
+  return SCL_OK;
+}
+
 extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
                              int64_t idx_offset, int force_path, double* dist, int64_t* idx, int32_t* stats,
                              void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
@@ -816,9 +1028,9 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
     rc = run_exact(db, R, D, queries, nullptr, Q, k, idx_offset, dist, idx, w, stream);
     if (rc) return rc;
     if (stats) {
-      const int host_stats[4] = {Q, 0, Q, 1};
-      SCL_CUDA_TRY(cudaMemcpyAsync(stats, host_stats, sizeof(host_stats), cudaMemcpyHostToDevice, stream));
-      SCL_CUDA_TRY(cudaStreamSynchronize(stream));      // host_stats lives on this stack frame
+      const StatsOut so = {{Q, 0, Q, 1, 0, Q, 0, 0}};
+      knn_stats_out_kernel<<<1, 8, 0, stream>>>(stats, so);
+      SCL_LAUNCH_CHECK();
     }
     return SCL_OK;
   }
@@ -831,81 +1043,146 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
 
   knn_query_prep_kernel<<<Q, 256, 0, stream>>>(queries, Q, D, Dp, h, w.qh, w.qmul, w.qn2, w.qexp);
   SCL_LAUNCH_CHECK();
-
-  TcArgs a = {};
-  a.rn = rn; a.qmul = w.qmul; a.Q = Q; a.R = int(R); a.Dp = Dp;
-  knn_tc_tiling(Q, R, Dp, &a.num_m_blocks, &a.num_n_tiles, &a.NR, &a.tiles_per_range, &a.group_m);
-  a.cand_s = w.cand_s; a.cand_i = w.cand_i; a.cand_cnt = w.cand_cnt; a.q_thr = w.q_thr;
   SCL_CUDA_TRY(cudaMemsetAsync(w.q_thr, 0xff, size_t(Q) * sizeof(unsigned int), stream));
-  a.sync_ctr = w.sync_ctr;
-  SCL_CUDA_TRY(cudaMemsetAsync(w.sync_ctr, 0, size_t(kSyncMax) * sizeof(unsigned int), stream));
-  a.dbg_scores = nullptr;
-  const char* dbg = getenv("SCL_KNN_DEBUG_SCORES");     // test hook: address of a [Q,R] float buffer, in hex
-  if (dbg) a.dbg_scores = reinterpret_cast<float*>(strtoull(dbg, nullptr, 16));
-  // optional device timing of the tensor pass alone (bench.py's roofline line): events on the launching stream
-  static thread_local cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // Pipeline over query chunks: the tensor pass of chunk c runs on the launching stream while the candidate merge, the
+  // exact rescore and the certificate of chunk c-1 run on the helper stream (the tensor kernel leaves registers and
+  // ~20 KB of shared memory per SM free and is tensor-bound; the rescore is an HBM gather).  Two candidate-list slots.
+  HelperCtx& hc = t_helper[device_slot()];
+  const int nchunks = w.nchunks;
+  if (nchunks > 1 && !hc.h) SCL_CUDA_TRY(cudaStreamCreateWithFlags(&hc.h, cudaStreamNonBlocking));
   const bool timing = g_knn_timing.load(std::memory_order_relaxed) != 0;
-  if (timing) {
-    if (!ev0) { SCL_CUDA_TRY(cudaEventCreate(&ev0)); SCL_CUDA_TRY(cudaEventCreate(&ev1)); }
-    SCL_CUDA_TRY(cudaEventRecord(ev0, stream));
+  float* dbg = (t_dbg_scores && t_dbg_capacity >= size_t(Q) * size_t(R)) ? t_dbg_scores : nullptr;
+  for (int c = 0; c < nchunks; ++c) {
+    const int q0 = c * w.chunk_q, nq = std::min(w.chunk_q, Q - q0), slot = c & 1;
+    cudaEvent_t ev_tc = nullptr, ev_post = nullptr, t0 = nullptr, t1 = nullptr;
+    if (nchunks > 1) {
+      if ((rc = hc.get(hc.ev, size_t(2 * c), cudaEventDisableTiming, &ev_tc))) return rc;
+      if ((rc = hc.get(hc.ev, size_t(2 * c + 1), cudaEventDisableTiming, &ev_post))) return rc;
+      if (c >= 2) SCL_CUDA_TRY(cudaStreamWaitEvent(stream, hc.ev[2 * (c - 2) + 1], 0));   // the slot's previous reader
+    }
+    if (timing) {
+      if ((rc = hc.get(hc.tev, size_t(2 * c), cudaEventDefault, &t0))) return rc;
+      if ((rc = hc.get(hc.tev, size_t(2 * c + 1), cudaEventDefault, &t1))) return rc;
+      SCL_CUDA_TRY(cudaEventRecord(t0, stream));
+    }
+    rc = launch_tensor(w, slot, w.qh + size_t(q0) * Dp, w.qmul + q0, w.q_thr + q0, nq, R, Dp, rn, dbh,
+                       dbg ? dbg + size_t(q0) * size_t(R) : nullptr, false, stream);
+    if (rc) return rc;
+    if (timing) SCL_CUDA_TRY(cudaEventRecord(t1, stream));
+    cudaStream_t ps = stream;
+    if (nchunks > 1) {
+      SCL_CUDA_TRY(cudaEventRecord(ev_tc, stream));
+      SCL_CUDA_TRY(cudaStreamWaitEvent(hc.h, ev_tc, 0));
+      ps = hc.h;
+    }
+    int mb, nt, NR, tpr, gm;
+    knn_tc_tiling(nq, R, Dp, &mb, &nt, &NR, &tpr, &gm);
+    knn_cand_merge_kernel<<<nq, 256, 0, ps>>>(w.cand_s[slot], w.cand_i[slot], w.cand_cnt[slot], w.q_thr + q0, NR, k,
+                                              w.qn2 + q0, w.qexp + q0, h, w.sel_idx + size_t(q0) * kKeep, w.sel_T + q0,
+                                              w.sel_n + q0);
+    SCL_LAUNCH_CHECK();
+    const long long pairs = (long long)nq * kKeep;
+    knn_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, ps>>>(db, queries + size_t(q0) * D, D,
+                                                                 w.sel_idx + size_t(q0) * kKeep, pairs,
+                                                                 w.d2 + size_t(q0) * kKeep);
+    SCL_LAUNCH_CHECK();
+    knn_finalize_kernel<<<(nq + 7) / 8, 256, 0, ps>>>(w.sel_idx + size_t(q0) * kKeep, w.d2 + size_t(q0) * kKeep, w.sel_T + q0,
+                                                      w.sel_n + q0, w.qn2 + q0, w.qexp + q0, h, nq, k, idx_offset,
+                                                      force_path >= 3 ? 1 : 0, q0, dist + size_t(q0) * k,
+                                                      reinterpret_cast<long long*>(idx) + size_t(q0) * k, w.kth_d2 + q0,
+                                                      w.flag_list, w.stats);
+    SCL_LAUNCH_CHECK();
+    if (nchunks > 1) SCL_CUDA_TRY(cudaEventRecord(ev_post, hc.h));
   }
-  rc = knn_tc_launch(a, w.qh, dbh, stream);
-  if (rc) return rc;
-  if (timing) SCL_CUDA_TRY(cudaEventRecord(ev1, stream));
+  if (nchunks > 1) SCL_CUDA_TRY(cudaStreamWaitEvent(stream, hc.ev[2 * (nchunks - 1) + 1], 0));   // join (the helper is in order)
 
-  knn_cand_merge_kernel<<<Q, 256, 0, stream>>>(w.cand_s, w.cand_i, w.cand_cnt, w.q_thr, a.NR, k, w.qn2, w.qexp, h, w.sel_idx,
-                                               w.sel_T, w.sel_n);
-  SCL_LAUNCH_CHECK();
-  const long long pairs = (long long)Q * kKeep;
-  knn_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, stream>>>(db, queries, D, w.sel_idx, pairs, w.d2);
-  SCL_LAUNCH_CHECK();
-  knn_finalize_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(w.sel_idx, w.d2, w.sel_T, w.sel_n, w.qn2, w.qexp, h, Q, k,
-                                                       idx_offset, force_path == 3 ? 1 : 0, dist,
-                                                       reinterpret_cast<long long*>(idx), w.flag_list, w.stats);
-  SCL_LAUNCH_CHECK();
-
-  // the number of uncertified queries decides how much exact work follows: one small device->host read
-  int hs[4] = {0, 0, 0, 0};
+  // the number of refused queries decides how much work follows: one small device->host read (the only host
+  // synchronisation of a fully certified call)
+  int hs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   SCL_CUDA_TRY(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
   SCL_CUDA_TRY(cudaStreamSynchronize(stream));
   if (timing) {
-    float ms = 0.0f;
-    SCL_CUDA_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
-    g_knn_tc_ms_sum.store(g_knn_tc_ms_sum.load() + double(ms));
-    g_knn_tc_calls.fetch_add(1);
+    double sum = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+      float ms = 0.0f;
+      SCL_CUDA_TRY(cudaEventElapsedTime(&ms, hc.tev[2 * c], hc.tev[2 * c + 1]));
+      sum += double(ms);
+    }
+    std::lock_guard<std::mutex> lk(g_knn_timing_mu);
+    g_knn_tc_ms_sum += sum;
+    g_knn_tc_calls += 1;
   }
   const int nflag = hs[2];
+  int n_stage2 = 0, n_scan = 0;
   if (nflag > 0) {
-    rc = run_exact(db, R, D, queries, w.flag_list, nflag, k, idx_offset, dist, idx, w, stream);
-    if (rc) return rc;
+    // force_path 3: every query through the exact scan; 4: every query through stage 2 (test hooks)
+    const bool stage2 = force_path != 3 && knob_or(KNOB_KNN_STAGE2, 1) != 0;
+    if (!stage2) {
+      rc = run_exact(db, R, D, queries, w.flag_list, nflag, k, idx_offset, dist, idx, w, stream);
+      if (rc) return rc;
+      n_scan = nflag;
+    } else {
+      static SmemAttrCache sel2_cfg;
+      constexpr size_t sel2_smem = size_t(kCollectCap) * sizeof(SelKey);
+      if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(knn_stage2_select_kernel), sel2_smem, &sel2_cfg))) return rc;
+      for (int f0 = 0; f0 < nflag; f0 += w.q2max) {
+        const int n2 = std::min(w.q2max, nflag - f0);
+        knn_stage2_gather_kernel<<<n2, 256, 0, stream>>>(w.flag_list, f0, n2, Dp, w.qh, w.qmul, w.qn2, w.qexp, w.kth_d2, h,
+                                                         w.qh2, w.qmul2, w.thr2, w.cnt2);
+        SCL_LAUNCH_CHECK();
+        rc = launch_tensor(w, 0, w.qh2, w.qmul2, w.q_thr, n2, R, Dp, rn, dbh, nullptr, true, stream);
+        if (rc) return rc;
+        const long long pairs = (long long)n2 * kCollectCap;
+        knn_stage2_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, stream>>>(db, queries, D, w.flag_list, f0, w.coll_idx,
+                                                                                w.cnt2, pairs, w.coll_d2);
+        SCL_LAUNCH_CHECK();
+        knn_stage2_select_kernel<<<n2, 256, sel2_smem, stream>>>(w.flag_list, f0, w.coll_idx, w.cnt2, w.coll_d2, k,
+                                                                 idx_offset, dist, reinterpret_cast<long long*>(idx),
+                                                                 w.flag2_list, w.stats);
+        SCL_LAUNCH_CHECK();
+      }
+      // how many lists overflowed decides whether the exact scan runs at all: second (and last) host read
+      SCL_CUDA_TRY(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
+      SCL_CUDA_TRY(cudaStreamSynchronize(stream));
+      n_stage2 = hs[4];
+      n_scan = hs[5];
+      if (n_scan > 0) {
+        rc = run_exact(db, R, D, queries, w.flag2_list, n_scan, k, idx_offset, dist, idx, w, stream);
+        if (rc) return rc;
+      }
+    }
   }
   if (stats) {
-    const int host_stats[4] = {Q, hs[1], nflag, 2};
-    SCL_CUDA_TRY(cudaMemcpyAsync(stats, host_stats, sizeof(host_stats), cudaMemcpyHostToDevice, stream));
-    SCL_CUDA_TRY(cudaStreamSynchronize(stream));
+    const StatsOut so = {{Q, hs[1], nflag, 2, n_stage2, n_scan, nchunks, 0}};
+    knn_stats_out_kernel<<<1, 8, 0, stream>>>(stats, so);
+    SCL_LAUNCH_CHECK();
   }
   return SCL_OK;
 }
 
 extern "C" int scl_knn_timing(int enable, double* tensor_pass_ms_sum, int* tensor_pass_calls) {
-  if (tensor_pass_ms_sum) *tensor_pass_ms_sum = g_knn_tc_ms_sum.load();
-  if (tensor_pass_calls) *tensor_pass_calls = g_knn_tc_calls.load();
+  std::lock_guard<std::mutex> lk(g_knn_timing_mu);
+  if (tensor_pass_ms_sum) *tensor_pass_ms_sum = g_knn_tc_ms_sum;
+  if (tensor_pass_calls) *tensor_pass_calls = g_knn_tc_calls;
   if (enable >= 0) {
     g_knn_timing.store(enable);
-    g_knn_tc_ms_sum.store(0.0);
-    g_knn_tc_calls.store(0);
+    g_knn_tc_ms_sum = 0.0;
+    g_knn_tc_calls = 0;
   }
   return SCL_OK;
 }
 
-extern "C" int scl_topk_merge(const double* d_all, const int64_t* i_all, int G, int Q, int k, double* d, int64_t* i,
-                              scl_stream_t stream) {
+extern "C" int scl_topk_merge(const double* d_all, const int64_t* i_all, int G, int Q, int k, int64_t shard_stride,
+                              double* d, int64_t* i, scl_stream_t stream) {
   if (!d_all || !i_all || !d || !i || G < 1 || Q < 1 || k < 1) return SCL_ERR_BAD_ARG;
+  if (shard_stride == 0) shard_stride = (int64_t)Q * k;
+  if (shard_stride < (int64_t)Q * k) return SCL_ERR_BAD_SHAPE;
   int rc = check_device();
   if (rc) return rc;
   const long long n = (long long)G * Q * k;
   topk_merge_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_all, reinterpret_cast<const long long*>(i_all), G, Q, k, d, reinterpret_cast<long long*>(i));
+      d_all, reinterpret_cast<const long long*>(i_all), G, Q, k, (long long)shard_stride, d, reinterpret_cast<long long*>(i));
   SCL_LAUNCH_CHECK();
   return SCL_OK;
 }

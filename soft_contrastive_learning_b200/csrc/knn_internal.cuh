@@ -32,7 +32,14 @@ struct TcArgs {
   int* cand_cnt;         // [Q, NR]
   unsigned int* q_thr;   // [Q] best (smallest) pruning threshold any range has published for the query, as an
                          //     order-preserving uint (0xffffffff = none yet); shared by all ranges of the query
-  float* dbg_scores;     // optional [Q, R]: raw fp16-pass scores (tests)
+  float* dbg_scores;     // optional [Q, R]: raw fp16-pass scores (tests; scl_knn_set_debug_scores)
+  // Stage 2 ("collect" mode, knn.cu): every query carries a FIXED threshold and every row scoring below it is appended
+  // to ONE list per query (no pruning, no published thresholds); a list that overflows coll_cap is detected by its count.
+  int collect;
+  const float* fixed_thr;   // [Q]
+  uint32_t* coll_idx;       // [Q, coll_cap] database rows
+  int* coll_cnt;            // [Q] number of rows that passed (may exceed coll_cap)
+  int coll_cap;
   // Sliding-window pacing of the TMA producers (performance only, never needed for correctness): producer w bumps
   // sync_ctr[p] once it has issued the loads of its p-th sync point (a fraction of a tile) and does not start point p
   // before every worker has passed point p - sync_window.  Keeps the workers that stream the same database range (and
@@ -42,6 +49,7 @@ struct TcArgs {
   int sync_total, sync_window, sync_subs;
 };
 constexpr int kSyncMax = 1 << 16;
+constexpr int kCollectCap = 2048;   // stage-2 list capacity per query
 
 int knn_tc_launch(const TcArgs& a, const void* queries_fp16, const void* db_fp16, cudaStream_t stream);
 void knn_tc_tiling(int Q, int64_t R, int Dp, int* num_m_blocks, int* num_n_tiles, int* NR, int* tiles_per_range, int* group_m);

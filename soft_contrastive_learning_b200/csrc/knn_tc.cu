@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
       const float qmul = valid ? a.qmul[q] : 0.0f;
       const size_t base = (size_t(valid ? q : 0) * a.NR + range) * kCandCap;
       unsigned int* my_thr = a.q_thr + (valid ? q : 0);
-      float thr = INFINITY;
+      const bool collect = a.collect != 0;
+      float thr = collect ? (valid ? __ldg(a.fixed_thr + q) : -INFINITY) : INFINITY;
       int cnt = 0;
       for (int t = t0; t < t1; ++t, ++tile_count) {
         const uint32_t buf = tile_count % kBufs, use = tile_count / kBufs;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
           tail->rn[rbuf][u * 128 + et] = r < a.R ? __ldg(a.rn + r) : INFINITY;
         }
         // thresholds published by other ranges of the same query (other CTAs) tighten this row's filter too
-        if (valid) {
+        if (valid && !collect) {
           const unsigned int pub = __ldcg(my_thr);
           if (pub != 0xffffffffu) thr = fminf(thr, ord2f(pub));
         }
@@ -404,12 +405,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
           for (int j = 0; j < 32; ++j) hit |= (sc[j] < thr) ? (1u << j) : 0u;
           if (!valid) hit = 0;
           if (hit != 0) {
+            if (collect) {
+              // stage 2: one list per query shared by all ranges; survivors are rare (rows within the rounding bound
+              // of the k-th neighbour), so one atomic per survivor is cheap
+              while (hit) {
+                const int j = __ffs(hit) - 1;
+                hit &= hit - 1;
+                const int pos = atomicAdd(a.coll_cnt + q, 1);
+                if (pos < a.coll_cap) a.coll_idx[size_t(q) * a.coll_cap + pos] = uint32_t(n0 + c * 32 + j);
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if ((hit >> j) & 1u) {
-                a.cand_s[base + cnt] = sc[j];
-                a.cand_i[base + cnt] = uint32_t(n0 + c * 32 + j);
-                ++cnt;
+              for (int j = 0; j < 32; ++j) {
+                if ((hit >> j) & 1u) {
+                  a.cand_s[base + cnt] = sc[j];
+                  a.cand_i[base + cnt] = uint32_t(n0 + c * 32 + j);
+                  ++cnt;
+                }
               }
             }
           }
@@ -431,7 +443,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
       }
       // end of the item: publish the list length (<= kCandCap entries, unsorted; knn_cand_merge_kernel filters them by
       // the final published threshold and sorts what is left)
-      if (valid) a.cand_cnt[size_t(q) * a.NR + range] = cnt;
+      if (valid && !collect) a.cand_cnt[size_t(q) * a.NR + range] = cnt;
     }
   }
 
@@ -512,20 +524,17 @@ int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, 
 static int tc_variant() {
   // 1 = single-CTA 128x256 tiles, 2 = CTA pairs 256x256 with double-buffered accumulators (default: the epilogue
   // of tile i overlaps the MMAs of tile i+1), 3 = CTA pairs 256x512 (a quarter less L2->SM traffic, no overlap)
-  const char* env = getenv("SCL_KNN_TC_VARIANT");
-  if (env && atoi(env) >= 1 && atoi(env) <= 3) return atoi(env);
-  return 2;
+  const int v = knob(KNOB_KNN_TC_VARIANT);
+  return (v >= 1 && v <= 3) ? v : 2;
 }
 static int tc_tile_n(int variant) { return variant == 3 ? 2 * kBN : kBN; }
 
 template <bool kPair, int kNSub>
 static int tc_launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t stream) {
   auto kern = knn_tc_kernel<kPair, kNSub>;
-  static std::atomic<bool> configured{false};          // idempotent attribute: a race between host threads is benign
-  if (!configured.load(std::memory_order_acquire)) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tc_smem_bytes<kPair, kNSub>())));
-    configured.store(true, std::memory_order_release);
-  }
+  static SmemAttrCache configured;                     // per device
+  int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), tc_smem_bytes<kPair, kNSub>(), &configured);
+  if (rc_attr) return rc_attr;
   const int sms = num_sms();
   const int m_units = kPair ? (a.num_m_blocks + 1) / 2 : a.num_m_blocks;
   const int items = m_units * a.NR;
@@ -534,18 +543,15 @@ static int tc_launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   TcArgs args = a;
   {
     // pacing of the producers: `subs` sync points per tile, window in sync points (SCL_KNN_SYNC=0 switches it off)
-    const char* es = getenv("SCL_KNN_SYNC");
-    const char* ew = getenv("SCL_KNN_SYNC_WINDOW");
-    const char* eb = getenv("SCL_KNN_SYNC_SUBS");
     const int num_k = a.Dp / kBK;
-    int subs = eb ? atoi(eb) : 4;
+    int subs = knob_or(KNOB_KNN_SYNC_SUBS, 4);
     if (subs < 1) subs = 1;
     if (subs > num_k) subs = num_k;
-    int window = ew ? atoi(ew) : subs;
+    int window = knob_or(KNOB_KNN_SYNC_WINDOW, subs);
     if (window < 1) window = 1;
     const long long rounds = (items + workers - 1) / workers;
     const long long total = rounds * a.tiles_per_range * subs;
-    const bool on = !(es && atoi(es) == 0) && a.sync_ctr != nullptr && workers > 1 && total <= kSyncMax;
+    const bool on = knob_or(KNOB_KNN_SYNC, 1) != 0 && a.sync_ctr != nullptr && workers > 1 && total <= kSyncMax;
     args.sync_subs = subs;
     args.sync_window = window;
     args.sync_total = on ? int(total) : 0;
@@ -600,8 +606,8 @@ void knn_tc_tiling(int Q, int64_t R, int Dp, int* num_m_blocks, int* num_n_tiles
     const double eff = double(1ll * mu * nt) / (double(waves) * sms * tpr);
     if (eff > best_eff + 0.005) { best_eff = eff; best = nr; }
   }
-  const char* env = getenv("SCL_KNN_RANGES");
-  if (env && atoi(env) >= 1 && atoi(env) <= max_nr) best = atoi(env);
+  const int forced_nr = knob(KNOB_KNN_RANGES);
+  if (forced_nr >= 1 && forced_nr <= max_nr) best = forced_nr;
   *num_m_blocks = mb;
   *num_n_tiles = nt;
   *NR = best;
@@ -612,8 +618,7 @@ void knn_tc_tiling(int Q, int64_t R, int Dp, int* num_m_blocks, int* num_n_tiles
   const long long unit_bytes = (pair ? 2ll : 1ll) * kBM * Dp * 2;
   int gm = int((40ll << 20) / (unit_bytes > 0 ? unit_bytes : 1));
   if (gm < 2) gm = 2;
-  const char* genv = getenv("SCL_KNN_GROUP_M");
-  if (genv && atoi(genv) >= 1) gm = atoi(genv);
+  if (knob(KNOB_KNN_GROUP_M) >= 1) gm = knob(KNOB_KNN_GROUP_M);
   if (gm > mu) gm = mu;
   gm = (mu + (mu + gm - 1) / gm - 1) / ((mu + gm - 1) / gm);      // equal-sized groups
   *group_m = gm;

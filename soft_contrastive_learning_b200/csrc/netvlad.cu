@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(256) pca_scale_dy_kernel(const float* __restri
 }
 
 static bool pca_tc_ok(const void* a, const void* b, const void* c, int Din, int Dout) {
-  return (Din % 4 == 0) && (Dout % 4 == 0) && aligned16(a) && aligned16(b) && aligned16(c) && !getenv("SCL_GEMM_SIMT");
+  return (Din % 4 == 0) && (Dout % 4 == 0) && aligned16(a) && aligned16(b) && aligned16(c) && knob_or(KNOB_GEMM_SIMT, 0) == 0;
 }
 
 extern "C" int scl_pca_workspace_bytes(int B, int Din, int Dout, size_t* bytes) {

@@ -1,5 +1,6 @@
 // runtime.cu -- status strings, device check, thread-local error detail.
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -39,6 +40,42 @@ int check_device() {
   return cc / 10 == 10 ? SCL_OK : SCL_ERR_ARCH;   // sm_100a code only runs on compute capability 10.x
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
+int ensure_dyn_smem(const void* func, size_t bytes, SmemAttrCache* cache) {
+  if (bytes <= 48 * 1024) return SCL_OK;
+  const int dev = device_slot();
+  // the attribute only ever grows and setting it twice is harmless
+  if (cache->bytes[dev].load(std::memory_order_relaxed) >= bytes) return SCL_OK;
+  SCL_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+  cache->bytes[dev].store(bytes, std::memory_order_relaxed);
+  return SCL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tuning knobs: environment read once at load, then scl_set_tuning only
+// ---------------------------------------------------------------------------------------------
+static const char* const kKnobNames[KNOB_COUNT] = {
+    "SCL_WMS_STREAM", "SCL_WMS_STREAM_CFG", "SCL_WMS_CLUSTER", "SCL_WMS_CHUNKED", "SCL_TUPLE_CLUSTER",
+    "SCL_KNN_TC_VARIANT", "SCL_KNN_SYNC", "SCL_KNN_SYNC_WINDOW", "SCL_KNN_SYNC_SUBS", "SCL_KNN_RANGES",
+    "SCL_KNN_GROUP_M", "SCL_KNN_CHUNK_Q", "SCL_KNN_STAGE2", "SCL_GEMM_SIMT", "SCL_NV_FUSED"};
+struct KnobTable {
+  std::atomic<int> v[KNOB_COUNT];
+  KnobTable() {
+    for (int i = 0; i < KNOB_COUNT; ++i) {
+      const char* e = getenv(kKnobNames[i]);
+      v[i].store((e && *e) ? atoi(e) : kKnobUnset, std::memory_order_relaxed);
+    }
+  }
+};
+static KnobTable g_knobs;       // constructed when the shared library is loaded
+
+int knob(Knob k) { return g_knobs.v[k].load(std::memory_order_relaxed); }
+
 int num_sms() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
@@ -68,3 +105,22 @@ extern "C" const char* scl_strerror(int status) {
 extern "C" const char* scl_last_error(void) { return scl::g_err; }
 
 extern "C" int scl_device_ok(void) { return scl::check_device(); }
+
+extern "C" int scl_set_tuning(const char* name, int value) {
+  if (!name) return SCL_ERR_BAD_ARG;
+  for (int i = 0; i < scl::KNOB_COUNT; ++i)
+    if (strcmp(name, scl::kKnobNames[i]) == 0) {
+      scl::g_knobs.v[i].store(value, std::memory_order_relaxed);
+      return SCL_OK;
+    }
+  return SCL_ERR_BAD_ARG;
+}
+extern "C" int scl_get_tuning(const char* name, int* value) {
+  if (!name || !value) return SCL_ERR_BAD_ARG;
+  for (int i = 0; i < scl::KNOB_COUNT; ++i)
+    if (strcmp(name, scl::kKnobNames[i]) == 0) {
+      *value = scl::g_knobs.v[i].load(std::memory_order_relaxed);
+      return SCL_OK;
+    }
+  return SCL_ERR_BAD_ARG;
+}

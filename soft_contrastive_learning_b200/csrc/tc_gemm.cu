@@ -343,11 +343,9 @@ static int tc_gemm_launch(const TcGemmDesc& d, cudaStream_t stream) {
   }
   auto kern = tc_gemm_kernel<BN, kX3, kAMn, kBMn>;
   const size_t smem = 1024 + size_t(Cfg::kStages) * Cfg::kStageBytes + sizeof(GSmemTail);
-  static std::atomic<bool> configured{false};          // idempotent attribute: a race between host threads is benign
-  if (!configured.load(std::memory_order_acquire)) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured.store(true, std::memory_order_release);
-  }
+  static SmemAttrCache configured;                     // per device
+  rc = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem, &configured);
+  if (rc) return rc;
   TcGemmArgs g;
   g.M = d.M; g.N = d.N; g.K = d.K + (dual ? d.K2 : 0); g.colscale = d.colscale; g.C = d.C; g.ldc = d.ldc;
   g.k1_stages = dual ? d.K / kGBK : 0x7fffffff;

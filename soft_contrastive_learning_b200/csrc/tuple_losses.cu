@@ -299,9 +299,8 @@ static int anchor_plan(int S, int D, TupPlan* pl) {
   pl->sg = S <= 25 ? 25 : (S <= 30 ? 30 : 35);
   int c = 1;
   while (c < kMaxCluster && (D / (c * 2)) >= 512 && (D % (c * 2 * 4)) == 0) c *= 2;
-  const char* env = getenv("SCL_TUPLE_CLUSTER");
-  if (env) {
-    int e = atoi(env);
+  const int e = knob(KNOB_TUPLE_CLUSTER);
+  if (e != kKnobUnset) {
     if ((e == 1 || e == 2 || e == 4 || e == 8) && D % (4 * e) == 0) c = e;
   }
   pl->cluster = c;
@@ -322,11 +321,9 @@ template <int SG>
 static int anchor_launch(const TupPlan& pl, const float* emb, int T, int S, int D, const AnchorArgs& a, float* demb,
                          float* loss, unsigned int* ws, cudaStream_t stream) {
   auto kern = anchor_tuple_kernel<SG>;
-  static std::atomic<size_t> configured{0};
-  if (configured.load(std::memory_order_relaxed) < pl.smem) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    configured.store(pl.smem, std::memory_order_relaxed);
-  }
+  static SmemAttrCache configured;            // per device
+  int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), pl.smem, &configured);
+  if (rc_attr) return rc_attr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(T) * pl.cluster);
   cfg.blockDim = dim3(kTupThreads);

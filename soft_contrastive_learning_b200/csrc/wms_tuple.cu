@@ -315,9 +315,8 @@ static int wms_plan(int S, int D, WmsPlan* pl) {
   // cluster size: keep the per-CTA slice around 512 columns (two CTAs per SM stay resident)
   int c = 1;
   while (c < kMaxCluster && (D / (c * 2)) >= 512 && (D % (c * 2 * 4)) == 0) c *= 2;
-  const char* env = getenv("SCL_WMS_CLUSTER");
-  if (env) {
-    int e = atoi(env);
+  const int e = knob(KNOB_WMS_CLUSTER);
+  if (e != kKnobUnset) {
     if ((e == 1 || e == 2 || e == 4 || e == 8) && D % (4 * e) == 0) c = e;
   }
   pl->cluster = c;
@@ -341,11 +340,9 @@ static int wms_launch_chunked(const WmsPlan& pl, const float* emb, const float* 
                       const scl_ms_params& p, float* per_tuple, float* demb, uint32_t* kept, float* loss,
                       unsigned int* counter, cudaStream_t stream) {
   auto kern = wms_tuple_chunked_kernel<TS>;
-  static std::atomic<size_t> configured{0};   // idempotent attribute, set only when it has to grow
-  if (configured.load(std::memory_order_relaxed) < pl.smem) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    configured.store(pl.smem, std::memory_order_relaxed);
-  }
+  static SmemAttrCache configured;            // per device; set only when it has to grow
+  int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), pl.smem, &configured);
+  if (rc_attr) return rc_attr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(T) * pl.cluster);
   cfg.blockDim = dim3(kWmsThreads);

@@ -404,9 +404,8 @@ static bool resident_plan(int T, int S, int D, ResidentPlan* pl) {
     if (D % (4 * c)) break;
     if (resident_bytes(ts, D / c, c) <= budget) { chosen = c; break; }
   }
-  const char* env = getenv("SCL_WMS_CLUSTER");
-  if (env) {
-    const int e = atoi(env);
+  const int e = knob(KNOB_WMS_CLUSTER);
+  if (e != kKnobUnset) {
     if ((e == 1 || e == 2 || e == 4 || e == 8) && D % (4 * e) == 0 && resident_bytes(ts, D / e, e) <= budget) chosen = e;
   } else if (chosen) {
     const int sms = num_sms();
@@ -427,11 +426,9 @@ static int resident_launch(const ResidentPlan& pl, const float* emb, const float
                            const scl_ms_params& p, float* per_tuple, float* demb, uint32_t* kept, float* loss,
                            unsigned int* counter, cudaStream_t stream) {
   auto kern = wms_tuple_kernel<TS>;
-  static std::atomic<size_t> configured{0};   // idempotent attribute, set only when it has to grow
-  if (configured.load(std::memory_order_relaxed) < pl.smem) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    configured.store(pl.smem, std::memory_order_relaxed);
-  }
+  static SmemAttrCache configured;            // per device; set only when it has to grow
+  int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), pl.smem, &configured);
+  if (rc_attr) return rc_attr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(unsigned(T) * pl.cluster);
   cfg.blockDim = dim3(kRThreads);
@@ -451,8 +448,7 @@ static int resident_launch(const ResidentPlan& pl, const float* emb, const float
 // SCL_ERR_UNSUPPORTED: the shape does not fit the resident kernel (caller falls through to the chunked one).
 int wms_resident_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
                         float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream) {
-  const char* off = getenv("SCL_WMS_CHUNKED");
-  if (off && atoi(off) != 0) return SCL_ERR_UNSUPPORTED;
+  if (knob_or(KNOB_WMS_CHUNKED, 0) != 0) return SCL_ERR_UNSUPPORTED;
   ResidentPlan pl;
   if (!resident_plan(T, S, D, &pl)) return SCL_ERR_UNSUPPORTED;
   switch (pl.ts) {

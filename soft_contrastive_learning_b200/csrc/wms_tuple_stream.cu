@@ -608,11 +608,9 @@ static int stream_launch(const float* emb, const float* dist, int T, int S, int 
                          cudaStream_t stream) {
   auto kern = wms_stream_kernel<TS, NW, CH, kPackedGram, kMmaBwd>;
   constexpr size_t smem = SSmem<TS, CH, kMmaBwd>::bytes;
-  static std::atomic<int> configured{0};
-  if (!configured.load(std::memory_order_relaxed)) {
-    SCL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured.store(1, std::memory_order_relaxed);
-  }
+  static SmemAttrCache configured;                      // per device
+  int rc_attr = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem, &configured);
+  if (rc_attr) return rc_attr;
   const int per_sm = (TS == 5 && NW <= 8) ? 2 : 1;
   int grid = num_sms() * per_sm;
   if (grid > T) grid = T;
@@ -641,8 +639,7 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   // backward with 10 consumer warps x 160 columns x 5 stages at 80 registers (2 CTAs per SM) ran 1.24-1.26 ms.
   // cp.async.bulk.prefetch.L2 of the chunks 4 / 8 positions beyond the ring: 1.07 / 1.09 ms (the prefetched lines push
   // the tuples waiting for their re-read out of L2).
-  const char* ce = getenv("SCL_WMS_STREAM_CFG");
-  const int cfg = ce ? atoi(ce) : (TS == 5 ? 6 : 2);
+  const int cfg = knob_or(KNOB_WMS_STREAM_CFG, TS == 5 ? 6 : 2);
   if (cfg == 6) return stream_launch<TS, 7, 224, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   // the wider register tiles (S > 25) need more registers than 16+ warps leave per thread
   if constexpr (TS == 5) {
@@ -657,8 +654,7 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
 // SCL_ERR_UNSUPPORTED: small batches go to the cluster kernels (more SMs per tuple).
 int wms_stream_launch(const float* emb, const float* dist, int T, int S, int D, const scl_ms_params& p, float* loss,
                       float* per_tuple, float* demb, uint32_t* kept, unsigned int* counter, cudaStream_t stream) {
-  const char* env = getenv("SCL_WMS_STREAM");          // 0: never, 1: always, unset: large batches
-  const int mode = env ? atoi(env) : -1;
+  const int mode = knob_or(KNOB_WMS_STREAM, -1);        // 0: never, 1: always, unset: large batches
   if (mode == 0) return SCL_ERR_UNSUPPORTED;
   if (S < 2 || S > 32 || D < 4 || (D & 3)) return SCL_ERR_UNSUPPORTED;
   if (mode != 1 && T < num_sms()) return SCL_ERR_UNSUPPORTED;

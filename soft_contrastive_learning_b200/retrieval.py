@@ -47,8 +47,17 @@ class KDTree:
               "scl_knn_build")
         self.last_stats = None
 
-    def query_device(self, queries, k=1, force_path=0):
-        """Device tensors in, device tensors out: (dist [Q,k] float64, idx [Q,k] int64)."""
+    MAX_K = 1024
+
+    def query_device(self, queries, k=1, force_path=0, out=None):
+        """Device tensors in, device tensors out: (dist [Q,k] float64, idx [Q,k] int64).
+        ``out`` = (dist, idx) pre-allocated contiguous device tensors (e.g. the two halves of one packed buffer)."""
+        k = int(k)
+        if k < 1:
+            raise ValueError("k must be >= 1")
+        if k > self.MAX_K:
+            raise ValueError(f"k={k} exceeds the supported maximum of {self.MAX_K} neighbours per query "
+                             "(scl_knn_query); split the request or raise kSelThreads/kTieCap in csrc/knn.cu")
         q = _f32(queries)
         if q.dim() == 1:
             q = q[None]
@@ -59,9 +68,13 @@ class KDTree:
         nbytes = C.c_size_t()
         check(L.scl_knn_query_workspace_bytes(self.R, self.D, Q, k, C.byref(nbytes)), "scl_knn_query_workspace_bytes")
         ws = _ws(nbytes.value, q.device)
-        dist = torch.empty((Q, k), dtype=torch.float64, device=q.device)
-        idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
-        stats = torch.zeros(4, dtype=torch.int32, device=q.device)
+        if out is None:
+            dist = torch.empty((Q, k), dtype=torch.float64, device=q.device)
+            idx = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+        else:
+            dist, idx = out
+            assert dist.shape == (Q, k) and idx.shape == (Q, k) and dist.is_contiguous() and idx.is_contiguous()
+        stats = torch.zeros(8, dtype=torch.int32, device=q.device)
         check(L.scl_knn_query(_p(self.db), _p(self.shadow), self.R, self.D, _p(q), Q, k, self.index_offset,
                               int(force_path), _p(dist), _p(idx), _p(stats), _p(ws), ws.numel(), _stream()),
               "scl_knn_query")
@@ -77,9 +90,12 @@ class KDTree:
         return (dist, idx) if return_distance else idx
 
     def stats(self):
-        """{n_queries, n_certified, n_fallback, path} of the last query (path 1 = exact scan, 2 = tensor pass)."""
+        """Counters of the last query (path 1 = exact scan, 2 = tensor pass).  ``n_fallback`` = queries the first tensor
+        pass could not certify; of those ``n_stage2`` were resolved by the second tensor stage and ``n_scan`` went to
+        the exact float64 scan."""
         s = self.last_stats.cpu().tolist()
-        return {"n_queries": s[0], "n_certified": s[1], "n_fallback": s[2], "path": s[3]}
+        return {"n_queries": s[0], "n_certified": s[1], "n_fallback": s[2], "path": s[3], "n_stage2": s[4],
+                "n_scan": s[5], "chunks": s[6]}
 
 
 def topk_merge(d_all, i_all):
@@ -87,7 +103,19 @@ def topk_merge(d_all, i_all):
     G, Q, k = d_all.shape
     d = torch.empty((Q, k), dtype=torch.float64, device=d_all.device)
     i = torch.empty((Q, k), dtype=torch.int64, device=d_all.device)
-    check(lib().scl_topk_merge(_p(d_all.contiguous()), _p(i_all.contiguous()), G, Q, k, _p(d), _p(i), _stream()),
+    check(lib().scl_topk_merge(_p(d_all.contiguous()), _p(i_all.contiguous()), G, Q, k, 0, _p(d), _p(i), _stream()),
+          "scl_topk_merge")
+    return d, i
+
+
+def topk_merge_packed(packed, G, Q, k):
+    """Merge G packed per-rank messages ``packed`` [G, 2, Q, k] (8-byte words: [g,0] = float64 distances, [g,1] = int64
+    indices) as one all-gather delivers them, without a repack."""
+    assert packed.is_contiguous() and packed.element_size() == 8 and packed.numel() == G * 2 * Q * k
+    d = torch.empty((Q, k), dtype=torch.float64, device=packed.device)
+    i = torch.empty((Q, k), dtype=torch.int64, device=packed.device)
+    base = packed.data_ptr()
+    check(lib().scl_topk_merge(C.c_void_p(base), C.c_void_p(base + Q * k * 8), G, Q, k, 2 * Q * k, _p(d), _p(i), _stream()),
           "scl_topk_merge")
     return d, i
 
@@ -106,16 +134,19 @@ class ShardedKDTree:
 
     def query_device(self, queries, k=1, force_path=0):
         import torch.distributed as dist
-        d, i = self.local.query_device(queries, k, force_path)
         if self.world == 1:
-            return d, i
-        Q, kk = d.shape
-        # concatenated layout [G*Q, k] (what both NCCL and gloo accept), viewed as [G, Q, k] for the merge
-        d_all = torch.empty((self.world * Q, kk), dtype=d.dtype, device=d.device)
-        i_all = torch.empty((self.world * Q, kk), dtype=i.dtype, device=i.device)
-        dist.all_gather_into_tensor(d_all, d.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(i_all, i.contiguous(), group=self.group)
-        return topk_merge(d_all.view(self.world, Q, kk), i_all.view(self.world, Q, kk))
+            return self.local.query_device(queries, k, force_path)
+        q = queries if isinstance(queries, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(queries))
+        q = q.to(self.local.db.device, dtype=torch.float32).contiguous()      # the device the shard lives on
+        if q.dim() == 1:
+            q = q[None]
+        Q = q.shape[0]
+        # one packed message per rank: [2, Q, k] 8-byte words (float64 distances | int64 indices), ONE all-gather
+        mine = torch.empty((2, Q, k), dtype=torch.int64, device=q.device)
+        self.local.query_device(q, k, force_path, out=(mine[0].view(torch.float64), mine[1]))
+        packed = torch.empty((self.world, 2, Q, k), dtype=torch.int64, device=q.device)
+        dist.all_gather_into_tensor(packed.view(self.world * 2 * Q, k), mine.view(2 * Q, k), group=self.group)
+        return topk_merge_packed(packed, self.world, Q, k)
 
     def query_from_host(self, q_host, k=1):
         """Queries that live in (pinned) host memory, identical on every rank: each rank copies only its 1/G slice over

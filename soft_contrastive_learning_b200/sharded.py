@@ -38,3 +38,42 @@ def wms_loss_sharded(distances, embeddings, d_alpha, d_beta, alpha=2.0, beta=50.
     emb = losses._f32(embeddings)
     loss, grad, _, _ = losses._wms_tuple_raw(emb, losses._f32(distances), params, need_grad=True)
     return combine_tuple_shards(loss.reshape(()), grad, emb.shape[0], group)
+
+
+# ----------------------------------------------------------------------------------------------
+# NetVLAD head + PCA projection, batch-parallel
+# ----------------------------------------------------------------------------------------------
+def _netvlad_local_fwd_bwd(x_local, assign_w, centers, dout_fn):
+    """This rank's images through the CUDA head (csrc/netvlad*.cu): returns (vlad, dx, dW_local, dC_local)."""
+    from . import netvlad
+    xt = x_local.detach().requires_grad_(True)
+    wt = assign_w.detach().requires_grad_(True)
+    ct = centers.detach().requires_grad_(True)
+    vlad = netvlad.netVLAD(xt, wt, ct)
+    dout = dout_fn(vlad.detach())
+    vlad.backward(dout)
+    return vlad.detach(), xt.grad, wt.grad, ct.grad
+
+
+def allreduce_netvlad_grads(dw_local, dc_local, group=None):
+    """ONE all-reduce (sum) of the packed [dW | dC] buffer (2 x C x K floats = 256 KB for the reference's 512 x 64):
+    the only parameters of the head are 'assignment/kernel' and 'cluster_centers' (model/nets.py:12), restored and trained
+    as ordinary variables (train/train.py:874-892).  Returns (dW, dC) views of the reduced buffer."""
+    packed = torch.stack((dw_local.reshape(-1), dc_local.reshape(-1)))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed[0].reshape(dw_local.shape), packed[1].reshape(dc_local.shape)
+
+
+def netvlad_step_sharded(x_local, assign_w, centers, dout_fn, group=None, local_fwd_bwd=None):
+    """One data-parallel forward+backward of the NetVLAD head (model/nets.py:66-67 and what ``optimizer.minimize``
+    differentiates, train/train.py:874-878): the images of the batch are split over the ranks (``x_local`` [B_local,
+    HW, C] on this rank), the weights are replicated; every rank runs the head on its images and the only exchange is
+    the all-reduce of ``[dW | dC]``.  ``dout_fn(vlad_local)`` returns d(global loss)/d(vlad_local) -- e.g. the PCA
+    backward of the gradient a tuple-sharded loss produced (``V`` replicated, 537 MB at 32768 -> 4096); it must already
+    carry the global-batch normalisation (``combine_tuple_shards`` does that for the tuple losses).
+    Returns (vlad_local, dx_local, dW, dC) with dW, dC identical on every rank."""
+    fn = local_fwd_bwd or _netvlad_local_fwd_bwd
+    vlad, dx, dw, dc = fn(x_local, assign_w, centers, dout_fn)
+    dw, dc = allreduce_netvlad_grads(dw, dc, group)
+    return vlad, dx, dw, dc

@@ -84,6 +84,61 @@ def retrieval_problem(R, Q, D, seed=42, noise=0.5, dtype=np.float32, extent=1000
     return db.astype(dtype), qry.astype(dtype), ref_xy, query_xy, src
 
 
+def trajectory_layout(R, rng, stop_frac=0.05, stop_len=(100, 300)):
+    """Frame index -> distance travelled along the route, in frames at cruising speed, for one traversal with stops.
+    About ``stop_frac`` of the R frames belong to stops (vehicle standing: zero velocity for stop_len[0]..stop_len[1]
+    consecutive frames).  Returns (s [R] float64, stopped [R] bool)."""
+    stopped = np.zeros(R, dtype=bool)
+    target = int(stop_frac * R)
+    placed, guard = 0, 0
+    while placed < target and guard < 10000:
+        guard += 1
+        n = int(rng.integers(stop_len[0], stop_len[1] + 1))
+        t0 = int(rng.integers(0, max(1, R - n)))
+        if stopped[max(0, t0 - 1):t0 + n + 1].any():
+            continue
+        stopped[t0:t0 + n] = True
+        placed += n
+    s = np.cumsum(~stopped).astype(np.float64)
+    return s, stopped
+
+
+def trajectory_rows(s, stopped, anchors, seg_len, frame_noise, stop_noise, noise):
+    """Descriptors of frames at route positions ``s``: great-circle interpolation between consecutive random anchor
+    descriptors (cos/sin weights keep every dimension at unit variance: PCA-whitened statistics), plus per-frame noise
+    (``stop_noise`` while standing, ``frame_noise`` otherwise).  Works on NumPy arrays and on torch tensors alike."""
+    seg = (s // seg_len)
+    theta = (s - seg * seg_len) * (np.pi / 2 / seg_len)
+    if type(s).__module__.startswith("torch"):
+        import torch
+        seg = seg.long()
+        sig = torch.where(stopped, torch.full_like(theta, stop_noise), torch.full_like(theta, frame_noise))
+        x = torch.cos(theta)[:, None].float() * anchors[seg] + torch.sin(theta)[:, None].float() * anchors[seg + 1]
+        return x + sig[:, None].float() * noise
+    seg = seg.astype(np.int64)
+    sig = np.where(stopped, stop_noise, frame_noise)
+    x = np.cos(theta)[:, None] * anchors[seg] + np.sin(theta)[:, None] * anchors[seg + 1]
+    return (x + sig[:, None] * noise).astype(np.float32)
+
+
+def trajectory_problem(R, Q, D, seed=42, seg_len=64, frame_noise=0.05, stop_noise=2e-3, stop_frac=0.05,
+                       stop_len=(100, 300), query_noise=0.05):
+    """Clustered retrieval data as a real traversal produces it (SURVEY 8d `db = f(xy) + noise`):
+    the database holds the descriptors of R CONSECUTIVE frames of one drive -- neighbouring frames are near-duplicates
+    (squared distance ~ D (pi/2/seg_len)^2 j^2 for frames j apart) and at the stops hundreds of frames are identical up
+    to sensor noise, far inside the fp16 rounding bound of the tensor pass.  Queries are frames of a second drive:
+    perturbed database frames, about ``stop_frac`` of them on a stop.
+    Returns (db [R,D] f32, queries [Q,D] f32, info dict with 'src', 'stopped', 's')."""
+    rng = np.random.default_rng(seed)
+    s, stopped = trajectory_layout(R, rng, stop_frac, stop_len)
+    n_anchor = int(s[-1] // seg_len) + 2
+    anchors = rng.standard_normal((n_anchor, D)).astype(np.float32)
+    db = trajectory_rows(s, stopped, anchors, seg_len, frame_noise, stop_noise, rng.standard_normal((R, D)).astype(np.float32))
+    src = rng.integers(0, R, size=Q)
+    qry = (db[src] + query_noise * rng.standard_normal((Q, D))).astype(np.float32)
+    return db, qry, {"src": src, "stopped": stopped, "s": s}
+
+
 def netvlad_problem(B=2, H=3, W=4, C=512, K=64, Dout=128, seed=42):
     """BASELINE config 2 shape (scaled by the caller): conv5 maps, assignment weights, centres, PCA (V, m, var)."""
     rng = np.random.default_rng(seed)

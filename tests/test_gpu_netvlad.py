@@ -13,8 +13,11 @@ def relmax(a, b):
     return np.abs(np.asarray(a, dtype=np.float64) - b).max() / max(np.abs(b).max(), 1e-30)
 
 
-@pytest.mark.parametrize("B,H,W", [(2, 3, 4), (3, 11, 15), (2, 30, 40)])
-def test_netvlad_forward_backward(cuda_lib, B, H, W):
+NV_TOL = 1e-5      # north_star: 1e-5 relative (fp32); gradients relative to their max-norm
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 3, 4), (3, 11, 15), (2, 30, 40), (5, 9, 13)])
+def test_netvlad_forward_backward(cuda_lib, measured, B, H, W):
     from soft_contrastive_learning_b200 import netvlad
     x, aw, cc, *_ = synth.netvlad_problem(B=B, H=H, W=W, seed=42)
     rng = np.random.default_rng(0)
@@ -29,14 +32,78 @@ def test_netvlad_forward_backward(cuda_lib, B, H, W):
     co = torch.tensor(cc.astype(np.float64), requires_grad=True)
     ro = onv.netvlad_head(xo, wo, co)
     (ro * torch.tensor(dout.astype(np.float64))).sum().backward()
-    assert relmax(out.detach().cpu().numpy(), ro.detach().numpy()) < 1e-5
-    assert relmax(xt.grad.cpu().numpy(), xo.grad.numpy()) < 5e-5
-    assert relmax(wt.grad.cpu().numpy(), wo.grad.numpy()) < 5e-5
-    assert relmax(ct.grad.cpu().numpy(), co.grad.numpy()) < 5e-5
+    errs = dict(out=relmax(out.detach().cpu().numpy(), ro.detach().numpy()), dx=relmax(xt.grad.cpu().numpy(), xo.grad.numpy()),
+                dW=relmax(wt.grad.cpu().numpy(), wo.grad.numpy()), dC=relmax(ct.grad.cpu().numpy(), co.grad.numpy()))
+    measured(f"netvlad_B{B}_{H}x{W}", **errs)
+    assert max(errs.values()) < NV_TOL, errs
     assert np.allclose((out.detach().cpu().numpy() ** 2).sum(1), 1.0, atol=1e-5)
 
 
-def test_pca_forward_backward_and_sklearn(cuda_lib):
+def test_netvlad_and_pca_config2_full_size(cuda_lib, measured):
+    """BASELINE config 2 at its size: B = 256 maps of 30x40x512, K = 64, PCA 32768 -> 4096, forward and backward on the GPU.
+    The float64 oracle runs on a 16-image subset (NetVLAD is per image; dW / dC are sums over images, checked by
+    linearity: the B = 256 result equals the sum of sixteen 16-image calls, one of which is held to the oracle) and on a
+    subset of the PCA's output / input columns (all 256 rows)."""
+    from soft_contrastive_learning_b200 import netvlad
+    free, _ = torch.cuda.mem_get_info()
+    if free < 12 * 2 ** 30:
+        pytest.skip("needs ~8 GB of HBM")
+    B, H, W, Cc, K, Dout = 256, 30, 40, 512, 64, 4096
+    Din = Cc * K
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.randn((B, H, W, Cc), generator=g, device="cuda")
+    aw = 0.05 * torch.randn((Cc, K), generator=g, device="cuda")
+    cc = 0.05 * torch.randn((Cc, K), generator=g, device="cuda")
+    V = torch.randn((Dout, Din), generator=g, device="cuda") / Din ** 0.5
+    m = 0.01 * torch.randn(Din, generator=g, device="cuda")
+    var = 0.5 + 1.5 * torch.rand(Dout, generator=g, device="cuda")
+    dy = torch.randn((B, Dout), generator=g, device="cuda")
+
+    def run(xs, dys):
+        xt, wt, ct = xs.clone().requires_grad_(True), aw.clone().requires_grad_(True), cc.clone().requires_grad_(True)
+        vlad = netvlad.netVLAD(xt, wt, ct)
+        vlad.retain_grad()
+        y = netvlad.pca_project(vlad, V, m, var)
+        (y * dys).sum().backward()
+        return vlad.detach(), y.detach(), vlad.grad, xt.grad, wt.grad, ct.grad
+
+    vlad, y, dvlad, dx, dw, dc = run(x, dy)
+    assert torch.isfinite(y).all() and torch.isfinite(dx).all()
+    # (1) linearity in the batch: sum of 16-image calls == the 256-image call (dW, dC); per-image results identical
+    dw_sum, dc_sum = torch.zeros_like(dw), torch.zeros_like(dc)
+    for b0 in range(0, B, 16):
+        v16, y16, dv16, dx16, dw16, dc16 = run(x[b0:b0 + 16], dy[b0:b0 + 16])
+        dw_sum += dw16
+        dc_sum += dc16
+        if b0 in (0, 112, 240):
+            assert relmax(v16.cpu().numpy(), vlad[b0:b0 + 16].double().cpu().numpy()) < 2e-6
+            assert relmax(dx16.cpu().numpy(), dx[b0:b0 + 16].double().cpu().numpy()) < 2e-6
+    lin = dict(dW=relmax(dw_sum.cpu().numpy(), dw.double().cpu().numpy()), dC=relmax(dc_sum.cpu().numpy(), dc.double().cpu().numpy()))
+    measured("netvlad_config2_linearity", **lin)
+    assert max(lin.values()) < 5e-6, lin
+    # (2) the float64 oracle on images 96..111 with the gradient that actually arrived from the PCA backward
+    sl = slice(96, 112)
+    xo = x[sl].double().cpu().requires_grad_(True)
+    wo, co = aw.double().cpu().requires_grad_(True), cc.double().cpu().requires_grad_(True)
+    ro = onv.netvlad_head(xo, wo, co)
+    (ro * dvlad[sl].double().cpu()).sum().backward()
+    _, _, _, dx_s, dw_s, dc_s = run(x[sl], dy[sl])
+    errs = dict(out=relmax(vlad[sl].cpu().numpy(), ro.detach().numpy()), dx=relmax(dx[sl].cpu().numpy(), xo.grad.numpy()),
+                dW16=relmax(dw_s.cpu().numpy(), wo.grad.numpy()), dC16=relmax(dc_s.cpu().numpy(), co.grad.numpy()))
+    measured("netvlad_config2_vs_oracle_16_images", **errs)
+    assert max(errs.values()) < NV_TOL, errs
+    # (3) PCA 32768 -> 4096 against float64 on 256 output columns (forward) and 512 input columns (backward), all rows
+    gi = torch.Generator().manual_seed(1)
+    oc = torch.randperm(Dout, generator=gi)[:256].cuda()
+    ic = torch.randperm(Din, generator=gi)[:512].cuda()
+    yo = ((vlad.double() - m.double()) @ V[oc].double().t()) / var[oc].double().sqrt()
+    dxo = (dy.double() / var.double().sqrt()) @ V[:, ic].double()
+    perr = dict(y=relmax(y[:, oc].cpu().numpy(), yo.cpu().numpy()), dvlad=relmax(dvlad[:, ic].cpu().numpy(), dxo.cpu().numpy()))
+    measured("pca_config2_32768_to_4096", **perr)
+    assert max(perr.values()) < NV_TOL, perr
+
+
+def test_pca_forward_backward_and_sklearn(cuda_lib, measured):
     from sklearn.decomposition import PCA
     from soft_contrastive_learning_b200 import netvlad
     x, aw, cc, V, m, var = synth.netvlad_problem(B=4, H=2, W=2, Dout=256, seed=1)
@@ -50,6 +117,7 @@ def test_pca_forward_backward_and_sklearn(cuda_lib):
     fo = torch.tensor(feats.astype(np.float64), requires_grad=True)
     yo = onv.pca_project(fo, V.astype(np.float64), m.astype(np.float64), var.astype(np.float64))
     (yo * torch.tensor(dy.astype(np.float64))).sum().backward()
+    measured("pca_B4_Dout256", y=relmax(y.detach().cpu().numpy(), yo.detach().numpy()), dx=relmax(ft.grad.cpu().numpy(), fo.grad.numpy()))
     assert relmax(y.detach().cpu().numpy(), yo.detach().numpy()) < 1e-5
     assert relmax(ft.grad.cpu().numpy(), fo.grad.numpy()) < 1e-5
     # evaluation twin: sklearn PCA(whiten=True).transform (top-n.py:74-77)
@@ -90,7 +158,7 @@ def test_pca_tensor_core_gemm_shapes(cuda_lib, B, Din, Dout, precision):
     assert relmax(xt.grad.cpu().numpy(), dxo) < tol
 
 
-def test_pca_tensor_core_matches_simt_fallback(cuda_lib, monkeypatch):
+def test_pca_tensor_core_matches_simt_fallback(cuda_lib, tune):
     from soft_contrastive_learning_b200 import netvlad
     rng = np.random.default_rng(5)
     x = rng.standard_normal((64, 1024)).astype(np.float32)
@@ -98,7 +166,7 @@ def test_pca_tensor_core_matches_simt_fallback(cuda_lib, monkeypatch):
     m = (0.1 * rng.standard_normal(1024)).astype(np.float32)
     var = rng.uniform(0.5, 2.0, 128).astype(np.float32)
     a = netvlad.pca_project(x, V, m, var)
-    monkeypatch.setenv("SCL_GEMM_SIMT", "1")
+    tune("SCL_GEMM_SIMT", 1)
     b = netvlad.pca_project(x, V, m, var)
     assert relmax(a, b) < 1e-5
 

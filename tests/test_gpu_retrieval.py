@@ -46,17 +46,59 @@ def test_ties_are_ordered_by_index(cuda_lib):
     base = rng.standard_normal((50, 16)).astype(np.float32)
     db = np.concatenate([base, base, base], 0)               # every row appears three times
     qry = base[:7] + 0.0
-    for path in (1,):
-        d, i = retrieval.KDTree(db).query(qry, k=6, force_path=path)
-        rd, ri = orr.knn_bruteforce_exact(db, qry, 6)
-        check_exact(d, i, rd, ri)
-        assert (i[:, :3] == np.arange(7)[:, None] + np.array([0, 50, 100])[None]).all()
+    d, i = retrieval.KDTree(db).query(qry, k=6, force_path=1)
+    rd, ri = orr.knn_bruteforce_exact(db, qry, 6)
+    check_exact(d, i, rd, ri)
+    assert (i[:, :3] == np.arange(7)[:, None] + np.array([0, 50, 100])[None]).all()
+
+
+@pytest.mark.parametrize("force_path", [2, 4], ids=["tensor_pass", "tensor_pass_then_stage2"])
+@pytest.mark.parametrize("copies,k", [(3, 6), (3, 25), (40, 25), (100, 25)])
+def test_exact_ties_on_the_tensor_path(cuda_lib, force_path, copies, k):
+    """Exact duplicate rows through the tcgen05 candidate pass: equal fp16 scores, the `s_k + 2 eps` cut, the (distance,
+    index) order of the rescored candidates and -- with 40 / 100 copies -- more ties than the k' = 64 candidate list
+    holds, which the certificate must refuse and the second tensor stage (or the exact scan) must order by index."""
+    from soft_contrastive_learning_b200 import retrieval
+    rng = np.random.default_rng(13)
+    n_base = 6000 // copies
+    base = rng.standard_normal((n_base, 64)).astype(np.float32)
+    db = np.concatenate([base] * copies, 0)                  # row j appears at j, j + n_base, j + 2 n_base, ...
+    nq = min(96, n_base)
+    qry = np.concatenate([base[:nq], base[:32] + 0.25 * rng.standard_normal((32, 64)).astype(np.float32)], 0)
+    tree = retrieval.KDTree(db)
+    d, i = tree.query(qry, k=k, force_path=force_path)
+    assert tree.stats()["path"] == 2
+    rd, ri = orr.knn_bruteforce_exact(db, qry, k)
+    check_exact(d, i, rd, ri)
+    m = min(copies, k)
+    assert (i[:nq, :m] == np.arange(nq)[:, None] + n_base * np.arange(m)[None]).all()
+    assert (d[:nq, :m] == 0).all()
+
+
+def test_exact_ties_across_shards_and_the_merge(cuda_lib):
+    """Duplicates that live on DIFFERENT shards: per-shard tensor passes, global index offsets, the merge kernel's
+    (distance, index) order -- through the packed one-message layout the NCCL path uses."""
+    from soft_contrastive_learning_b200 import retrieval
+    rng = np.random.default_rng(14)
+    base = rng.standard_normal((1500, 64)).astype(np.float32)
+    db = np.concatenate([base] * 4, 0)                       # 6000 rows, copy c of row j at c * 1500 + j
+    qry = base[:50]
+    G, k, Q = 3, 25, 50                                      # 2000 rows per shard: the copies straddle shard borders
+    packed = torch.empty((G, 2, Q, k), dtype=torch.int64, device="cuda")
+    for r in range(G):
+        lo, hi = retrieval.shard_bounds(6000, G, r)
+        retrieval.KDTree(db[lo:hi], index_offset=lo).query_device(torch.tensor(qry, device="cuda"), k, force_path=2,
+                                                                  out=(packed[r, 0].view(torch.float64), packed[r, 1]))
+    d, i = retrieval.topk_merge_packed(packed, G, Q, k)
+    rd, ri = orr.knn_bruteforce_exact(db, qry, k)
+    check_exact(d.cpu().numpy(), i.cpu().numpy(), rd, ri)
+    assert (i[:, :4].cpu().numpy() == np.arange(50)[:, None] + 1500 * np.arange(4)[None]).all()
 
 
 @pytest.fixture(params=["1", "2", "3"], ids=["cta_group1", "cta_pair", "cta_pair_wide"])
-def tc_variant(request, monkeypatch):
-    """Both tensor-pass kernels: single-CTA 128x256 tiles and cta_group::2 CTA pairs (256x256)."""
-    monkeypatch.setenv("SCL_KNN_TC_VARIANT", request.param)
+def tc_variant(request, tune):
+    """The tensor-pass kernels: single-CTA 128x256 tiles and cta_group::2 CTA pairs (256x256, 256x512)."""
+    tune("SCL_KNN_TC_VARIANT", int(request.param))
     return request.param
 
 
@@ -67,11 +109,11 @@ def test_tensor_pass_raw_scores_match_fp16_gemm(cuda_lib, tc_variant):
     db, qry, *_ = synth.retrieval_problem(R=R, Q=Q, D=D, seed=4)
     tree = retrieval.KDTree(db)
     dbg = torch.full((Q, R), float("nan"), dtype=torch.float32, device="cuda")
-    os.environ["SCL_KNN_DEBUG_SCORES"] = hex(dbg.data_ptr())
+    cuda_lib.scl_knn_set_debug_scores(C.c_void_p(dbg.data_ptr()), dbg.numel())    # explicit, size-checked test hook
     try:
         tree.query_device(torch.tensor(qry, device="cuda"), k=25, force_path=2)
     finally:
-        del os.environ["SCL_KNN_DEBUG_SCORES"]
+        cuda_lib.scl_knn_set_debug_scores(None, 0)
     torch.cuda.synchronize()
     got = dbg.cpu().numpy().astype(np.float64)
     assert not np.isnan(got).any(), "some tiles were never written"
@@ -101,24 +143,28 @@ def test_tensor_pass_is_exact(cuda_lib, tc_variant, R, Q, D, k):
     assert st["n_fallback"] <= Q // 10, st
 
 
-def test_fallback_path_is_exact(cuda_lib):
+@pytest.mark.parametrize("force_path,key", [(3, "n_scan"), (4, "n_stage2")], ids=["exact_scan", "stage2"])
+def test_fallback_paths_are_exact(cuda_lib, force_path, key):
     from soft_contrastive_learning_b200 import retrieval
     db, qry, *_ = synth.retrieval_problem(R=6000, Q=40, D=128, seed=6)
     tree = retrieval.KDTree(db)
-    d, i = tree.query(qry, k=25, force_path=3)               # every query forced through the exact-scan fallback
-    assert tree.stats()["n_fallback"] == 40
+    d, i = tree.query(qry, k=25, force_path=force_path)      # every query forced through the exact scan / the second stage
+    st = tree.stats()
+    assert st["n_fallback"] == 40 and st[key] == 40, st
     rd, ri = orr.knn_bruteforce(db, qry, 25)
     check_exact(d, i, rd, ri)
 
 
-def test_clustered_descriptors_trigger_the_certificate(cuda_lib):
-    """Adversarial for fp16: 200 near-duplicates of each query direction differ by less than the rounding bound,
-    so the certificate must refuse and the exact path must still return the right order."""
+@pytest.mark.parametrize("dups,expect", [(200, "n_stage2"), (3000, "n_scan")])
+def test_clustered_descriptors_trigger_the_certificate(cuda_lib, dups, expect):
+    """Adversarial for fp16: `dups` near-duplicates of each query direction differ by less than the rounding bound, so the
+    certificate must refuse.  200 of them fit the second tensor stage's list (2048 rows inside the bound); 3000 overflow it
+    and go to the float64 scan.  Either way the order is the exact one."""
     from soft_contrastive_learning_b200 import retrieval
     rng = np.random.default_rng(7)
     D = 128
     centers = rng.standard_normal((8, D)).astype(np.float32)
-    near = (centers[:, None, :] + 1e-4 * rng.standard_normal((8, 200, D))).reshape(-1, D).astype(np.float32)
+    near = (centers[:, None, :] + 1e-4 * rng.standard_normal((8, dups, D))).reshape(-1, D).astype(np.float32)
     far = rng.standard_normal((4000, D)).astype(np.float32)
     db = np.concatenate([far, near], 0)
     qry = centers
@@ -126,7 +172,46 @@ def test_clustered_descriptors_trigger_the_certificate(cuda_lib):
     d, i = tree.query(qry, k=25, force_path=2)
     rd, ri = orr.knn_bruteforce_exact(db, qry, 25)
     check_exact(d, i, rd, ri)
-    assert tree.stats()["n_fallback"] >= 1
+    st = tree.stats()
+    assert st["n_fallback"] == 8 and st[expect] == 8, st
+
+
+def test_stage2_resolves_refused_queries_of_a_trajectory(cuda_lib, tune):
+    """Clustered descriptors as a real traversal produces them (synth.trajectory_problem: AR(1) frames with stops where
+    the vehicle stands still and hundreds of frames are near-identical).  Queries that fall on a stop are refused by the
+    first pass and must be resolved by the second tensor stage, not by the float64 scan; with stage 2 switched off the
+    scan gives the same answer.  Checked against the reference's own call, sklearn KDTree.query."""
+    from soft_contrastive_learning_b200 import retrieval
+    db, qry, info = synth.trajectory_problem(R=12000, Q=256, D=128, seed=3, stop_frac=0.25, stop_len=(150, 400))
+    tree = retrieval.KDTree(db)
+    d, i = tree.query(qry, k=25, force_path=2)
+    st = tree.stats()
+    kd_d, kd_i = orr.knn_kdtree(db, qry, 25)                 # evaluation/top-n.py:103-106
+    check_exact(d, i, kd_d, kd_i)
+    assert st["n_fallback"] >= 16 and st["n_scan"] == 0 and st["n_stage2"] == st["n_fallback"], st
+    tune("SCL_KNN_STAGE2", 0)
+    d0, i0 = tree.query(qry, k=25, force_path=2)
+    assert tree.stats()["n_scan"] == st["n_fallback"]
+    assert np.array_equal(i0, i) and np.array_equal(d0, d)
+
+
+@pytest.mark.parametrize("chunk", [256, 512])
+def test_chunk_pipeline_matches_single_chunk(cuda_lib, tune, chunk):
+    """scl_knn_query splits the queries into chunks and runs the merge / rescore / certificate of one chunk on a helper
+    stream under the tensor pass of the next: any chunking must return bit-identical results (ragged last chunk,
+    refused queries in several chunks)."""
+    from soft_contrastive_learning_b200 import retrieval
+    db, qry, info = synth.trajectory_problem(R=9000, Q=1100, D=64, seed=5, stop_frac=0.1, stop_len=(100, 200))
+    tree = retrieval.KDTree(db)
+    tune("SCL_KNN_CHUNK_Q", 0)
+    d1, i1 = tree.query(qry, k=25, force_path=2)
+    assert tree.stats()["chunks"] == 1
+    tune("SCL_KNN_CHUNK_Q", chunk)
+    d2, i2 = tree.query(qry, k=25, force_path=2)
+    assert tree.stats()["chunks"] == -(-1100 // chunk)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    rd, ri = orr.knn_bruteforce_exact(db, qry, 25)
+    check_exact(d2, i2, rd, ri)
 
 
 def test_topk_merge_and_index_offsets(cuda_lib):
@@ -163,17 +248,39 @@ def test_geo_and_recall_and_top_n_payload(cuda_lib):
         assert np.array_equal(retrieval.recall_curves(np.asarray(got[1]), Xo1)[0], Yo1)
 
 
-def test_full_size_properties_1M_x_4096(cuda_lib):
-    """BASELINE config 4 size (1M x 4096 fp32 database) through size-independent properties:
-    queries that ARE database rows return themselves at distance 0; lists are sorted; the tensor pass and the
-    exact scan agree bit-for-bit on a query subset."""
-    from soft_contrastive_learning_b200 import retrieval
+def _fp64_topk_chunked(db, qry, k, chunk=32768):
+    """Independent float64 reference on the device, nothing of the product in it: d^2 = |q|^2 + |r|^2 - 2 q.r with a
+    float64 GEMM per row chunk, torch.topk per chunk, final order by (d^2, index) on the host."""
+    q64 = qry.double()
+    qn = (q64 * q64).sum(1, keepdim=True)
+    cand_d, cand_i = [], []
+    for r0 in range(0, db.shape[0], chunk):
+        r64 = db[r0:r0 + chunk].double()
+        d2 = qn + (r64 * r64).sum(1)[None, :] - 2.0 * (q64 @ r64.t())
+        v, ix = torch.topk(d2, min(k + 8, d2.shape[1]), dim=1, largest=False)
+        cand_d.append(v.cpu().numpy())
+        cand_i.append((ix + r0).cpu().numpy())
+    cd, ci = np.concatenate(cand_d, 1), np.concatenate(cand_i, 1)
+    out_d, out_i = np.empty((qry.shape[0], k)), np.empty((qry.shape[0], k), dtype=np.int64)
+    for q in range(qry.shape[0]):
+        order = np.lexsort((ci[q], cd[q]))[:k]
+        out_d[q], out_i[q] = cd[q][order], ci[q][order]
+    return out_d, out_i
+
+
+def test_full_size_properties_1M_x_4096(cuda_lib, measured):
+    """BASELINE config 4 size (1M x 4096 fp32 database): 512 queries against an INDEPENDENT chunked float64 computation
+    (torch float64 GEMM + topk on the device, no kernel of this repo), plus size-independent properties: queries that ARE
+    database rows return themselves at distance 0, lists are sorted, the pipelined chunks agree with one chunk."""
+    from soft_contrastive_learning_b200 import _lib, retrieval
     free, _ = torch.cuda.mem_get_info()
     if free < 60 * 2 ** 30:
         pytest.skip("needs ~30 GB of HBM")
     R, D, Q = 1_000_000, 4096, 512
     g = torch.Generator(device="cuda").manual_seed(42)
-    db = torch.randn((R, D), generator=g, device="cuda", dtype=torch.float32)
+    db = torch.empty((R, D), device="cuda", dtype=torch.float32)
+    for r0 in range(0, R, 65536):
+        db[r0:r0 + 65536] = torch.randn((min(65536, R - r0), D), generator=g, device="cuda")
     src = torch.randint(0, R, (Q,), generator=g, device="cuda")
     qry = db[src] + 0.5 * torch.randn((Q, D), generator=g, device="cuda")
     qry[:64] = db[src[:64]]
@@ -184,9 +291,58 @@ def test_full_size_properties_1M_x_4096(cuda_lib):
     assert (i[:, 0] == src).all()                                  # planted neighbour is rank 1
     assert (d[:64, 0] == 0).all()
     assert (d[:, 1:] >= d[:, :-1]).all()
-    d2, i2 = tree.query_device(qry[:12], k=25, force_path=1)       # exact scan on a subset
-    assert torch.equal(i[:12], i2) and torch.equal(d[:12], d2)
+    ref_d2, ref_i = _fp64_topk_chunked(db, qry, 25)
+    assert np.array_equal(i.cpu().numpy(), ref_i), f"{(i.cpu().numpy() != ref_i).sum()} index mismatches vs float64 GEMM"
+    got_d2 = d.cpu().numpy() ** 2
+    # the GEMM form cancels |q|^2 + |r|^2 ~ 8200 down to d^2: absolute error ~ 8200 * 2^-52 * sqrt(4096)
+    err = np.abs(got_d2[:, 1:] - ref_d2[:, 1:]).max()
+    measured("retrieval_1Mx4096_vs_fp64_gemm", max_abs_d2_err=err, n_queries=Q, n_fallback=st["n_fallback"])
+    assert err < 1e-8
     assert st["n_fallback"] <= Q // 20, st
+    with _lib.tuning(SCL_KNN_CHUNK_Q=128):                         # 4 pipelined chunks
+        d4, i4 = tree.query_device(qry, k=25)
+    assert tree.stats()["chunks"] == 4 and torch.equal(i4, i) and torch.equal(d4, d)
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from soft_contrastive_learning_b200 import retrieval
+        R, Q, D, k = 40000, 300, 128, 25
+        db, qry, info = synth.trajectory_problem(R=R, Q=Q, D=D, seed=9, stop_frac=0.05, stop_len=(100, 200))
+        db = np.concatenate([db, db[:2000]], 0)                     # exact duplicates that land on the OTHER shard
+        lo, hi = retrieval.shard_bounds(db.shape[0], world, rank)
+        tree = retrieval.ShardedKDTree(torch.tensor(db[lo:hi], device="cuda"), index_offset=lo)
+        d, i = tree.query_device(torch.tensor(qry, device="cuda"), k)
+        d2, i2 = tree.query_from_host(torch.tensor(qry).pin_memory(), k)
+        assert torch.equal(i, i2) and torch.equal(d, d2)
+        if rank == 0:
+            np.savez(out, d=d.cpu().numpy(), i=i.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_kdtree_two_processes_nccl(cuda_lib, tmp_path):
+    """one process per GPU, database rows split over the ranks, ONE packed NCCL all-gather, merge kernel --
+    the exact global top-k on every rank, bit-identical to float64 brute force (ties across shards ordered by index)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "nccl.npz")
+    mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
+    db, qry, info = synth.trajectory_problem(R=40000, Q=300, D=128, seed=9, stop_frac=0.05, stop_len=(100, 200))
+    db = np.concatenate([db, db[:2000]], 0)
+    rd, ri = orr.knn_bruteforce_exact(db, qry, 25)
+    got = np.load(out)
+    check_exact(got["d"], got["i"], rd, ri)
 
 
 # ---------------------------------------------------------------------------------------------

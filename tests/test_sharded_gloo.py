@@ -1,5 +1,5 @@
 """CPU, world_size 2 over gloo: the sharded-retrieval host protocol (contiguous row shards, global index offsets,
-one all-gather of the per-shard [Q,k] lists, merge by (distance, index)) returns the exact global top-k.
+ONE all-gather of the packed per-shard [2,Q,k] messages, merge by (distance, index)) returns the exact global top-k.
 
 The two device-side pieces (local kNN, merge kernel) are replaced by oracle stand-ins injected from here; what is
 exercised is the product's distributed plumbing in soft_contrastive_learning_b200.retrieval."""
@@ -26,14 +26,19 @@ class _OracleLocal:
         self.X, self.off = np.asarray(X), index_offset
         self.db = torch.zeros(1)                 # the device the shard lives on (CPU in this test)
 
-    def query_device(self, q, k=1, force_path=0):
+    def query_device(self, q, k=1, force_path=0, out=None):
         from oracle import retrieval as orr
         d, i = orr.knn_bruteforce_exact(self.X, np.asarray(q), k)
         if d.shape[1] < k:      # shard smaller than k: pad like the device path (inf, -1)
             pad = k - d.shape[1]
             d = np.concatenate([d, np.full((d.shape[0], pad), np.inf)], 1)
             i = np.concatenate([i, np.full((i.shape[0], pad), -1 - self.off, dtype=np.int64)], 1)
-        return torch.from_numpy(d), torch.from_numpy(i + self.off)
+        d, i = torch.from_numpy(d), torch.from_numpy(i + self.off)
+        if out is not None:     # the product hands over the two halves of its packed all-gather message
+            out[0].copy_(d)
+            out[1].copy_(i)
+            return out
+        return d, i
 
 
 def _numpy_merge(d_all, i_all):
@@ -59,6 +64,9 @@ def _worker(rank, world, port, R, D, Q, k, out):
         lo, hi = retrieval.shard_bounds(R, world, rank)
         retrieval.KDTree = _OracleLocal            # test doubles for the two CUDA pieces
         retrieval.topk_merge = _numpy_merge
+        # the packed message [G, 2, Q, k] of 8-byte words, as ONE all-gather delivers it
+        retrieval.topk_merge_packed = lambda packed, G, Q, k: _numpy_merge(packed[:, 0].contiguous().view(torch.float64),
+                                                                         packed[:, 1].contiguous())
         tree = retrieval.ShardedKDTree(db[lo:hi], index_offset=lo)
         d, i = tree.query_device(qry, k)
         # queries in host memory: every rank copies its 1/G slice (ragged: Q = 9 over 2 ranks) and the slices are all-gathered
@@ -123,3 +131,56 @@ def test_tuple_shards_reproduce_the_single_call(tmp_path, counts):
         assert abs(float(p["loss"]) - float(whole)) <= 1e-12 * abs(float(whole))
     got = torch.cat([p["grad"] for p in parts])
     assert torch.allclose(got, g, rtol=1e-12, atol=1e-15)
+
+
+# ---------------------------------------------------------------------------------------------
+# NetVLAD head batch-parallel; the only exchange is one all-reduce of [dW | dC]
+# ---------------------------------------------------------------------------------------------
+def _oracle_netvlad_local(x_local, assign_w, centers, dout_fn):
+    """float64 oracle stand-in for the CUDA head on CPU (same contract as sharded._netvlad_local_fwd_bwd)."""
+    from oracle import netvlad as onv
+    xt = x_local.detach().clone().requires_grad_(True)
+    wt = assign_w.detach().clone().requires_grad_(True)
+    ct = centers.detach().clone().requires_grad_(True)
+    vlad = onv.netvlad_head(xt, wt, ct)
+    vlad.backward(dout_fn(vlad.detach()))
+    return vlad.detach(), xt.grad, wt.grad, ct.grad
+
+
+def _netvlad_worker(rank, world, port, counts, out):
+    import torch.distributed as dist
+    from soft_contrastive_learning_b200 import sharded
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(3)
+        B = sum(counts)
+        x = torch.randn((B, 12, 32), generator=g, dtype=torch.float64)
+        w = 0.3 * torch.randn((32, 64), generator=g, dtype=torch.float64)
+        c = 0.3 * torch.randn((32, 64), generator=g, dtype=torch.float64)
+        dout = torch.randn((B, 32 * 64), generator=g, dtype=torch.float64) / B      # gradient of a global-batch mean
+        lo = sum(counts[:rank])
+        sl = slice(lo, lo + counts[rank])
+        vlad, dx, dw, dc = sharded.netvlad_step_sharded(x[sl], w, c, lambda v: dout[sl], local_fwd_bwd=_oracle_netvlad_local)
+        torch.save({"vlad": vlad, "dx": dx, "dw": dw, "dc": dc}, out + f".{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("counts", [(4, 4), (5, 2)])
+def test_netvlad_batch_parallel_reproduces_the_single_call(tmp_path, counts):
+    """world_size 2 over gloo: per-rank images, replicated weights, ONE all-reduce of the packed [dW | dC]: both ranks end
+    with the gradients of one call over the whole batch; outputs and dx stay with the rank that owns the images."""
+    out = str(tmp_path / "nv_shard")
+    mp.spawn(_netvlad_worker, args=(2, _free_port(), counts, out), nprocs=2, join=True)
+    g = torch.Generator().manual_seed(3)
+    B = sum(counts)
+    x = torch.randn((B, 12, 32), generator=g, dtype=torch.float64)
+    w = 0.3 * torch.randn((32, 64), generator=g, dtype=torch.float64)
+    c = 0.3 * torch.randn((32, 64), generator=g, dtype=torch.float64)
+    dout = torch.randn((B, 32 * 64), generator=g, dtype=torch.float64) / B
+    vlad, dx, dw, dc = _oracle_netvlad_local(x, w, c, lambda v: dout)
+    parts = [torch.load(out + f".{r}") for r in range(2)]
+    for p in parts:
+        assert torch.allclose(p["dw"], dw, rtol=1e-12, atol=1e-15) and torch.allclose(p["dc"], dc, rtol=1e-12, atol=1e-15)
+    assert torch.allclose(torch.cat([p["vlad"] for p in parts]), vlad, rtol=1e-12, atol=1e-15)
+    assert torch.allclose(torch.cat([p["dx"] for p in parts]), dx, rtol=1e-12, atol=1e-15)
