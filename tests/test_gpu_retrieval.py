@@ -299,9 +299,9 @@ def test_full_size_properties_1M_x_4096(cuda_lib, measured):
     measured("retrieval_1Mx4096_vs_fp64_gemm", max_abs_d2_err=err, n_queries=Q, n_fallback=st["n_fallback"])
     assert err < 1e-8
     assert st["n_fallback"] <= Q // 20, st
-    with _lib.tuning(SCL_KNN_CHUNK_Q=128):                         # 4 pipelined chunks
+    with _lib.tuning(SCL_KNN_CHUNK_Q=128):                         # rounded up to the 256-query tile unit: 2 pipelined chunks
         d4, i4 = tree.query_device(qry, k=25)
-    assert tree.stats()["chunks"] == 4 and torch.equal(i4, i) and torch.equal(d4, d)
+    assert tree.stats()["chunks"] == 2 and torch.equal(i4, i) and torch.equal(d4, d)
 
 
 def _nccl_worker(rank, world, port, out):
