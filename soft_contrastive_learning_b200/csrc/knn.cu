@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
         }
         int before = incl - sum;
         const int rank = s_rank;
+        __syncwarp();                                 // every lane has read s_rank / s_prefix before one lane rewrites them
         if (before < rank && rank <= incl) {          // exactly one lane
           int j = 0;
           while (before + c[j] < rank) { before += c[j]; ++j; }

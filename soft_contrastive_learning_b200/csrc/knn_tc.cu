@@ -510,7 +510,8 @@ int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, 
   cuuint32_t box[3] = {box_inner, box_outer, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, dtype, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  swizzle_atom32 == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                      : (swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[96];

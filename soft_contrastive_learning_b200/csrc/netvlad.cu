@@ -16,6 +16,7 @@
 // warp-shuffle kernels.
 #include <algorithm>
 
+#include "netvlad_fused.cuh"
 #include "sgemm.cuh"
 #include "tc_gemm.cuh"
 
@@ -42,6 +43,10 @@ static size_t nv_ws_bytes(int B, int HW, int C, int K) {
   n += 3 * carve_bytes(size_t(B) * K, 4);
   n += carve_bytes(B, 4);
   return n;
+}
+// the fused kernels' scratch sits behind the buffers both paths share
+static size_t nv_ws_total(int B, int HW, int C, int K) {
+  return nv_ws_bytes(B, HW, C, K) + (nv_fused_ok(B, HW, C, K) ? nv_fused_ws_bytes(B, HW, C, K) : 0);
 }
 static NvWs nv_carve(void* p, size_t bytes, int B, int HW, int C, int K) {
   Carver c(p, bytes);
@@ -291,7 +296,7 @@ extern "C" int scl_netvlad_workspace_bytes(int B, int HW, int C, int K, size_t* 
   if (!bytes) return SCL_ERR_BAD_ARG;
   int rc = nv_check(B, HW, C, K);
   if (rc) return rc;
-  *bytes = nv_ws_bytes(B, HW, C, K);
+  *bytes = nv_ws_total(B, HW, C, K);
   return SCL_OK;
 }
 
@@ -301,12 +306,19 @@ extern "C" int scl_netvlad_fwd(const float* x, const float* assign_w, const floa
   int rc = nv_check(B, HW, C, K);
   if (rc) return rc;
   if (!aligned16(x) || !aligned16(out) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return SCL_ERR_ALIGN;
-  if (workspace_bytes < nv_ws_bytes(B, HW, C, K)) return SCL_ERR_WORKSPACE;
+  if (workspace_bytes < nv_ws_total(B, HW, C, K)) return SCL_ERR_WORKSPACE;
   rc = check_device();
   if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NvWs w = nv_carve(workspace, workspace_bytes, B, HW, C, K);
   const long long P = (long long)B * HW;
+  if (nv_fused_ok(B, HW, C, K) && tc_gemm_precision() == 0) {
+    // one pass over x: netvlad_fused.cu (the backward finds inv, a, V, asum, nk, nt where the generic path leaves them)
+    const size_t base = nv_ws_bytes(B, HW, C, K);
+    rc = nv_fused_fwd(x, assign_w, centers, B, HW, C, w.inv, w.a, w.V, w.asum, w.nk, w.nt, out,
+                      static_cast<char*>(workspace) + base, workspace_bytes - base, stream);
+    if (rc != SCL_ERR_UNSUPPORTED) return rc;
+  }
   nv_rownorm_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(x, P, C, w.inv);
   SCL_LAUNCH_CHECK();
   const int prec = tc_gemm_precision();

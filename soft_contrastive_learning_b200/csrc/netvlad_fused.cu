@@ -1,0 +1,721 @@
+// netvlad_fused.cu -- N1 NetVLAD aggregation head, forward, as ONE persistent tcgen05 kernel + a small tail.
+//
+// Replaces  x = tf.nn.l2_normalize(x, axis=-1); x = layers.netVLAD(x, 64)      (/root/reference/model/nets.py:66-67)
+// (math in netvlad.cu's header).  The generic path there is  rownorm -> logits GEMM -> softmax -> colsum ->
+// aggregation GEMM -> norms  and streams the [B,HW,C] conv5 maps from HBM three times.  Here every 128-position tile of
+// a map is read from HBM exactly once (and a second time from L2):
+//
+//   pass 1   logits[128 x 64] = X_tile[128 x C] . W[C x 64], 64 channels per stage.
+//   epilogue one thread per position (TMEM lane): logits * 1/|x|, soft-max over the 64 clusters (thread-local: the
+//            whole row sits in one accumulator row), a -> workspace (the backward reads it), a -> shared memory as the
+//            B operand of pass 2, column sums by a shuffle butterfly.
+//   pass 2   V[C x 64] += Xn_tile^T[C x 128] . a[128 x 64], Xn = X / |x|: the SAME tile, streamed again (L2 hit), as the
+//            MN-major A operand; C/128 accumulators of 64 TMEM columns stay resident across the tiles of an image.
+//   drain    when the image changes (or the CTA's range ends) the accumulators go to a per-(image, slot) partial;
+//            CTA ranges are contiguous runs of tiles, so an image is covered by a known, small number of CTAs.
+//   tail     (one CTA per image) fixed-order sum of the partials, centre term Cc * colsum(a), intra-normalisation,
+//            flatten, l2-normalisation.  Deterministic: no atomics anywhere.
+//
+// Arithmetic: fp32-grade on kind::f16.  Every fp32 operand is split into two fp16 halves x * 2^e = hi + lo (22
+// significant bits, |rounding| <= 2^-25 in scaled units) and a product is hi*hi + hi*lo + lo*hi with fp32 accumulation
+// (the dropped lo*lo is 2^-22 relative) -- the same error class as 3xTF32 at half the shared-memory traffic and half the
+// tensor time.  The fp16 range is handled exactly, not hoped for:
+//   pass 1   the eight "splitter" warps turn each landed fp32 stage into the two fp16 operand tiles; the power-of-two
+//            scale is chosen PER POSITION AND STAGE (max over the row's 64 channels -> [2^14, 2^15)), which is free
+//            because the logits accumulator is flushed into registers after every stage anyway (tensor-core fp32
+//            accumulation truncates; tc_gemm.cu) and the flush multiplies by the row's inverse scale.  The splitters
+//            also accumulate the row sums of squares: the l2-normalisation of nets.py:66 costs no pass of its own.
+//   pass 2   the splitters scale by 1/|x| (known by then), so |Xn| <= 1 and a <= 1: the constant scale 2^14 fits both.
+// Shared-memory layouts are the canonical 128-byte-swizzled tiles of the tcgen05 descriptors, written by the
+// splitter / epilogue threads (chunk ^ (row & 7)); TMA only lands raw fp32 boxes and the pre-split W.
+//
+// TMEM: columns [0,128) two logit accumulators (stages alternate), [128, 128 + C/2) the V accumulators.
+// [384, 512) two A-operand slots (fp16 hi | lo of the stage's X tile, written by the splitters with tcgen05.st).
+// Warps: 0, 3 = TMA producers (X), 1 = MMA issuer, 2 = TMA producer (W), 4-7 = epilogue, 8-15 = splitters.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "netvlad_fused.cuh"
+#include "tc_common.cuh"
+
+namespace scl {
+
+using namespace tc;
+
+constexpr int kFM = 128;                               // positions per tile
+constexpr uint32_t kLandBytes = 16384;                 // one landed fp32 box
+constexpr int kLand = 9;                               // landing slots (a stage consumes two)
+constexpr uint32_t kWBytes = 16384;                    // W slot: hi (8 KB) | lo (8 KB)
+constexpr uint32_t kOffW = kLand * kLandBytes;         // 144 KB
+constexpr uint32_t kOffA = kOffW + 2 * kWBytes;        // 176 KB: assignment tile, hi (16 KB) | lo (16 KB)
+constexpr uint32_t kOffTail = kOffA + 32768;           // 208 KB
+constexpr int kFThreads = 512;
+constexpr uint32_t kFTmemCols = 512;
+constexpr uint32_t kFVCol0 = 128;                      // V accumulators: columns [128, 384)
+constexpr uint32_t kFACol0 = 384;                      // A-operand slots: [384, 448), [448, 512): hi (32 columns) | lo (32)
+constexpr float kScale14 = 16384.0f;
+constexpr int kWCopies = 16;                           // replicas of the pre-split W (L2 hot-spot relief)
+
+struct FSmemTail {
+  uint64_t land_full[kLand], land_empty[kLand], a_full[2], a_empty[2], w_full[2], w_empty[2], acc_full[2], acc_empty[2];
+  uint64_t norm_full, at_full, v_full, v_empty;
+  uint32_t tmem_base;
+  alignas(16) float ssqp[2][kFM];                      // row sums of squares, one partial per splitter group
+  alignas(16) float inv[2][kFM];                       // 1 / |x| of the tile's rows (double-buffered by tile parity)
+  alignas(16) float uns[4][kFM];                       // per-row inverse scale of the last four pass-1 stages
+};
+
+struct NvFusedArgs {
+  int B, HW, C, tpi, units, nslots, dbg;
+  const float* x;      // [B, HW, C]
+  float* inv;          // [B*HW]
+  float* a;            // [B*HW, 64]
+  float* vpart;        // [B][nslots][C*64]
+  float* aspart;       // [B][nslots][4][64]
+  const float* wun;    // 2^-ew of the pre-split W
+  long long* trace;    // debug: [role][4096] clock stamps of CTA 0
+};
+
+#define NV_TRACE(role, idx) do { if (g.trace && blockIdx.x == 0 && (idx) < 4096) g.trace[(role) * 4096 + (idx)] = clock64(); } while (0)
+
+__host__ __device__ __forceinline__ int nv_cta_of_unit(long long u, int G, long long units) {
+  return int(((u + 1) * G - 1) / units);
+}
+
+__device__ __forceinline__ void st_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+// two scaled fp32 values -> packed fp16 hi pair and fp16 lo pair (lo = x - hi, exact in fp32 before its own rounding)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 hh = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&hh);
+  lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  split2(x[0], x[1], hi.x, lo.x);
+  split2(x[2], x[3], hi.y, lo.y);
+  split2(x[4], x[5], hi.z, lo.z);
+  split2(x[6], x[7], hi.w, lo.w);
+}
+
+// column sums over the 32 rows held by a warp: v[64] per lane -> lane l ends with the sums of columns 2l, 2l+1
+__device__ __forceinline__ void warp_colsum64(const float (&v)[64], int lane, float& c0, float& c1) {
+  float t32[32], t16[16], t8[8], t4[4], t2[2];
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float keep = b16 ? v[i + 32] : v[i], send = b16 ? v[i] : v[i + 32];
+    t32[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float keep = b8 ? t32[i + 16] : t32[i], send = b8 ? t32[i] : t32[i + 16];
+    t16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = b4 ? t16[i + 8] : t16[i], send = b4 ? t16[i] : t16[i + 8];
+    t8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = b2 ? t8[i + 4] : t8[i], send = b2 ? t8[i] : t8[i + 4];
+    t4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = b1 ? t4[i + 2] : t4[i], send = b1 ? t4[i] : t4[i + 2];
+    t2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  c0 = t2[0];
+  c1 = t2[1];
+}
+
+__global__ void __launch_bounds__(kFThreads, 1)
+    nv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                        const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, NvFusedArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  FSmemTail* tail = reinterpret_cast<FSmemTail*>(smem + kOffTail);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = int(gridDim.x);
+  const long long units = g.units;
+  const int u0 = int((long long)blockIdx.x * units / G), u1 = int((long long)(blockIdx.x + 1) * units / G);
+  const int S1 = g.C / 64;                             // pass-1 stages per tile (64 channels each)
+  const int NCG = g.C / 128;                           // channel groups (V accumulators)
+  auto pos_halves = [&](int j) { const int left = g.HW - j * kFM; return left >= kFM ? 2 : (left + 63) / 64; };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX1);
+    prefetch_tmap(&tmX2);
+    prefetch_tmap(&tmWh);
+    prefetch_tmap(&tmWl);
+    for (int s = 0; s < kLand; ++s) {
+      mbar_init(&tail->land_full[s], 1);
+      mbar_init(&tail->land_empty[s], 4);              // the four warps of the splitter group that consumed it
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tail->a_full[b], 4);
+      mbar_init(&tail->a_empty[b], 1);
+      mbar_init(&tail->w_full[b], 1);
+      mbar_init(&tail->w_empty[b], 1);
+      mbar_init(&tail->acc_full[b], 1);
+      mbar_init(&tail->acc_empty[b], 4);
+    }
+    mbar_init(&tail->norm_full, 8);
+    mbar_init(&tail->at_full, 4);
+    mbar_init(&tail->v_full, 1);
+    mbar_init(&tail->v_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tail->tmem_base, kFTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0 || warp == 3) {
+    // ===================== TMA producers: raw fp32 boxes of X (warp 0: even landing slots, warp 3: odd) ==========
+    if (lane == 0) {
+      const uint32_t mine = warp == 0 ? 0u : 1u;
+      uint32_t ls = 0;
+      // pass 1: one box [128 positions x 32 channels]; pass 2: four boxes [32 positions x 32 channels] (128 channels).
+      // Both land with the 128-byte swizzle: the splitters' reads then spread over all banks (see there).
+      auto load = [&](bool p2, int c0, int c1, int c2) {
+        if ((ls & 1u) != mine) { ++ls; return; }
+        const int slot = ls % kLand;
+        mbar_wait(&tail->land_empty[slot], ((ls / kLand) & 1) ^ 1);
+        mbar_arrive_expect_tx(&tail->land_full[slot], kLandBytes);
+        uint8_t* dst = smem + size_t(slot) * kLandBytes;
+        if (!p2) {
+          tma_load_3d(dst, &tmX1, &tail->land_full[slot], c0, c1, c2);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_3d(dst + i * 4096, &tmX2, &tail->land_full[slot], c0 + 32 * i, c1, c2);
+        }
+        NV_TRACE(0, ls);
+        ++ls;
+      };
+      for (int u = u0; u < u1; ++u) {
+        const int b = u / g.tpi, j = u - b * g.tpi, pos0 = j * kFM;
+        for (int kc = 0; kc < S1; ++kc) {              // [128 positions x 32 channels] x 2
+          load(false, kc * 64, pos0, b);
+          load(false, kc * 64 + 32, pos0, b);
+        }
+        const int nph = pos_halves(j);
+        for (int cg = 0; cg < NCG; ++cg)
+          for (int ph = 0; ph < nph; ++ph) {           // [32 positions x 128 channels] x 2
+            load(true, cg * 128, pos0 + 64 * ph, b);
+            load(true, cg * 128, pos0 + 64 * ph + 32, b);
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== TMA producer: pre-split W chunks =====================
+    if (lane == 0) {
+      uint32_t wg = 0;
+      // every CTA streams the same 128 KB of W once per tile: kWCopies replicas in global memory spread that over
+      // kWCopies times as many L2 lines (and slices)
+      const int wrow = 64 * int(blockIdx.x % kWCopies);
+      for (int u = u0; u < u1; ++u)
+        for (int kc = 0; kc < S1; ++kc, ++wg) {
+          const int slot = wg & 1;
+          mbar_wait(&tail->w_empty[slot], ((wg >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&tail->w_full[slot], kWBytes);
+          uint8_t* ws = smem + kOffW + size_t(slot) * kWBytes;
+          tma_load_2d(ws, &tmWh, &tail->w_full[slot], kc * 64, wrow);
+          tma_load_2d(ws + 8192, &tmWl, &tail->w_full[slot], kc * 64, wrow);
+        }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (A operand from tensor memory) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc(kFmtF16, kFM, 64);                  // B = W, K-major
+      constexpr uint32_t idesc2 = make_idesc(kFmtF16, kFM, 64) | (1u << 16);     // B = assignments, MN-major
+      uint32_t sg = 0, wg = 0, vdrains = 0;
+      bool v_fresh = true;
+      for (int u = u0; u < u1; ++u) {
+        const int b = u / g.tpi, j = u - b * g.tpi;
+        for (int kc = 0; kc < S1; ++kc, ++sg, ++wg) {
+          const uint32_t buf = wg & 1, as = sg & 1;
+          mbar_wait(&tail->acc_empty[buf], ((wg >> 1) & 1) ^ 1);
+          mbar_wait(&tail->a_full[as], (sg >> 1) & 1);
+          mbar_wait(&tail->w_full[buf], (wg >> 1) & 1);
+          tc_fence_after();
+          NV_TRACE(1, sg);
+          const uint32_t d_tmem = tmem_base + buf * 64;
+          const uint32_t ta = tmem_base + kFACol0 + as * 64;
+          const uint32_t wa = smem_u32(smem + kOffW + size_t(buf) * kWBytes);
+          const uint64_t db = smem_desc_sw128(wa), dbl = smem_desc_sw128(wa + 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                // 16 fp16: +8 TMEM columns (A), +32 bytes in the swizzle row (B)
+            mma_f16_ts(d_tmem, ta + 8 * k, db + 2 * k, idesc1, k != 0 ? 1u : 0u);
+            mma_f16_ts(d_tmem, ta + 8 * k, dbl + 2 * k, idesc1, 1u);
+            mma_f16_ts(d_tmem, ta + 32 + 8 * k, db + 2 * k, idesc1, 1u);
+          }
+          mma_commit(&tail->a_empty[as]);
+          mma_commit(&tail->w_empty[buf]);
+          mma_commit(&tail->acc_full[buf]);
+          NV_TRACE(2, sg);
+        }
+        if (v_fresh && vdrains > 0) {                  // the previous image's accumulators have been drained
+          mbar_wait(&tail->v_empty, (vdrains - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(&tail->at_full, uint32_t(u - u0) & 1);
+        tc_fence_after();
+        const int nph = pos_halves(j);
+        const uint32_t at = smem_u32(smem + kOffA);
+        for (int cg = 0; cg < NCG; ++cg)
+          for (int ph = 0; ph < nph; ++ph, ++sg) {
+            const uint32_t as = sg & 1;
+            mbar_wait(&tail->a_full[as], (sg >> 1) & 1);
+            tc_fence_after();
+            NV_TRACE(1, sg);
+            const uint32_t d_tmem = tmem_base + kFVCol0 + uint32_t(cg) * 64;
+            const uint32_t ta = tmem_base + kFACol0 + as * 64;
+            const bool first = v_fresh && ph == 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {              // 16 positions = two 8-row groups of the assignment tile = 2048 bytes
+              const uint64_t db = smem_desc_sw128_mn16(at + 8192 * ph + 2048 * k, 8192);
+              const uint64_t dbl = smem_desc_sw128_mn16(at + 16384 + 8192 * ph + 2048 * k, 8192);
+              mma_f16_ts(d_tmem, ta + 8 * k, db, idesc2, (first && k == 0) ? 0u : 1u);
+              mma_f16_ts(d_tmem, ta + 8 * k, dbl, idesc2, 1u);
+              mma_f16_ts(d_tmem, ta + 32 + 8 * k, db, idesc2, 1u);
+            }
+            mma_commit(&tail->a_empty[as]);
+            NV_TRACE(2, sg);
+          }
+        v_fresh = false;
+        if (u + 1 == u1 || (u + 1) / g.tpi != b) {     // last tile of this image in this CTA's range
+          mma_commit(&tail->v_full);
+          ++vdrains;
+          v_fresh = true;
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int lq = warp & 3;
+    const int row = lq * 32 + lane;
+    uint32_t wg = 0, vdr = 0;
+    float cs0 = 0.0f, cs1 = 0.0f;                      // running column sums of this warp's rows (image so far)
+    uint8_t* at = smem + kOffA;
+#pragma unroll 1
+    for (int u = u0; u < u1; ++u) {
+      const int b = u / g.tpi, j = u - b * g.tpi;
+      const int p = j * kFM + row;
+      const bool valid = p < g.HW;
+      float acc[64];
+#pragma unroll
+      for (int k = 0; k < 64; ++k) acc[k] = 0.0f;
+#pragma unroll 1
+      for (int kc = 0; kc < S1; ++kc, ++wg) {
+        const uint32_t buf = wg & 1;
+        mbar_wait(&tail->acc_full[buf], (wg >> 1) & 1);
+        tc_fence_after();
+        if (warp == 4 && lane == 0) NV_TRACE(3, wg);
+        const float us = tail->uns[wg & 3][row];
+        const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16) + buf * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) acc[c * 32 + k] = fmaf(__uint_as_float(v[k]), us, acc[c * 32 + k]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->acc_empty[buf]);
+        if (warp == 4 && lane == 0) NV_TRACE(4, wg);
+      }
+      mbar_wait(&tail->norm_full, uint32_t(u - u0) & 1);
+      const float iv = tail->inv[(u - u0) & 1][row];
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        acc[k] *= iv;
+        m = fmaxf(m, acc[k]);
+      }
+      float s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        acc[k] = expf(acc[k] - m);
+        s += acc[k];
+      }
+      const float rs = valid ? 1.0f / s : 0.0f;        // rows past the map contribute nothing
+#pragma unroll
+      for (int k = 0; k < 64; ++k) acc[k] *= rs;
+      // B operand of pass 2: a * 2^14 as fp16 hi / lo, MN-major rows of 128 bytes, chunk ^ (row & 7)
+#pragma unroll
+      for (int j8 = 0; j8 < 8; ++j8) {
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = acc[8 * j8 + e] * kScale14;
+        uint4 hi, lo;
+        split8(t, hi, lo);
+        const uint32_t off = uint32_t(row) * 128u + (uint32_t(j8 ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(at + off) = hi;
+        *reinterpret_cast<uint4*>(at + 16384 + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->at_full);
+      if (warp == 4 && lane == 0) NV_TRACE(7, u - u0);
+      if (valid) {
+        float* arow = g.a + (size_t(b) * g.HW + p) * 64;
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) st_v8(arow + 8 * k8, acc + 8 * k8);
+        g.inv[size_t(b) * g.HW + p] = iv;
+      }
+      {
+        float c0, c1;
+        warp_colsum64(acc, lane, c0, c1);
+        cs0 += c0;
+        cs1 += c1;
+      }
+      if (u + 1 == u1 || (u + 1) / g.tpi != b) {
+        // drain the V accumulators of image b into this CTA's slot
+        const int slot = int(blockIdx.x) - nv_cta_of_unit((long long)b * g.tpi, G, units);
+        mbar_wait(&tail->v_full, vdr & 1);
+        tc_fence_after();
+        float* vp = g.vpart + (size_t(b) * g.nslots + slot) * g.C * 64;
+        constexpr float kUn = 1.0f / (kScale14 * kScale14);
+        for (int cg = 0; cg < NCG; ++cg) {
+          float* vrow = vp + size_t(cg * 128 + row) * 64;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(lq * 32) << 16) + kFVCol0 + uint32_t(cg) * 64 + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              float t[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) t[e] = __uint_as_float(v[8 * k8 + e]) * kUn;
+              st_v8(vrow + c * 32 + 8 * k8, t);
+            }
+          }
+        }
+        float* as = g.aspart + ((size_t(b) * g.nslots + slot) * 4 + lq) * 64;
+        *reinterpret_cast<float2*>(as + 2 * lane) = make_float2(cs0, cs1);
+        cs0 = cs1 = 0.0f;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->v_empty);
+        ++vdr;
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== splitters: landed fp32 -> fp16 hi / lo A operand in TENSOR MEMORY =====================
+    // Two groups of four warps; group grp converts the stages with (stage & 1) == grp into A slot grp.  A thread owns one
+    // TMEM lane = one row of the operand: a position in pass 1, a channel in pass 2.  Writing the operand with tcgen05.st
+    // keeps it out of shared memory altogether: the tensor core then reads only the small B operand (W / assignments)
+    // from shared memory, and the shared-memory pipe -- the unit this kernel is bound by -- carries the landed fp32 tile
+    // once in (TMA) and once out (these loads), not five times.
+    const int grp = (warp - 8) >> 2;
+    const int lq = warp & 3;
+    const int row = lq * 32 + lane;
+    const float wun = __ldg(g.wun);
+    const uint32_t tA = tmem_base + (uint32_t(lq * 32) << 16) + kFACol0 + uint32_t(grp) * 64;
+    uint32_t sg = 0, wg = 0;
+    auto wait_stage = [&](int& l0, int& l1) {
+      const uint32_t ls = 2 * sg;
+      l0 = ls % kLand;
+      l1 = (ls + 1) % kLand;
+      mbar_wait(&tail->land_full[l0], (ls / kLand) & 1);
+      mbar_wait(&tail->land_full[l1], ((ls + 1) / kLand) & 1);
+      mbar_wait(&tail->a_empty[grp], ((sg >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lq == 0 && lane == 0) NV_TRACE(5, sg);
+    };
+    auto done_stage = [&](int l0, int l1) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tail->land_empty[l0]);
+        mbar_arrive(&tail->land_empty[l1]);
+        mbar_arrive(&tail->a_full[grp]);
+      }
+      if (lq == 0 && lane == 0) NV_TRACE(6, sg);
+    };
+#pragma unroll 1
+    for (int u = u0; u < u1; ++u) {
+      const int j = u % g.tpi;
+      const int par = (u - u0) & 1;
+      float ssq = 0.0f;
+      // ---- pass 1: this thread's position, 64 channels = the row's eight 16-byte chunks in each of the two boxes.
+      // Chunk c of row r sits at c ^ (r & 7): the eight consecutive rows of a quarter-warp read eight different chunk
+      // positions, i.e. all 32 banks, with every LDS.128 ----
+#pragma unroll 1
+      for (int kc = 0; kc < S1; ++kc, ++sg, ++wg) {
+        if ((sg & 1u) != uint32_t(grp)) continue;
+        int l0, l1;
+        wait_stage(l0, l1);
+        const uint8_t* r0 = smem + size_t(l0) * kLandBytes + row * 128;
+        const uint8_t* r1 = smem + size_t(l1) * kLandBytes + row * 128;
+        const int sw = row & 7;
+        float x[64];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v0 = *reinterpret_cast<const float4*>(r0 + ((c ^ sw) << 4));
+          const float4 v1 = *reinterpret_cast<const float4*>(r1 + ((c ^ sw) << 4));
+          x[4 * c] = v0.x; x[4 * c + 1] = v0.y; x[4 * c + 2] = v0.z; x[4 * c + 3] = v0.w;
+          x[32 + 4 * c] = v1.x; x[32 + 4 * c + 1] = v1.y; x[32 + 4 * c + 2] = v1.z; x[32 + 4 * c + 3] = v1.w;
+        }
+        float mx = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) {
+          mx = fmaxf(mx, fabsf(x[e]));
+          ssq = fmaf(x[e], x[e], ssq);
+        }
+        // power-of-two scale putting the row's maximum in [2^14, 2^15); rows below 2^-100 are numerically zero
+        const uint32_t mb = __float_as_uint(fmaxf(mx, 7.8886090522101181e-31f)) & 0x7f800000u;
+        const float sc = __uint_as_float((268u << 23) - mb);
+        tail->uns[wg & 3][row] = __uint_as_float(mb - (14u << 23)) * wun;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {                 // 16 channels = 8 TMEM columns of hi and 8 of lo
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split2(x[16 * qd + 2 * e] * sc, x[16 * qd + 2 * e + 1] * sc, hi[e], lo[e]);
+          tmem_st_32x8(tA + 8 * qd, hi);
+          tmem_st_32x8(tA + 32 + 8 * qd, lo);
+        }
+        done_stage(l0, l1);
+      }
+      tail->ssqp[grp][row] = ssq;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (grp == 0) tail->inv[par][row] = rsqrtf(fmaxf(tail->ssqp[0][row] + tail->ssqp[1][row], 1e-12f));   // nets.py:66
+      asm volatile("bar.sync 2, 256;" ::: "memory");   // every splitter sees every row's 1/|x|; ssqp may be rewritten
+      if (lane == 0) mbar_arrive(&tail->norm_full);
+      // ---- pass 2: this thread's channel (box lq, float `lane` of the 128-byte row), 64 positions; a warp reads one
+      // whole row per LDS.32 ----
+      const int nph = pos_halves(j);
+      const int n2 = NCG * nph;
+#pragma unroll 1
+      for (int s2 = 0; s2 < n2; ++s2, ++sg) {
+        if ((sg & 1u) != uint32_t(grp)) continue;
+        const int ph = s2 % nph;
+        int l0, l1;
+        wait_stage(l0, l1);
+        const float* ivp = &tail->inv[par][64 * ph];
+#pragma unroll
+        for (int p16 = 0; p16 < 4; ++p16) {
+          const uint8_t* base = smem + size_t(p16 < 2 ? l0 : l1) * kLandBytes + lq * 4096 + (lane & 3) * 4;
+          float xv[16];
+#pragma unroll
+          for (int pp = 0; pp < 16; ++pp) {
+            const int ri = (16 * p16 + pp) & 31;           // row inside the 32-position box
+            xv[pp] = *reinterpret_cast<const float*>(base + ri * 128 + (((lane >> 2) ^ (ri & 7)) << 4));
+          }
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 iv4 = *reinterpret_cast<const float4*>(ivp + 16 * p16 + 4 * q4);
+            split2(xv[4 * q4] * (iv4.x * kScale14), xv[4 * q4 + 1] * (iv4.y * kScale14), hi[2 * q4], lo[2 * q4]);
+            split2(xv[4 * q4 + 2] * (iv4.z * kScale14), xv[4 * q4 + 3] * (iv4.w * kScale14), hi[2 * q4 + 1], lo[2 * q4 + 1]);
+          }
+          tmem_st_32x8(tA + 8 * p16, hi);
+          tmem_st_32x8(tA + 32 + 8 * p16, lo);
+        }
+        done_stage(l0, l1);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kFTmemCols);
+  }
+}
+
+// W [C,64] fp32 -> W^T as fp16 hi / lo [64, C] (K-major rows for the B operand of pass 1) with one power-of-two scale.
+// One CTA per cluster (row of W^T); every CTA finds the global maximum itself (128 KB, L2-resident): no second launch.
+__global__ void __launch_bounds__(256) nv_wprep_kernel(const float* __restrict__ w, int C, __half* __restrict__ wt_hi,
+                                                       __half* __restrict__ wt_lo, float* __restrict__ wun) {
+  __shared__ float s_mx[8];
+  float mx = 0.0f;
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  for (int i = threadIdx.x; i < C * 16; i += blockDim.x) {
+    const float4 v = __ldg(w4 + i);
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.0f;
+  for (int i = 0; i < 8; ++i) mx = fmaxf(mx, s_mx[i]);
+  const uint32_t mb = __float_as_uint(fmaxf(mx, 7.8886090522101181e-31f)) & 0x7f800000u;
+  const float sc = __uint_as_float((267u << 23) - mb);          // max |w| -> [2^13, 2^14)
+  const int k = blockIdx.x;
+  if (k == 0 && blockIdx.y == 0 && threadIdx.x == 0) *wun = __uint_as_float(mb - (13u << 23));
+  const size_t copy = size_t(blockIdx.y) * 64 * C;                 // replica blockIdx.y
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float xs = __ldg(w + size_t(c) * 64 + k) * sc;
+    const __half h = __float2half_rn(xs);
+    wt_hi[copy + size_t(k) * C + c] = h;
+    wt_lo[copy + size_t(k) * C + c] = __float2half_rn(xs - __half2float(h));
+  }
+}
+
+// Tail, one CTA per image: V = sum of the partials + Cc * colsum(a); intra-normalisation per cluster; flatten (index
+// c*64 + k); l2-normalisation.  Few registers on purpose (every image's CTA is resident at once); the second pass re-reads
+// the V this CTA has just written (L2).
+__global__ void __launch_bounds__(256, 4) nv_fused_tail_kernel(const float* __restrict__ vpart, const float* __restrict__ aspart,
+                                                               const float* __restrict__ centers, int C, int tpi, int units,
+                                                               int G, int nslots, float* __restrict__ V,
+                                                               float* __restrict__ asum, float* __restrict__ nk,
+                                                               float* __restrict__ nt, float* __restrict__ out) {
+  __shared__ float s_as[64];
+  __shared__ float s_col[16][64];
+  __shared__ float s_ink[64];
+  __shared__ float s_tot[2];
+  __shared__ float s_nt;
+  const int b = blockIdx.x;
+  const int first = nv_cta_of_unit((long long)b * tpi, G, units);
+  const int ns = nv_cta_of_unit((long long)b * tpi + tpi - 1, G, units) - first + 1;
+  const int k4 = (threadIdx.x & 15) * 4, grp = threadIdx.x >> 4;      // 16 row groups x 16 column quads
+  if (threadIdx.x < 64) {
+    float acc = 0.0f;
+    for (int s = 0; s < ns; ++s)
+      for (int w = 0; w < 4; ++w) acc += aspart[((size_t(b) * nslots + s) * 4 + w) * 64 + threadIdx.x];
+    s_as[threadIdx.x] = acc;
+    asum[b * 64 + threadIdx.x] = acc;
+  }
+  __syncthreads();
+  const float4 as4 = *reinterpret_cast<const float4*>(s_as + k4);
+  float4 ss = make_float4(0.f, 0.f, 0.f, 0.f);
+  float* Vb = V + size_t(b) * C * 64;
+#pragma unroll 4
+  for (int c = grp; c < C; c += 16) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < ns; ++s) {
+      const float4 t = ldg_stream(reinterpret_cast<const float4*>(vpart + ((size_t(b) * nslots + s) * C + c) * 64 + k4));
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    const float4 cc = __ldg(reinterpret_cast<const float4*>(centers + size_t(c) * 64 + k4));
+    a.x = fmaf(cc.x, as4.x, a.x); a.y = fmaf(cc.y, as4.y, a.y); a.z = fmaf(cc.z, as4.z, a.z); a.w = fmaf(cc.w, as4.w, a.w);
+    ss.x = fmaf(a.x, a.x, ss.x); ss.y = fmaf(a.y, a.y, ss.y); ss.z = fmaf(a.z, a.z, ss.z); ss.w = fmaf(a.w, a.w, ss.w);
+    *reinterpret_cast<float4*>(Vb + size_t(c) * 64 + k4) = a;
+  }
+  *reinterpret_cast<float4*>(&s_col[grp][k4]) = ss;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc += s_col[r][threadIdx.x];
+    const float n = sqrtf(acc + 1e-12f);
+    nk[b * 64 + threadIdx.x] = n;
+    s_ink[threadIdx.x] = 1.0f / n;
+    // |V / nk|^2 summed over the channels of this cluster
+    float tot = acc * (1.0f / n) * (1.0f / n);
+    tot = warp_sum(tot);
+    if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = tot;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float n_t = sqrtf(s_tot[0] + s_tot[1] + 1e-12f);
+    nt[b] = n_t;
+    s_nt = n_t;
+  }
+  __syncthreads();
+  const float int_ = 1.0f / s_nt;
+  float4 ik = *reinterpret_cast<const float4*>(s_ink + k4);
+  ik.x *= int_; ik.y *= int_; ik.z *= int_; ik.w *= int_;
+  float* ob = out + size_t(b) * C * 64;
+#pragma unroll 4
+  for (int c = grp; c < C; c += 16) {
+    const float4 a = *reinterpret_cast<const float4*>(Vb + size_t(c) * 64 + k4);     // written by this thread above
+    stg_stream(reinterpret_cast<float4*>(ob + size_t(c) * 64 + k4), make_float4(a.x * ik.x, a.y * ik.y, a.z * ik.z, a.w * ik.w));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int kFMaxCtas = 160;
+
+static int nv_fused_slots(int B, int tpi) {
+  const long long units = (long long)B * tpi;
+  const long long Gm = units < kFMaxCtas ? units : kFMaxCtas;
+  const long long per = units / Gm;                                   // >= 1
+  long long n = (tpi + per - 1) / per + 1;
+  if (n > tpi) n = tpi;
+  return int(n);
+}
+
+bool nv_fused_ok(int B, int HW, int C, int K) {
+  if (knob_or(KNOB_NV_FUSED, 1) == 0) return false;
+  if (K != 64 || C < 128 || C > 512 || (C % 128) != 0 || B < 1 || HW < 1) return false;
+  if ((long long)B * ((HW + kFM - 1) / kFM) > 0x7fffffffLL / kFMaxCtas) return false;
+  return true;
+}
+
+size_t nv_fused_ws_bytes(int B, int HW, int C, int K) {
+  (void)K;
+  const int tpi = (HW + kFM - 1) / kFM;
+  const int ns = nv_fused_slots(B, tpi);
+  return 2 * carve_bytes(size_t(kWCopies) * 64 * C, 2) + carve_bytes(1, 4) + carve_bytes(size_t(B) * ns * C * 64, 4) +
+         carve_bytes(size_t(B) * ns * 4 * 64, 4);
+}
+
+int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, int B, int HW, int C, float* inv, float* a,
+                 float* V, float* asum, float* nk, float* nt, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (ws_bytes < nv_fused_ws_bytes(B, HW, C, 64)) return SCL_ERR_WORKSPACE;
+  const int tpi = (HW + kFM - 1) / kFM;
+  const long long units = (long long)B * tpi;
+  const int G = int(units < num_sms() ? units : num_sms());
+  if (G > kFMaxCtas) return SCL_ERR_UNSUPPORTED;
+  Carver c(ws, ws_bytes);
+  NvFusedArgs g;
+  g.B = B; g.HW = HW; g.C = C; g.tpi = tpi; g.units = int(units); g.nslots = nv_fused_slots(B, tpi);
+  g.x = x; g.inv = inv; g.a = a;
+  { const char* e = getenv("SCL_NV_DBG"); g.dbg = e ? atoi(e) : 0; }
+  g.trace = nullptr;
+  static long long* s_trace = nullptr;
+  if (g.dbg & 1024) {
+    if (!s_trace) { cudaMalloc(&s_trace, 8 * 4096 * sizeof(long long)); }
+    cudaMemsetAsync(s_trace, 0, 8 * 4096 * sizeof(long long), stream);
+    g.trace = s_trace;
+  }
+  __half* wt_hi = c.take<__half>(size_t(kWCopies) * 64 * C);
+  __half* wt_lo = c.take<__half>(size_t(kWCopies) * 64 * C);
+  float* wun = c.take<float>(1);
+  g.wun = wun;
+  g.vpart = c.take<float>(size_t(B) * g.nslots * C * 64);
+  g.aspart = c.take<float>(size_t(B) * g.nslots * 4 * 64);
+  nv_wprep_kernel<<<dim3(64, kWCopies), 256, 0, stream>>>(assign_w, C, wt_hi, wt_lo, wun);
+  SCL_LAUNCH_CHECK();
+  CUtensorMap tmX1, tmX2, tmWh, tmWl;
+  int rc;
+  const uint64_t pitchX = uint64_t(C) * 4, batchX = uint64_t(HW) * C * 4;
+  if ((rc = make_tmap_3d(&tmX1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, uint64_t(C), uint64_t(HW), uint64_t(B), pitchX, batchX, 32, kFM, 0))) return rc;
+  if ((rc = make_tmap_3d(&tmX2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, uint64_t(C), uint64_t(HW), uint64_t(B), pitchX, batchX, 32, 32, 0))) return rc;
+  if ((rc = make_tmap_2d(&tmWh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wt_hi, uint64_t(C), 64 * kWCopies, uint64_t(C) * 2, 64, 64))) return rc;
+  if ((rc = make_tmap_2d(&tmWl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wt_lo, uint64_t(C), 64 * kWCopies, uint64_t(C) * 2, 64, 64))) return rc;
+  const size_t smem = 1024 + size_t(kOffTail) + sizeof(FSmemTail);
+  static SmemAttrCache configured;
+  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(nv_fused_fwd_kernel), smem, &configured))) return rc;
+  nv_fused_fwd_kernel<<<G, kFThreads, smem, stream>>>(tmX1, tmX2, tmWh, tmWl, g);
+  SCL_LAUNCH_CHECK();
+  nv_fused_tail_kernel<<<B, 256, 0, stream>>>(g.vpart, g.aspart, centers, C, tpi, int(units), G, g.nslots, V, asum, nk, nt, out);
+  SCL_LAUNCH_CHECK();
+  if (g.trace) {
+    static long long h[8 * 4096];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost);
+    FILE* f = fopen("gpurun_out/nv_trace.txt", "w");
+    if (f) { for (int r = 0; r < 8; ++r) for (int i = 0; i < 4096; ++i) if (h[r * 4096 + i]) fprintf(f, "%d %d %lld\n", r, i, h[r * 4096 + i]); fclose(f); }
+  }
+  return SCL_OK;
+}
+
+}  // namespace scl

@@ -19,6 +19,8 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// generic-proxy writes (any state space) -> visible to later async-proxy (TMA) reads
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -40,14 +42,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef SCL_MBAR_TIMEOUT_CYCLES
 #define SCL_MBAR_TIMEOUT_CYCLES 8000000000ll   // ~4 s at 2 GHz
 #endif
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+// re-issuing the poll every ~60 cycles -- idle roles of a warp-specialised kernel then cost the busy ones no issue slots.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > SCL_MBAR_TIMEOUT_CYCLES) {
-      printf("scl: mbarrier timeout block %d thread %d bar %u parity %u\n", int(blockIdx.x), int(threadIdx.x),
-             smem_u32(bar), parity);
-      __trap();
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if ((++spins & 63u) == 0) {                      // look at the clock once in a while only
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > SCL_MBAR_TIMEOUT_CYCLES) {
+        printf("scl: mbarrier timeout block %d thread %d bar %u parity %u\n", int(blockIdx.x), int(threadIdx.x),
+               smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }
@@ -72,6 +92,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// L2 prefetch of a 3-D tiled box (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 
 // ------------------------------- tcgen05 -------------------------------
@@ -105,6 +132,24 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the M x K operand comes from tensor memory (lane = row m, 32-bit column = two
+// consecutive K elements for 16-bit types), written there with tcgen05.st by the thread that owns the row.
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns, registers -> TMEM: thread i of the warp writes TMEM lane (base lane + i)
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -192,6 +237,28 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
          (uint64_t(2) << 61);
 }
+// MN-major 32-bit operand tile.  tcgen05 accepts exactly one layout for it: 128-byte swizzle with 32-byte atomicity
+// (descriptor layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), atoms of 4 k-rows x 128 bytes.  One TMA box is
+// 32 MN-elements (128 bytes) x 32 k-rows = 4 KB:
+//   leading byte offset = distance between MN groups (next box, 4096), stride byte offset = between 4-k-row atoms (512)
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(4096 >> 4) << 16) | (uint64_t(512 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
+
+// Round to nearest tf32 (10-bit mantissa), result as fp32 bits.  cvt.rna.tf32.f32 has no native SASS form on sm_100 (it
+// expands to five instructions with an Inf/NaN guard); the integer form below is two, and the splitter warps are on the
+// critical path of the 3xTF32 mode.  Ties round away from zero like .rna; Inf stays Inf, NaN stays NaN.
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+// MN-major 16-bit operand tile, plain 128-byte swizzle (layout type 2): blocks of 64 MN-elements (128 bytes) x K rows,
+// row pitch 128 bytes, 16-byte chunks XOR-swizzled with (row & 7); canonical form ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units: leading byte offset = distance between 64-element MN blocks, stride byte offset = 1024 (8 K rows).
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn16(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+
 // Instruction descriptor (upper 32 bits of the idesc operand):
 //   [4,6) D format (1 = F32)  [7,10) A format  [10,13) B format (kind::f16: 0 = F16, 1 = BF16; kind::tf32: 2 = TF32)
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3   [24,29) M >> 4
@@ -203,7 +270,8 @@ constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1, kFmtTF32 = 2;
 }  // namespace tc
 
 // Host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
-// swizzle_atom32 = 0: SWIZZLE_128B; 1: SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands)
+// swizzle_atom32 = 0: SWIZZLE_128B; 1: SWIZZLE_128B_ATOM_32B (the only layout tcgen05 accepts for MN-major 32-bit operands);
+// 2 (rank-3 only): no swizzle (boxes that are re-laid-out by threads, not read by the tensor core)
 int make_tmap_2d(CUtensorMap* out, CUtensorMapDataType dtype, size_t elem_bytes, const void* base, uint64_t inner,
                  uint64_t outer, uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_atom32 = 0);
 // rank-3 variant: dims {inner, outer, batch}, strides {row_pitch_bytes, batch_pitch_bytes}, box {box_inner, box_outer, 1}

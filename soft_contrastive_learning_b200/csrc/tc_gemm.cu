@@ -50,20 +50,6 @@ struct GSmemTail {
   uint32_t tmem_base;
 };
 
-// MN-major 32-bit operand tile.  tcgen05 accepts exactly one layout for it: 128-byte swizzle with 32-byte atomicity
-// (descriptor layout type 1, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), atoms of 4 k-rows x 128 bytes.  One TMA box is
-// 32 MN-elements (128 bytes) x 32 k-rows = 4 KB:
-//   leading byte offset = distance between MN groups (next box, 4096), stride byte offset = between 4-k-row atoms (512)
-__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t smem_addr) {
-  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(4096 >> 4) << 16) | (uint64_t(512 >> 4) << 32) |
-         (uint64_t(1) << 46) | (uint64_t(1) << 61);
-}
-
-// Round to nearest tf32 (10-bit mantissa), result as fp32 bits.  cvt.rna.tf32.f32 has no native SASS form on sm_100 (it
-// expands to five instructions with an Inf/NaN guard); the integer form below is two, and the splitter warps are on the
-// critical path of the 3xTF32 mode.  Ties round away from zero like .rna; Inf stays Inf, NaN stays NaN.
-__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
-
 template <int BN, bool kX3, bool kAMn, bool kBMn>
 __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
