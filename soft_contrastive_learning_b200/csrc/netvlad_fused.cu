@@ -53,17 +53,18 @@ constexpr uint32_t kOffTail = kOffA + 32768;           // 208 KB
 constexpr int kFThreads = 512;
 constexpr uint32_t kFTmemCols = 512;
 constexpr uint32_t kFVCol0 = 128;                      // V accumulators: columns [128, 384)
-constexpr uint32_t kFACol0 = 384;                      // A-operand slots: [384, 448), [448, 512): hi (32 columns) | lo (32)
+constexpr uint32_t kFACol0 = 384;                      // four A-operand slots of 32 columns: hi (16 columns) | lo (16)
+constexpr int kASlots = 4;
 constexpr float kScale14 = 16384.0f;
 constexpr int kWCopies = 16;                           // replicas of the pre-split W (L2 hot-spot relief)
 
 struct FSmemTail {
-  uint64_t land_full[kLand], land_empty[kLand], a_full[2], a_empty[2], w_full[2], w_empty[2], acc_full[2], acc_empty[2];
+  uint64_t land_full[kLand], land_empty[kLand], a_full[kASlots], a_empty[kASlots], w_full[2], w_empty[2], acc_full[2], acc_empty[2];
   uint64_t norm_full, at_full, v_full, v_empty;
   uint32_t tmem_base;
   alignas(16) float ssqp[2][kFM];                      // row sums of squares, one partial per splitter group
   alignas(16) float inv[2][kFM];                       // 1 / |x| of the tile's rows (double-buffered by tile parity)
-  alignas(16) float uns[4][kFM];                       // per-row inverse scale of the last four pass-1 stages
+  alignas(16) float uns[4][kFM];                       // per-row inverse scale of the last four pass-1 stage pairs
 };
 
 struct NvFusedArgs {
@@ -147,9 +148,9 @@ __global__ void __launch_bounds__(kFThreads, 1)
   const int G = int(gridDim.x);
   const long long units = g.units;
   const int u0 = int((long long)blockIdx.x * units / G), u1 = int((long long)(blockIdx.x + 1) * units / G);
-  const int S1 = g.C / 64;                             // pass-1 stages per tile (64 channels each)
+  const int S1 = g.C / 32;                             // pass-1 stages per tile (32 channels each)
   const int NCG = g.C / 128;                           // channel groups (V accumulators)
-  auto pos_halves = [&](int j) { const int left = g.HW - j * kFM; return left >= kFM ? 2 : (left + 63) / 64; };
+  auto pos_chunks = [&](int j) { const int left = g.HW - j * kFM; return left >= kFM ? 4 : (left + 31) / 32; };   // pass-2 stages per channel group
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX1);
@@ -158,11 +159,13 @@ __global__ void __launch_bounds__(kFThreads, 1)
     prefetch_tmap(&tmWl);
     for (int s = 0; s < kLand; ++s) {
       mbar_init(&tail->land_full[s], 1);
-      mbar_init(&tail->land_empty[s], 4);              // the four warps of the splitter group that consumed it
+      mbar_init(&tail->land_empty[s], 8);              // both splitter groups (the partner reads it for the row maximum)
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kASlots; ++b) {
       mbar_init(&tail->a_full[b], 4);
       mbar_init(&tail->a_empty[b], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
       mbar_init(&tail->w_full[b], 1);
       mbar_init(&tail->w_empty[b], 1);
       mbar_init(&tail->acc_full[b], 1);
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
 
   if (warp == 0 || warp == 3) {
     // ===================== TMA producers: raw fp32 boxes of X (warp 0: even landing slots, warp 3: odd) ==========
-    if (lane == 0) {
+    {
       const uint32_t mine = warp == 0 ? 0u : 1u;
       uint32_t ls = 0;
       // pass 1: one box [128 positions x 32 channels]; pass 2: four boxes [32 positions x 32 channels] (128 channels).
@@ -191,51 +194,51 @@ __global__ void __launch_bounds__(kFThreads, 1)
         if ((ls & 1u) != mine) { ++ls; return; }
         const int slot = ls % kLand;
         mbar_wait(&tail->land_empty[slot], ((ls / kLand) & 1) ^ 1);
-        mbar_arrive_expect_tx(&tail->land_full[slot], kLandBytes);
         uint8_t* dst = smem + size_t(slot) * kLandBytes;
-        if (!p2) {
-          tma_load_3d(dst, &tmX1, &tail->land_full[slot], c0, c1, c2);
-        } else {
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&tail->land_full[slot], kLandBytes);
+          if (!p2) {
+            tma_load_3d(dst, &tmX1, &tail->land_full[slot], c0, c1, c2);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) tma_load_3d(dst + i * 4096, &tmX2, &tail->land_full[slot], c0 + 32 * i, c1, c2);
+            for (int i = 0; i < 4; ++i) tma_load_3d(dst + i * 4096, &tmX2, &tail->land_full[slot], c0 + 32 * i, c1, c2);
+          }
+          NV_TRACE(0, ls);
         }
-        NV_TRACE(0, ls);
+        __syncwarp();
         ++ls;
       };
       for (int u = u0; u < u1; ++u) {
         const int b = u / g.tpi, j = u - b * g.tpi, pos0 = j * kFM;
-        for (int kc = 0; kc < S1; ++kc) {              // [128 positions x 32 channels] x 2
-          load(false, kc * 64, pos0, b);
-          load(false, kc * 64 + 32, pos0, b);
-        }
-        const int nph = pos_halves(j);
+        for (int kc = 0; kc < S1; ++kc) load(false, kc * 32, pos0, b);               // [128 positions x 32 channels]
+        const int npc = pos_chunks(j);
         for (int cg = 0; cg < NCG; ++cg)
-          for (int ph = 0; ph < nph; ++ph) {           // [32 positions x 128 channels] x 2
-            load(true, cg * 128, pos0 + 64 * ph, b);
-            load(true, cg * 128, pos0 + 64 * ph + 32, b);
-          }
+          for (int pc = 0; pc < npc; ++pc) load(true, cg * 128, pos0 + 32 * pc, b);  // [32 positions x 128 channels]
       }
     }
   } else if (warp == 2) {
     // ===================== TMA producer: pre-split W chunks =====================
-    if (lane == 0) {
+    {
       uint32_t wg = 0;
       // every CTA streams the same 128 KB of W once per tile: kWCopies replicas in global memory spread that over
       // kWCopies times as many L2 lines (and slices)
       const int wrow = 64 * int(blockIdx.x % kWCopies);
       for (int u = u0; u < u1; ++u)
-        for (int kc = 0; kc < S1; ++kc, ++wg) {
+        for (int kc = 0; kc < S1 / 2; ++kc, ++wg) {    // a W chunk covers 64 channels = two stages
           const int slot = wg & 1;
           mbar_wait(&tail->w_empty[slot], ((wg >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&tail->w_full[slot], kWBytes);
           uint8_t* ws = smem + kOffW + size_t(slot) * kWBytes;
-          tma_load_2d(ws, &tmWh, &tail->w_full[slot], kc * 64, wrow);
-          tma_load_2d(ws + 8192, &tmWl, &tail->w_full[slot], kc * 64, wrow);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&tail->w_full[slot], kWBytes);
+            tma_load_2d(ws, &tmWh, &tail->w_full[slot], kc * 64, wrow);
+            tma_load_2d(ws + 8192, &tmWl, &tail->w_full[slot], kc * 64, wrow);
+          }
+          __syncwarp();
         }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (A operand from tensor memory) =====================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc1 = make_idesc(kFmtF16, kFM, 64);                  // B = W, K-major
       constexpr uint32_t idesc2 = make_idesc(kFmtF16, kFM, 64) | (1u << 16);     // B = assignments, MN-major
       uint32_t sg = 0, wg = 0, vdrains = 0;
@@ -243,26 +246,35 @@ __global__ void __launch_bounds__(kFThreads, 1)
       for (int u = u0; u < u1; ++u) {
         const int b = u / g.tpi, j = u - b * g.tpi;
         for (int kc = 0; kc < S1; ++kc, ++sg, ++wg) {
-          const uint32_t buf = wg & 1, as = sg & 1;
-          mbar_wait(&tail->acc_empty[buf], ((wg >> 1) & 1) ^ 1);
-          mbar_wait(&tail->a_full[as], (sg >> 1) & 1);
-          mbar_wait(&tail->w_full[buf], (wg >> 1) & 1);
+          // two stages (64 channels) share one logits accumulator, one W chunk and one per-row scale
+          const uint32_t pg = wg >> 1, odd = wg & 1;
+          const uint32_t buf = pg & 1, as = sg & 3;
+          if (!odd) {
+            mbar_wait(&tail->acc_empty[buf], ((pg >> 1) & 1) ^ 1);
+            mbar_wait(&tail->w_full[buf], (pg >> 1) & 1);
+          }
+          mbar_wait(&tail->a_full[as], (sg >> 2) & 1);
           tc_fence_after();
           NV_TRACE(1, sg);
           const uint32_t d_tmem = tmem_base + buf * 64;
-          const uint32_t ta = tmem_base + kFACol0 + as * 64;
-          const uint32_t wa = smem_u32(smem + kOffW + size_t(buf) * kWBytes);
+          const uint32_t ta = tmem_base + kFACol0 + as * 32;
+          const uint32_t wa = smem_u32(smem + kOffW + size_t(buf) * kWBytes) + odd * 64;   // second half of the 128-byte rows
           const uint64_t db = smem_desc_sw128(wa), dbl = smem_desc_sw128(wa + 8192);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {                // 16 fp16: +8 TMEM columns (A), +32 bytes in the swizzle row (B)
-            mma_f16_ts(d_tmem, ta + 8 * k, db + 2 * k, idesc1, k != 0 ? 1u : 0u);
-            mma_f16_ts(d_tmem, ta + 8 * k, dbl + 2 * k, idesc1, 1u);
-            mma_f16_ts(d_tmem, ta + 32 + 8 * k, db + 2 * k, idesc1, 1u);
+            for (int k = 0; k < 2; ++k) {              // 16 fp16: +8 TMEM columns (A), +32 bytes in the swizzle row (B)
+              mma_f16_ts(d_tmem, ta + 8 * k, db + 2 * k, idesc1, (odd | uint32_t(k)) != 0 ? 1u : 0u);
+              mma_f16_ts(d_tmem, ta + 8 * k, dbl + 2 * k, idesc1, 1u);
+              mma_f16_ts(d_tmem, ta + 16 + 8 * k, db + 2 * k, idesc1, 1u);
+            }
+            mma_commit(&tail->a_empty[as]);
+            if (odd) {
+              mma_commit(&tail->w_empty[buf]);
+              mma_commit(&tail->acc_full[buf]);
+            }
+            NV_TRACE(2, sg);
           }
-          mma_commit(&tail->a_empty[as]);
-          mma_commit(&tail->w_empty[buf]);
-          mma_commit(&tail->acc_full[buf]);
-          NV_TRACE(2, sg);
+          __syncwarp();
         }
         if (v_fresh && vdrains > 0) {                  // the previous image's accumulators have been drained
           mbar_wait(&tail->v_empty, (vdrains - 1) & 1);
@@ -270,31 +282,35 @@ __global__ void __launch_bounds__(kFThreads, 1)
         }
         mbar_wait(&tail->at_full, uint32_t(u - u0) & 1);
         tc_fence_after();
-        const int nph = pos_halves(j);
+        const int npc = pos_chunks(j);
         const uint32_t at = smem_u32(smem + kOffA);
         for (int cg = 0; cg < NCG; ++cg)
-          for (int ph = 0; ph < nph; ++ph, ++sg) {
-            const uint32_t as = sg & 1;
-            mbar_wait(&tail->a_full[as], (sg >> 1) & 1);
+          for (int pc = 0; pc < npc; ++pc, ++sg) {
+            const uint32_t as = sg & 3;
+            mbar_wait(&tail->a_full[as], (sg >> 2) & 1);
             tc_fence_after();
             NV_TRACE(1, sg);
             const uint32_t d_tmem = tmem_base + kFVCol0 + uint32_t(cg) * 64;
-            const uint32_t ta = tmem_base + kFACol0 + as * 64;
-            const bool first = v_fresh && ph == 0;
+            const uint32_t ta = tmem_base + kFACol0 + as * 32;
+            const bool first = v_fresh && pc == 0;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {              // 16 positions = two 8-row groups of the assignment tile = 2048 bytes
-              const uint64_t db = smem_desc_sw128_mn16(at + 8192 * ph + 2048 * k, 8192);
-              const uint64_t dbl = smem_desc_sw128_mn16(at + 16384 + 8192 * ph + 2048 * k, 8192);
-              mma_f16_ts(d_tmem, ta + 8 * k, db, idesc2, (first && k == 0) ? 0u : 1u);
-              mma_f16_ts(d_tmem, ta + 8 * k, dbl, idesc2, 1u);
-              mma_f16_ts(d_tmem, ta + 32 + 8 * k, db, idesc2, 1u);
+              for (int k = 0; k < 2; ++k) {            // 16 positions = two 8-row groups of the assignment tile = 2048 bytes
+                const uint64_t db = smem_desc_sw128_mn16(at + 4096 * pc + 2048 * k, 8192);
+                const uint64_t dbl = smem_desc_sw128_mn16(at + 16384 + 4096 * pc + 2048 * k, 8192);
+                mma_f16_ts(d_tmem, ta + 8 * k, db, idesc2, (first && k == 0) ? 0u : 1u);
+                mma_f16_ts(d_tmem, ta + 8 * k, dbl, idesc2, 1u);
+                mma_f16_ts(d_tmem, ta + 16 + 8 * k, db, idesc2, 1u);
+              }
+              mma_commit(&tail->a_empty[as]);
+              NV_TRACE(2, sg);
             }
-            mma_commit(&tail->a_empty[as]);
-            NV_TRACE(2, sg);
+            __syncwarp();
           }
         v_fresh = false;
         if (u + 1 == u1 || (u + 1) / g.tpi != b) {     // last tile of this image in this CTA's range
-          mma_commit(&tail->v_full);
+          if (elect_one()) mma_commit(&tail->v_full);
+          __syncwarp();
           ++vdrains;
           v_fresh = true;
         }
@@ -316,11 +332,10 @@ __global__ void __launch_bounds__(kFThreads, 1)
 #pragma unroll
       for (int k = 0; k < 64; ++k) acc[k] = 0.0f;
 #pragma unroll 1
-      for (int kc = 0; kc < S1; ++kc, ++wg) {
+      for (int kc = 0; kc < S1 / 2; ++kc, ++wg) {      // wg counts stage pairs here
         const uint32_t buf = wg & 1;
         mbar_wait(&tail->acc_full[buf], (wg >> 1) & 1);
         tc_fence_after();
-        if (warp == 4 && lane == 0) NV_TRACE(3, wg);
         const float us = tail->uns[wg & 3][row];
         const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16) + buf * 64;
 #pragma unroll
@@ -334,7 +349,6 @@ __global__ void __launch_bounds__(kFThreads, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tail->acc_empty[buf]);
-        if (warp == 4 && lane == 0) NV_TRACE(4, wg);
       }
       mbar_wait(&tail->norm_full, uint32_t(u - u0) & 1);
       const float iv = tail->inv[(u - u0) & 1][row];
@@ -345,9 +359,10 @@ __global__ void __launch_bounds__(kFThreads, 1)
         m = fmaxf(m, acc[k]);
       }
       float s = 0.0f;
+      const float ml2 = m * 1.4426950408889634f;
 #pragma unroll
       for (int k = 0; k < 64; ++k) {
-        acc[k] = expf(acc[k] - m);
+        acc[k] = exp2f(fmaf(acc[k], 1.4426950408889634f, -ml2));   // ex2.approx: 2 ulp, the exponent is <= 0
         s += acc[k];
       }
       const float rs = valid ? 1.0f / s : 0.0f;        // rows past the map contribute nothing
@@ -424,110 +439,136 @@ __global__ void __launch_bounds__(kFThreads, 1)
     const int lq = warp & 3;
     const int row = lq * 32 + lane;
     const float wun = __ldg(g.wun);
-    const uint32_t tA = tmem_base + (uint32_t(lq * 32) << 16) + kFACol0 + uint32_t(grp) * 64;
+    const uint32_t tA0 = tmem_base + (uint32_t(lq * 32) << 16) + kFACol0;
     uint32_t sg = 0, wg = 0;
-    auto wait_stage = [&](int& l0, int& l1) {
-      const uint32_t ls = 2 * sg;
-      l0 = ls % kLand;
-      l1 = (ls + 1) % kLand;
-      mbar_wait(&tail->land_full[l0], (ls / kLand) & 1);
-      mbar_wait(&tail->land_full[l1], ((ls + 1) / kLand) & 1);
-      mbar_wait(&tail->a_empty[grp], ((sg >> 1) & 1) ^ 1);
-      tc_fence_after();
-      if (lq == 0 && lane == 0) NV_TRACE(5, sg);
-    };
-    auto done_stage = [&](int l0, int l1) {
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&tail->land_empty[l0]);
-        mbar_arrive(&tail->land_empty[l1]);
-        mbar_arrive(&tail->a_full[grp]);
+    // A stage's tcgen05.st are left in flight: its A slot is published (wait::st, fence, arrive) only after the loads of
+    // this group's NEXT stage have been issued, so the store drain and the barrier round trips overlap them.
+    int pending = -1;
+    auto publish = [&]() {
+      if (pending >= 0) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->a_full[pending]);
+        pending = -1;
       }
-      if (lq == 0 && lane == 0) NV_TRACE(6, sg);
     };
 #pragma unroll 1
     for (int u = u0; u < u1; ++u) {
       const int j = u % g.tpi;
       const int par = (u - u0) & 1;
       float ssq = 0.0f;
-      // ---- pass 1: this thread's position, 64 channels = the row's eight 16-byte chunks in each of the two boxes.
-      // Chunk c of row r sits at c ^ (r & 7): the eight consecutive rows of a quarter-warp read eight different chunk
-      // positions, i.e. all 32 banks, with every LDS.128 ----
+      // ---- pass 1: this thread's position, the stage's 32 channels = the row's eight 16-byte chunks.  Chunk c of row r
+      // sits at c ^ (r & 7): the eight consecutive rows of a quarter-warp read eight different chunk positions, i.e. all
+      // 32 banks, with every LDS.128.  The power-of-two scale is common to a PAIR of stages (they share one logits
+      // accumulator): the row maximum also runs over the partner stage's box, which the other group converts ----
 #pragma unroll 1
       for (int kc = 0; kc < S1; ++kc, ++sg, ++wg) {
         if ((sg & 1u) != uint32_t(grp)) continue;
-        int l0, l1;
-        wait_stage(l0, l1);
+        const uint32_t sp = (kc & 1) ? sg - 1 : sg + 1;                 // partner stage
+        const int l0 = sg % kLand, lp = sp % kLand;
+        mbar_wait(&tail->land_full[l0], (sg / kLand) & 1);
+        mbar_wait(&tail->land_full[lp], (sp / kLand) & 1);
+        if (lq == 0 && lane == 0) NV_TRACE(5, sg);
         const uint8_t* r0 = smem + size_t(l0) * kLandBytes + row * 128;
-        const uint8_t* r1 = smem + size_t(l1) * kLandBytes + row * 128;
+        const uint8_t* rp = smem + size_t(lp) * kLandBytes + row * 128;
         const int sw = row & 7;
-        float x[64];
+        float x[32];
+        float4 vp[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float4 v0 = *reinterpret_cast<const float4*>(r0 + ((c ^ sw) << 4));
-          const float4 v1 = *reinterpret_cast<const float4*>(r1 + ((c ^ sw) << 4));
+          vp[c] = *reinterpret_cast<const float4*>(rp + ((c ^ sw) << 4));
           x[4 * c] = v0.x; x[4 * c + 1] = v0.y; x[4 * c + 2] = v0.z; x[4 * c + 3] = v0.w;
-          x[32 + 4 * c] = v1.x; x[32 + 4 * c + 1] = v1.y; x[32 + 4 * c + 2] = v1.z; x[32 + 4 * c + 3] = v1.w;
         }
+        publish();                                       // the previous stage of this group
         float mx = 0.0f;
 #pragma unroll
-        for (int e = 0; e < 64; ++e) {
+        for (int c = 0; c < 8; ++c)
+          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(vp[c].x), fabsf(vp[c].y)), fmaxf(fabsf(vp[c].z), fabsf(vp[c].w))));
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
           mx = fmaxf(mx, fabsf(x[e]));
           ssq = fmaf(x[e], x[e], ssq);
+        }
+        __syncwarp();
+        if (lane == 0) {                                 // the landed boxes are in registers now
+          mbar_arrive(&tail->land_empty[l0]);
+          mbar_arrive(&tail->land_empty[lp]);
         }
         // power-of-two scale putting the row's maximum in [2^14, 2^15); rows below 2^-100 are numerically zero
         const uint32_t mb = __float_as_uint(fmaxf(mx, 7.8886090522101181e-31f)) & 0x7f800000u;
         const float sc = __uint_as_float((268u << 23) - mb);
-        tail->uns[wg & 3][row] = __uint_as_float(mb - (14u << 23)) * wun;
+        if (!(kc & 1)) tail->uns[(wg >> 1) & 3][row] = __uint_as_float(mb - (14u << 23)) * wun;
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {                 // 16 channels = 8 TMEM columns of hi and 8 of lo
-          uint32_t hi[8], lo[8];
+        for (int e = 0; e < 16; ++e) split2(x[2 * e] * sc, x[2 * e + 1] * sc, hi[e], lo[e]);
+        mbar_wait(&tail->a_empty[sg & 3], ((sg >> 2) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tA = tA0 + (sg & 3) * 32;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split2(x[16 * qd + 2 * e] * sc, x[16 * qd + 2 * e + 1] * sc, hi[e], lo[e]);
-          tmem_st_32x8(tA + 8 * qd, hi);
-          tmem_st_32x8(tA + 32 + 8 * qd, lo);
+        for (int qd = 0; qd < 2; ++qd) {                 // 16 channels = 8 TMEM columns of hi and 8 of lo
+          uint32_t h8[8], l8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { h8[e] = hi[8 * qd + e]; l8[e] = lo[8 * qd + e]; }
+          tmem_st_32x8(tA + 8 * qd, h8);
+          tmem_st_32x8(tA + 16 + 8 * qd, l8);
         }
-        done_stage(l0, l1);
+        pending = int(sg & 3);
+        if (lq == 0 && lane == 0) NV_TRACE(6, sg);
       }
+      publish();
       tail->ssqp[grp][row] = ssq;
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (grp == 0) tail->inv[par][row] = rsqrtf(fmaxf(tail->ssqp[0][row] + tail->ssqp[1][row], 1e-12f));   // nets.py:66
       asm volatile("bar.sync 2, 256;" ::: "memory");   // every splitter sees every row's 1/|x|; ssqp may be rewritten
       if (lane == 0) mbar_arrive(&tail->norm_full);
-      // ---- pass 2: this thread's channel (box lq, float `lane` of the 128-byte row), 64 positions; a warp reads one
-      // whole row per LDS.32 ----
-      const int nph = pos_halves(j);
-      const int n2 = NCG * nph;
+      // ---- pass 2: this thread's channel (box lq, float `lane` of the 128-byte row), the stage's 32 positions; a warp
+      // reads one whole row per LDS.32.  The group that does not own a stage only hands its landing slot back ----
+      const int npc = pos_chunks(j);
+      const int n2 = NCG * npc;
 #pragma unroll 1
       for (int s2 = 0; s2 < n2; ++s2, ++sg) {
-        if ((sg & 1u) != uint32_t(grp)) continue;
-        const int ph = s2 % nph;
-        int l0, l1;
-        wait_stage(l0, l1);
-        const float* ivp = &tail->inv[par][64 * ph];
-#pragma unroll
-        for (int p16 = 0; p16 < 4; ++p16) {
-          const uint8_t* base = smem + size_t(p16 < 2 ? l0 : l1) * kLandBytes + lq * 4096 + (lane & 3) * 4;
-          float xv[16];
-#pragma unroll
-          for (int pp = 0; pp < 16; ++pp) {
-            const int ri = (16 * p16 + pp) & 31;           // row inside the 32-position box
-            xv[pp] = *reinterpret_cast<const float*>(base + ri * 128 + (((lane >> 2) ^ (ri & 7)) << 4));
-          }
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 iv4 = *reinterpret_cast<const float4*>(ivp + 16 * p16 + 4 * q4);
-            split2(xv[4 * q4] * (iv4.x * kScale14), xv[4 * q4 + 1] * (iv4.y * kScale14), hi[2 * q4], lo[2 * q4]);
-            split2(xv[4 * q4 + 2] * (iv4.z * kScale14), xv[4 * q4 + 3] * (iv4.w * kScale14), hi[2 * q4 + 1], lo[2 * q4 + 1]);
-          }
-          tmem_st_32x8(tA + 8 * p16, hi);
-          tmem_st_32x8(tA + 32 + 8 * p16, lo);
+        const int l0 = sg % kLand;
+        mbar_wait(&tail->land_full[l0], (sg / kLand) & 1);
+        if ((sg & 1u) != uint32_t(grp)) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tail->land_empty[l0]);
+          continue;
         }
-        done_stage(l0, l1);
+        const int pc = s2 % npc;
+        if (lq == 0 && lane == 0) NV_TRACE(5, sg);
+        const float* ivp = &tail->inv[par][32 * pc];
+        const uint8_t* base = smem + size_t(l0) * kLandBytes + lq * 4096 + (lane & 3) * 4;
+        float xv[32];
+#pragma unroll
+        for (int ri = 0; ri < 32; ++ri)                    // row inside the 32-position box
+          xv[ri] = *reinterpret_cast<const float*>(base + ri * 128 + (((lane >> 2) ^ (ri & 7)) << 4));
+        publish();
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 iv4 = *reinterpret_cast<const float4*>(ivp + 4 * q4);
+          split2(xv[4 * q4] * (iv4.x * kScale14), xv[4 * q4 + 1] * (iv4.y * kScale14), hi[2 * q4], lo[2 * q4]);
+          split2(xv[4 * q4 + 2] * (iv4.z * kScale14), xv[4 * q4 + 3] * (iv4.w * kScale14), hi[2 * q4 + 1], lo[2 * q4 + 1]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->land_empty[l0]);
+        mbar_wait(&tail->a_empty[sg & 3], ((sg >> 2) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tA = tA0 + (sg & 3) * 32;
+#pragma unroll
+        for (int qd = 0; qd < 2; ++qd) {
+          uint32_t h8[8], l8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { h8[e] = hi[8 * qd + e]; l8[e] = lo[8 * qd + e]; }
+          tmem_st_32x8(tA + 8 * qd, h8);
+          tmem_st_32x8(tA + 16 + 8 * qd, l8);
+        }
+        pending = int(sg & 3);
+        if (lq == 0 && lane == 0) NV_TRACE(6, sg);
       }
+      publish();
     }
   }
 

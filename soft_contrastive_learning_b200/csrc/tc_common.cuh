@@ -13,6 +13,16 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One lane of a fully converged warp.  Single-thread instructions (tcgen05.mma / commit, TMA) take their operands from
+// UNIFORM registers: issued under `if (lane == 0)` the operands live in a divergent region and ptxas wraps every such
+// instruction in an ELECT / R2UR / branch loop (~12 instructions, ~70 cycles each); issued by all lanes of a converged warp
+// under this predicate the operands are provably warp-uniform and the loop disappears.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------- mbarrier -------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
