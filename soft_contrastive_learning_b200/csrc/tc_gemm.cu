@@ -102,7 +102,9 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // every lane runs the loop, one elected lane issues: the operands of the single-thread instructions are then provably
+    // warp-uniform and go straight to uniform registers (tc_common.cuh: elect_one)
+    {
       uint32_t kcg = 0;                                 // ring position, running across tiles
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const Tile t = decode(tile);
@@ -112,7 +114,6 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
         mbar_wait(&tail->empty[stage], ((kcg / kStages) & 1) ^ 1);
         uint8_t* sa = smem + size_t(stage) * Cfg::kStageBytes;
         uint8_t* sb = sa + kGABytes;
-        mbar_arrive_expect_tx(&tail->full[stage], Cfg::kHiBytes);
         // K stages beyond k1_stages come from the second operand pair (K-concatenated problem)
         const int ka = k_begin + kc;
         const bool second = ka >= g.k1_stages;
@@ -120,24 +121,28 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
         const CUtensorMap* mB = second ? &tmB2 : &tmB;
         const int kk = (second ? ka - g.k1_stages : ka) * kGBK;
         const int bzb = (second ? g.b2_shared : g.b_shared) ? 0 : bz;
-        if (kAMn) {
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&tail->full[stage], Cfg::kHiBytes);
+          if (kAMn) {
 #pragma unroll
-          for (int grp = 0; grp < kGBM / 32; ++grp) tma_load_3d(sa + grp * 4096, mA, &tail->full[stage], m0 + 32 * grp, kk, bz);
-        } else {
-          tma_load_3d(sa, mA, &tail->full[stage], kk, m0, bz);
-        }
-        if (kBMn) {
+            for (int grp = 0; grp < kGBM / 32; ++grp) tma_load_3d(sa + grp * 4096, mA, &tail->full[stage], m0 + 32 * grp, kk, bz);
+          } else {
+            tma_load_3d(sa, mA, &tail->full[stage], kk, m0, bz);
+          }
+          if (kBMn) {
 #pragma unroll
-          for (int grp = 0; grp < BN / 32; ++grp) tma_load_3d(sb + grp * 4096, mB, &tail->full[stage], n0 + 32 * grp, kk, bzb);
-        } else {
-          tma_load_3d(sb, mB, &tail->full[stage], kk, n0, bzb);
+            for (int grp = 0; grp < BN / 32; ++grp) tma_load_3d(sb + grp * 4096, mB, &tail->full[stage], n0 + 32 * grp, kk, bzb);
+          } else {
+            tma_load_3d(sb, mB, &tail->full[stage], kk, n0, bzb);
+          }
         }
+        __syncwarp();
       }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = make_idesc(kFmtTF32, kGBM, BN) | (kAMn ? (1u << 15) : 0u) | (kBMn ? (1u << 16) : 0u);
       // K advance of 8 tf32 inside a stage: K-major +32 bytes within the swizzle row, MN-major +1024 bytes (next atom)
       constexpr uint64_t stepA = kAMn ? (1024 >> 4) : (32 >> 4), stepB = kBMn ? (1024 >> 4) : (32 >> 4);
@@ -159,23 +164,25 @@ __global__ void __launch_bounds__(GCfg<BN, kX3>::kThreads, 1)
         const uint32_t sb = sa + kGABytes;
         const uint64_t da = kAMn ? smem_desc_sw128_mn(sa) : smem_desc_sw128(sa);
         const uint64_t db = kBMn ? smem_desc_sw128_mn(sb) : smem_desc_sw128(sb);
+        const bool last = in_grp == Cfg::kFlush - 1 || kc == num_k - 1;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kGBK / 8; ++k)
-          mma_tf32_ss(d_tmem, da + stepA * k, db + stepB * k, idesc, (in_grp | k) != 0 ? 1u : 0u);
-        if (kX3) {
-          const uint64_t dal = kAMn ? smem_desc_sw128_mn(sa + Cfg::kHiBytes) : smem_desc_sw128(sa + Cfg::kHiBytes);
-          const uint64_t dbl = kBMn ? smem_desc_sw128_mn(sb + Cfg::kHiBytes) : smem_desc_sw128(sb + Cfg::kHiBytes);
+          for (int k = 0; k < kGBK / 8; ++k)
+            mma_tf32_ss(d_tmem, da + stepA * k, db + stepB * k, idesc, (in_grp | k) != 0 ? 1u : 0u);
+          if (kX3) {
+            const uint64_t dal = kAMn ? smem_desc_sw128_mn(sa + Cfg::kHiBytes) : smem_desc_sw128(sa + Cfg::kHiBytes);
+            const uint64_t dbl = kBMn ? smem_desc_sw128_mn(sb + Cfg::kHiBytes) : smem_desc_sw128(sb + Cfg::kHiBytes);
 #pragma unroll
-          for (int k = 0; k < kGBK / 8; ++k) {
-            mma_tf32_ss(d_tmem, da + stepA * k, dbl + stepB * k, idesc, 1u);     // hi_a * lo_b
-            mma_tf32_ss(d_tmem, dal + stepA * k, db + stepB * k, idesc, 1u);     // lo_a * hi_b
+            for (int k = 0; k < kGBK / 8; ++k) {
+              mma_tf32_ss(d_tmem, da + stepA * k, dbl + stepB * k, idesc, 1u);     // hi_a * lo_b
+              mma_tf32_ss(d_tmem, dal + stepA * k, db + stepB * k, idesc, 1u);     // lo_a * hi_b
+            }
           }
+          mma_commit(&tail->empty[stage]);              // frees the stage when these MMAs retire
+          if (last) mma_commit(&tail->acc_full[buf]);
         }
-        mma_commit(&tail->empty[stage]);              // frees the stage when these MMAs retire
-        if (in_grp == Cfg::kFlush - 1 || kc == num_k - 1) {
-          mma_commit(&tail->acc_full[buf]);
-          ++grpg;
-        }
+        __syncwarp();
+        if (last) ++grpg;
       }
       }
     }
