@@ -623,12 +623,27 @@ def bench_netvlad_pca(args, torch, pk, B=256, H=30, W=40, Cc=512, K=64, Dout=409
     f_pb = lambda: check(L.scl_pca_bwd(_p(dy), _p(V), _p(var), B, Din, Dout, _p(dvlad), _p(pws), pws.numel(), st), "pca bwd")
     f_nb = lambda: check(L.scl_netvlad_bwd(_p(x), _p(aw), _p(cc), _p(dvlad), B, HW, Cc, K, _p(dx), _p(dw), _p(dc), _p(ws),
                                            ws.numel(), st), "nv bwd")
+    # the PCA matrix is a fed constant (train/train.py:281-283): split once into fp16 hi / lo halves, outside the step
+    check(L.scl_pca_shadow_bytes(Din, Dout, C.byref(n)), "shadow bytes")
+    shadow = _ws(n.value, x.device)
+    f_prep = lambda: check(L.scl_pca_prepare(_p(V), Din, Dout, _p(shadow), shadow.numel(), st), "pca prepare")
+    prep_ms = _time_ms(torch, f_prep, 3, 1)
+    check(L.scl_pca_prepared_workspace_bytes(B, Din, Dout, C.byref(n)), "ws")
+    qws = _ws(n.value, x.device)
+    f_pfp = lambda: check(L.scl_pca_fwd_prepared(_p(vlad), _p(shadow), _p(m), _p(var), B, Din, Dout, _p(y), _p(qws), qws.numel(), st), "pca fwd prepared")
+    f_pbp = lambda: check(L.scl_pca_bwd_prepared(_p(dy), _p(shadow), _p(var), B, Din, Dout, _p(dvlad), _p(qws), qws.numel(), st), "pca bwd prepared")
     out = {}
     for prec, tag in ((0, "fp32-grade 3xTF32"), (1, "single-pass TF32")):
         check(L.scl_set_gemm_precision(prec), "prec")
         t = {"netvlad_fwd": _time_ms(torch, f_nv, 5), "pca_fwd": _time_ms(torch, f_pf, 5), "pca_bwd": _time_ms(torch, f_pb, 5),
              "netvlad_bwd": _time_ms(torch, f_nb, 5)}
-        t["total"] = sum(t.values())
+        if prec == 0:
+            # fp32-grade mode as the host wrapper runs it: fused NetVLAD forward (fp16 hi/lo operands in tensor memory) and
+            # the prepared PCA (pre-split f16 engine); the in-kernel 3xTF32 split is kept beside it
+            t["pca_fwd_3xtf32_unprepared"], t["pca_bwd_3xtf32_unprepared"] = t["pca_fwd"], t["pca_bwd"]
+            t["pca_fwd"], t["pca_bwd"] = _time_ms(torch, f_pfp, 5), _time_ms(torch, f_pbp, 5)
+            t["pca_prepare_once"] = prep_ms
+        t["total"] = t["netvlad_fwd"] + t["pca_fwd"] + t["pca_bwd"] + t["netvlad_bwd"]
         out[tag] = t
     check(L.scl_set_gemm_precision(0), "prec")
     flops = {"netvlad_fwd": 2 * 2.0 * B * HW * Cc * K, "netvlad_bwd": 4 * 2.0 * B * HW * Cc * K,
@@ -641,7 +656,7 @@ def bench_netvlad_pca(args, torch, pk, B=256, H=30, W=40, Cc=512, K=64, Dout=409
     hbm_bytes = 4.0 * (3 * B * HW * Cc + 2 * Dout * Din + 4 * B * Din + 2 * B * Dout)
     hbm_gbs = hbm_bytes / (t0["total"] * 1e-3) / 1e9
     return {"metric": "NetVLAD head + PCA fwd+bwd images/s", "value": B / (t0["total"] * 1e-3), "unit": "images/s",
-            "ms_per_step": t0["total"], "dtype": "tf32 x3 (fp32-grade) on tcgen05, fp32 accumulate",
+            "ms_per_step": t0["total"], "dtype": "fp32-grade on tcgen05: fp16 hi/lo split x3 (NetVLAD forward, PCA) and tf32 x3 (NetVLAD backward), fp32 accumulate",
             "config": {"workload": f"BASELINE config 2: B={B}, {H}x{W}x{Cc} conv5 maps, K={K}, PCA {Din}->{Dout}, fwd+bwd",
                        "ms": out, "inputs": "x 629 MB + V 537 MB fp32 (>> L2)"},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",

@@ -180,6 +180,20 @@ int scl_pca_fwd(const float* x, const float* v, const float* m, const float* var
 int scl_pca_bwd(const float* dy, const float* v, const float* var, int B, int Din, int Dout,
                 float* dx, void* workspace, size_t workspace_bytes, scl_stream_t stream);
 
+/* P1 with a prepared projection matrix.  v is a fed constant of the training loop (train/train.py:281-283, 647-649) and of
+ * top-n.py's sweep: scl_pca_prepare splits it ONCE into fp16 hi / lo halves with one power-of-two scale (the "shadow",
+ * 256-byte aligned, scl_pca_shadow_bytes); scl_pca_fwd_prepared / _bwd_prepared then run the same projection on the
+ * pre-split f16 tensor-core engine (csrc/tc_gemm_h3.cu): fp32-grade (22 significant bits per operand, three products,
+ * fp32 accumulation flushed every 128 k) like scl_pca_fwd, 2.5-3x faster.  Requires Din, Dout multiples of 8 and
+ * <= 32768 (SCL_ERR_UNSUPPORTED otherwise: use scl_pca_fwd / scl_pca_bwd).  Workspace: scl_pca_prepared_workspace_bytes. */
+int scl_pca_shadow_bytes(int Din, int Dout, size_t* bytes);
+int scl_pca_prepare(const float* v, int Din, int Dout, void* shadow, size_t shadow_bytes, scl_stream_t stream);
+int scl_pca_prepared_workspace_bytes(int B, int Din, int Dout, size_t* bytes);
+int scl_pca_fwd_prepared(const float* x, const void* shadow, const float* m, const float* var, int B, int Din, int Dout,
+                         float* y, void* workspace, size_t workspace_bytes, scl_stream_t stream);
+int scl_pca_bwd_prepared(const float* dy, const void* shadow, const float* var, int B, int Din, int Dout,
+                         float* dx, void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
 /* P0: the data-sized steps of the PCA *fit*, `PCA(whiten=True, n_components=d).fit(pca_f)` at
  * evaluation/top-n.py:74-75 (training twin: the incremental PCA of train/train.py:1039-1053, source absent upstream).
  *   mean[D] = column means of x [n,D] (float64 accumulation, fixed order), xc [n,D] = x - mean (may be NULL).

@@ -66,6 +66,11 @@ PROTOTYPES = {
     "scl_pca_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, _SIZE_P]),
     "scl_pca_fwd": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_pca_bwd": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "scl_pca_shadow_bytes": (C.c_int, [C.c_int, C.c_int, _SIZE_P]),
+    "scl_pca_prepare": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, C.c_size_t, c_ptr]),
+    "scl_pca_prepared_workspace_bytes": (C.c_int, [C.c_int, C.c_int, C.c_int, _SIZE_P]),
+    "scl_pca_fwd_prepared": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "scl_pca_bwd_prepared": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_pca_center_workspace_bytes": (C.c_int, [C.c_int, C.c_int, _SIZE_P]),
     "scl_pca_center": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_set_gemm_precision": (C.c_int, [C.c_int]),

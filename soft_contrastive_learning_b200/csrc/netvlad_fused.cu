@@ -34,8 +34,6 @@
 // Warps: 0, 3 = TMA producers (X), 1 = MMA issuer, 2 = TMA producer (W), 4-7 = epilogue, 8-15 = splitters.
 #include <cuda_fp16.h>
 
-#include <cstdlib>
-
 #include "netvlad_fused.cuh"
 #include "tc_common.cuh"
 
@@ -68,7 +66,7 @@ struct FSmemTail {
 };
 
 struct NvFusedArgs {
-  int B, HW, C, tpi, units, nslots, dbg;
+  int B, HW, C, tpi, units, nslots;
   const float* x;      // [B, HW, C]
   float* inv;          // [B*HW]
   float* a;            // [B*HW, 64]
@@ -78,7 +76,13 @@ struct NvFusedArgs {
   long long* trace;    // debug: [role][4096] clock stamps of CTA 0
 };
 
+// Role time-line of CTA 0 (clock64 stamps per pipeline event), compiled in with -DSCL_NV_TRACE only: how the stage period,
+// the hand-off latencies and the per-tile bubble quoted in DESIGN.md were measured.
+#ifdef SCL_NV_TRACE
 #define NV_TRACE(role, idx) do { if (g.trace && blockIdx.x == 0 && (idx) < 4096) g.trace[(role) * 4096 + (idx)] = clock64(); } while (0)
+#else
+#define NV_TRACE(role, idx) do { } while (0)
+#endif
 
 __host__ __device__ __forceinline__ int nv_cta_of_unit(long long u, int G, long long units) {
   return int(((u + 1) * G - 1) / units);
@@ -719,14 +723,13 @@ int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, in
   NvFusedArgs g;
   g.B = B; g.HW = HW; g.C = C; g.tpi = tpi; g.units = int(units); g.nslots = nv_fused_slots(B, tpi);
   g.x = x; g.inv = inv; g.a = a;
-  { const char* e = getenv("SCL_NV_DBG"); g.dbg = e ? atoi(e) : 0; }
   g.trace = nullptr;
+#ifdef SCL_NV_TRACE
   static long long* s_trace = nullptr;
-  if (g.dbg & 1024) {
-    if (!s_trace) { cudaMalloc(&s_trace, 8 * 4096 * sizeof(long long)); }
-    cudaMemsetAsync(s_trace, 0, 8 * 4096 * sizeof(long long), stream);
-    g.trace = s_trace;
-  }
+  if (!s_trace) cudaMalloc(&s_trace, 8 * 4096 * sizeof(long long));
+  cudaMemsetAsync(s_trace, 0, 8 * 4096 * sizeof(long long), stream);
+  g.trace = s_trace;
+#endif
   __half* wt_hi = c.take<__half>(size_t(kWCopies) * 64 * C);
   __half* wt_lo = c.take<__half>(size_t(kWCopies) * 64 * C);
   float* wun = c.take<float>(1);
@@ -749,13 +752,20 @@ int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, in
   SCL_LAUNCH_CHECK();
   nv_fused_tail_kernel<<<B, 256, 0, stream>>>(g.vpart, g.aspart, centers, C, tpi, int(units), G, g.nslots, V, asum, nk, nt, out);
   SCL_LAUNCH_CHECK();
-  if (g.trace) {
+#ifdef SCL_NV_TRACE
+  {
     static long long h[8 * 4096];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost);
     FILE* f = fopen("gpurun_out/nv_trace.txt", "w");
-    if (f) { for (int r = 0; r < 8; ++r) for (int i = 0; i < 4096; ++i) if (h[r * 4096 + i]) fprintf(f, "%d %d %lld\n", r, i, h[r * 4096 + i]); fclose(f); }
+    if (f) {
+      for (int r = 0; r < 8; ++r)
+        for (int i = 0; i < 4096; ++i)
+          if (h[r * 4096 + i]) fprintf(f, "%d %d %lld\n", r, i, h[r * 4096 + i]);
+      fclose(f);
+    }
   }
+#endif
   return SCL_OK;
 }
 

@@ -1,5 +1,7 @@
 // tc_gemm.cuh -- interface of the tcgen05 TF32 / 3xTF32 GEMM (tc_gemm.cu).
 #pragma once
+#include <cuda_fp16.h>
+
 #include <atomic>
 
 #include "common.cuh"
@@ -53,6 +55,18 @@ struct TcGemmArgs {
 };
 
 int tc_gemm(const TcGemmDesc& d, cudaStream_t stream);
+
+// tc_gemm_h3.cu: fp32-grade GEMM from operands pre-split into fp16 hi / lo halves (kind::f16, three products per k)
+//   C[M,N] = rowscale[m] * colscale[n] * (Ah + Al) . (Bh + Bl)^T;  B K-major [N,K] or MN-major [K,N] (b_mn)
+int tc_gemm_h3(const __half* Ah, const __half* Al, const __half* Bh, const __half* Bl, float* C, int M, int N, int K, int lda,
+               int ldb, int ldc, bool b_mn, const float* rowscale, const float* colscale, int split_k, cudaStream_t stream);
+// rows of x (minus `sub`, divided by sqrt(isqrt_of), both optional, per column) -> fp16 hi / lo with one power-of-two scale
+// per row; unscale[r] = 2^-e (* *mul)
+int h3_split_rows(const float* x, const float* sub, const float* isqrt_of, int R, int Cc, __half* hi, __half* lo,
+                  float* unscale, const float* mul, cudaStream_t stream);
+// whole matrix with ONE scale (usable as the contraction operand in either orientation); *unscale = 2^-e
+int h3_split_all(const float* x, long long n, unsigned int* maxbits, __half* hi, __half* lo, float* unscale,
+                 cudaStream_t stream);
 int tc_gemm_precision();   // process-wide default set through scl_set_gemm_precision
 
 }  // namespace scl

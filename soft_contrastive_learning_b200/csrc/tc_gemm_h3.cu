@@ -1,0 +1,350 @@
+// tc_gemm_h3.cu -- fp32-grade GEMM on tcgen05 kind::f16 from operands that are ALREADY split into fp16 hi / lo halves in
+// global memory:  C[M,N] (+)= rowscale[m] * colscale[n] * sum_k (Ah + Al)(m,k) (Bh + Bl)(n,k),  three products per k
+// (hi*hi + hi*lo + lo*hi, fp32 accumulation; the dropped lo*lo is 2^-22 relative).
+//
+// Why it exists: the 3xTF32 engine of tc_gemm.cu takes fp32 operands and splits every landed stage in shared memory;
+// per 32 k-elements its shared-memory pipe carries the stage five times (TMA in, splitter read, hi + lo written, three
+// operand reads by the tensor core) and that pipe -- 128 bytes per cycle for everything -- is what bounds it.  When an
+// operand is the same on every call (the PCA matrix of train/train.py:646-652 is a fed constant) or cheap to convert
+// (its [B, Din] partner), splitting ONCE into fp16 halves removes the splitters, halves the bytes of every operand and
+// runs the tensor core at the f16 rate: same error class (22 significant bits per operand), 2.5-3x the speed.
+// Power-of-two scaling keeps every half inside the fp16 range; the scales come back through rowscale / colscale.
+//
+// Persistent CTAs, 128 x 128 output tiles, stages of 64 k-elements (one 128-byte swizzle row): A hi | A lo | B hi | B lo
+// = 64 KB, three stages.  Warp 0 = TMA producer, 1 = MMA issuer, 2-5 = epilogue.  As in tc_gemm.cu the accumulator is
+// flushed into registers every two stages (tensor-core fp32 accumulation truncates), two TMEM accumulators alternate.
+#include <cuda_fp16.h>
+
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace scl {
+
+using namespace tc;
+
+constexpr int kHBM = 128, kHBN = 128, kHBK = 64;
+constexpr uint32_t kHTile = kHBM * kHBK * 2;            // 16 KB: one operand half of a stage
+constexpr uint32_t kHStage = 4 * kHTile;                // A hi | A lo | B hi | B lo
+constexpr int kHStages = 3;
+constexpr int kHFlush = 2;
+constexpr int kHThreads = 192;
+
+struct HSmemTail {
+  uint64_t full[kHStages], empty[kHStages], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct H3Args {
+  int M, N, K;
+  float* C;
+  int ldc;
+  const float* rowscale;   // [M] or null
+  const float* colscale;   // [N] or null
+  int split_k, tiles_n, tiles_m;
+};
+
+template <bool kBMn>
+__global__ void __launch_bounds__(kHThreads, 1)
+    tc_gemm_h3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                      const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, H3Args g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  HSmemTail* tail = reinterpret_cast<HSmemTail*>(smem + size_t(kHStages) * kHStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_k = (g.K + kHBK - 1) / kHBK;
+  const int ntiles = g.tiles_n * g.tiles_m * g.split_k;
+  struct Tile { int m0, n0, k_begin, num_k; };
+  // consecutive tiles share their B columns (the large operand): the M tiles of one N tile run next to each other
+  auto decode = [&](int tile) {
+    Tile t;
+    const int by = tile % g.tiles_m, r = tile / g.tiles_m, bx = r % g.tiles_n, ks = r / g.tiles_n;
+    t.m0 = by * kHBM;
+    t.n0 = bx * kHBN;
+    t.k_begin = (total_k * ks) / g.split_k;
+    t.num_k = (total_k * (ks + 1)) / g.split_k - t.k_begin;
+    return t;
+  };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmAh);
+    prefetch_tmap(&tmAl);
+    prefetch_tmap(&tmBh);
+    prefetch_tmap(&tmBl);
+    for (int s = 0; s < kHStages; ++s) {
+      mbar_init(&tail->full[s], 1);
+      mbar_init(&tail->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tail->acc_full[b], 1);
+      mbar_init(&tail->acc_empty[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tail->tmem_base, 2 * kHBN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t kcg = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const Tile t = decode(tile);
+      for (int kc = 0; kc < t.num_k; ++kc, ++kcg) {
+        const int stage = kcg % kHStages;
+        mbar_wait(&tail->empty[stage], ((kcg / kHStages) & 1) ^ 1);
+        uint8_t* s0 = smem + size_t(stage) * kHStage;
+        const int kk = (t.k_begin + kc) * kHBK;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&tail->full[stage], kHStage);
+          tma_load_2d(s0, &tmAh, &tail->full[stage], kk, t.m0);
+          tma_load_2d(s0 + kHTile, &tmAl, &tail->full[stage], kk, t.m0);
+          if (kBMn) {                                    // two boxes of 64 n x 64 k per half
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+              tma_load_2d(s0 + 2 * kHTile + nb * 8192, &tmBh, &tail->full[stage], t.n0 + 64 * nb, kk);
+              tma_load_2d(s0 + 3 * kHTile + nb * 8192, &tmBl, &tail->full[stage], t.n0 + 64 * nb, kk);
+            }
+          } else {
+            tma_load_2d(s0 + 2 * kHTile, &tmBh, &tail->full[stage], kk, t.n0);
+            tma_load_2d(s0 + 3 * kHTile, &tmBl, &tail->full[stage], kk, t.n0);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(kFmtF16, kHBM, kHBN) | (kBMn ? (1u << 16) : 0u);
+    uint32_t kcg = 0, grpg = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int num_k = decode(tile).num_k;
+      for (int kc = 0; kc < num_k; ++kc, ++kcg) {
+        const int stage = kcg % kHStages;
+        const int in_grp = kc % kHFlush;
+        const uint32_t buf = grpg & 1;
+        if (in_grp == 0) {
+          mbar_wait(&tail->acc_empty[buf], ((grpg >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        mbar_wait(&tail->full[stage], (kcg / kHStages) & 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kHBN;
+        const uint32_t sa = smem_u32(smem + size_t(stage) * kHStage);
+        const uint32_t sbh = sa + 2 * kHTile, sbl = sa + 3 * kHTile;
+        const bool last = in_grp == kHFlush - 1 || kc == num_k - 1;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kHBK / 16; ++k) {
+            // K-major: +32 bytes inside the swizzle row; MN-major: +16 k rows = 2048 bytes
+            const uint64_t dah = smem_desc_sw128(sa) + 2 * k, dal = smem_desc_sw128(sa + kHTile) + 2 * k;
+            const uint64_t dbh = kBMn ? smem_desc_sw128_mn16(sbh + 2048 * k, 8192) : smem_desc_sw128(sbh) + 2 * k;
+            const uint64_t dbl = kBMn ? smem_desc_sw128_mn16(sbl + 2048 * k, 8192) : smem_desc_sw128(sbl) + 2 * k;
+            mma_f16_ss(d_tmem, dah, dbh, idesc, (in_grp | k) != 0 ? 1u : 0u);
+            mma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
+            mma_f16_ss(d_tmem, dal, dbh, idesc, 1u);
+          }
+          mma_commit(&tail->empty[stage]);
+          if (last) mma_commit(&tail->acc_full[buf]);
+        }
+        __syncwarp();
+        if (last) ++grpg;
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int lq = warp & 3;
+    uint32_t grpg = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const Tile t = decode(tile);
+      const int m = t.m0 + lq * 32 + lane;
+      float acc[kHBN];
+#pragma unroll
+      for (int j = 0; j < kHBN; ++j) acc[j] = 0.0f;
+      const int ngroups = (t.num_k + kHFlush - 1) / kHFlush;
+#pragma unroll 1
+      for (int grp = 0; grp < ngroups; ++grp, ++grpg) {
+        const uint32_t buf = grpg & 1;
+        mbar_wait(&tail->acc_full[buf], (grpg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(lq * 32) << 16) + buf * kHBN;
+#pragma unroll
+        for (int c = 0; c < kHBN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->acc_empty[buf]);
+      }
+      if (m < g.M) {
+        float* crow = g.C + size_t(m) * g.ldc;
+        const float rs = g.rowscale ? __ldg(g.rowscale + m) : 1.0f;
+#pragma unroll
+        for (int j4 = 0; j4 < kHBN / 4; ++j4) {
+          const int n = t.n0 + 4 * j4;
+          if (n + 3 < g.N) {
+            float4 o = make_float4(acc[4 * j4] * rs, acc[4 * j4 + 1] * rs, acc[4 * j4 + 2] * rs, acc[4 * j4 + 3] * rs);
+            if (g.colscale) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(g.colscale + n));
+              o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w;
+            }
+            if (g.split_k > 1) {
+              atomicAdd(crow + n, o.x); atomicAdd(crow + n + 1, o.y); atomicAdd(crow + n + 2, o.z); atomicAdd(crow + n + 3, o.w);
+            } else {
+              *reinterpret_cast<float4*>(crow + n) = o;
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (n + u < g.N) {
+                const float v = acc[4 * j4 + u] * rs * (g.colscale ? g.colscale[n + u] : 1.0f);
+                if (g.split_k > 1) atomicAdd(crow + n + u, v); else crow[n + u] = v;
+              }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * kHBN);
+  }
+}
+
+// A: hi / lo [M, K] fp16, K-major (lda elements).  B: hi / lo fp16, [N, K] K-major or [K, N] MN-major (ldb elements).
+// split_k 2: two CTAs per tile combined with atomicAdd (C zeroed by the caller; two addends commute: deterministic).
+int tc_gemm_h3(const __half* Ah, const __half* Al, const __half* Bh, const __half* Bl, float* C, int M, int N, int K, int lda,
+               int ldb, int ldc, bool b_mn, const float* rowscale, const float* colscale, int split_k, cudaStream_t stream) {
+  if (!Ah || !Al || !Bh || !Bl || !C || M < 1 || N < 1 || K < 1) return SCL_ERR_BAD_ARG;
+  if ((lda & 7) || (ldb & 7) || (ldc & 3) || !aligned16(Ah) || !aligned16(Al) || !aligned16(Bh) || !aligned16(Bl) || !aligned16(C))
+    return SCL_ERR_ALIGN;
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  int rc;
+  if ((rc = make_tmap_2d(&tmAh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Ah, uint64_t(K), uint64_t(M), uint64_t(lda) * 2, kHBK, kHBM))) return rc;
+  if ((rc = make_tmap_2d(&tmAl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Al, uint64_t(K), uint64_t(M), uint64_t(lda) * 2, kHBK, kHBM))) return rc;
+  if (b_mn) {
+    if ((rc = make_tmap_2d(&tmBh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Bh, uint64_t(N), uint64_t(K), uint64_t(ldb) * 2, 64, kHBK))) return rc;
+    if ((rc = make_tmap_2d(&tmBl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Bl, uint64_t(N), uint64_t(K), uint64_t(ldb) * 2, 64, kHBK))) return rc;
+  } else {
+    if ((rc = make_tmap_2d(&tmBh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Bh, uint64_t(K), uint64_t(N), uint64_t(ldb) * 2, kHBK, kHBN))) return rc;
+    if ((rc = make_tmap_2d(&tmBl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Bl, uint64_t(K), uint64_t(N), uint64_t(ldb) * 2, kHBK, kHBN))) return rc;
+  }
+  H3Args g;
+  g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.rowscale = rowscale; g.colscale = colscale;
+  g.tiles_m = (M + kHBM - 1) / kHBM;
+  g.tiles_n = (N + kHBN - 1) / kHBN;
+  g.split_k = (split_k == 2 && (K + kHBK - 1) / kHBK >= 2) ? 2 : 1;
+  const long long ntiles = (long long)g.tiles_m * g.tiles_n * g.split_k;
+  if (ntiles > 0x7fffffffLL) return SCL_ERR_BAD_SHAPE;
+  const unsigned grid = unsigned(ntiles < num_sms() ? ntiles : num_sms());
+  const size_t smem = 1024 + size_t(kHStages) * kHStage + sizeof(HSmemTail);
+  if (b_mn) {
+    static SmemAttrCache cfg;
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(tc_gemm_h3_kernel<true>), smem, &cfg))) return rc;
+    tc_gemm_h3_kernel<true><<<grid, kHThreads, smem, stream>>>(tmAh, tmAl, tmBh, tmBl, g);
+  } else {
+    static SmemAttrCache cfg;
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(tc_gemm_h3_kernel<false>), smem, &cfg))) return rc;
+    tc_gemm_h3_kernel<false><<<grid, kHThreads, smem, stream>>>(tmAh, tmAl, tmBh, tmBl, g);
+  }
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 [R, Cc] -> fp16 hi / lo with ONE power-of-two scale per row (rows that are never a contraction index) or one for the
+// whole matrix (scale_mode 0: the scale exponent is read from *gexp; 1: per row, written to unscale[r] = 2^-e).
+// One CTA per row, the row stays in registers between the maximum and the conversion (<= 1024 x 32 elements).
+__global__ void __launch_bounds__(1024) h3_split_rows_kernel(const float* __restrict__ x, const float* __restrict__ sub,
+                                                            const float* __restrict__ isqrt_of, int Cc, long long ld,
+                                                            __half* __restrict__ hi, __half* __restrict__ lo,
+                                                            float* __restrict__ unscale, const float* __restrict__ mul) {
+  __shared__ float s_mx[32];
+  const long long r = blockIdx.x;
+  const float* row = x + r * ld;
+  float v[32];
+  float mx = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = threadIdx.x + 1024 * i;
+    float t = 0.0f;
+    if (c < Cc) {
+      t = ldg_stream(row + c);
+      if (sub) t -= __ldg(sub + c);                              // centring, in fp32 like the reference graph
+      if (isqrt_of) t /= sqrtf(__ldg(isqrt_of + c));
+    }
+    v[i] = t;
+    mx = fmaxf(mx, fabsf(t));
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) mx = fmaxf(mx, s_mx[i]);
+  const uint32_t mb = __float_as_uint(fmaxf(mx, 7.8886090522101181e-31f)) & 0x7f800000u;
+  const float sc = __uint_as_float((268u << 23) - mb);          // row maximum -> [2^14, 2^15)
+  if (threadIdx.x == 0) unscale[r] = __uint_as_float(mb - (14u << 23)) * (mul ? __ldg(mul) : 1.0f);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = threadIdx.x + 1024 * i;
+    if (c < Cc) {
+      const float xs = v[i] * sc;
+      const __half h = __float2half_rn(xs);
+      hi[r * ld + c] = h;
+      lo[r * ld + c] = __float2half_rn(xs - __half2float(h));
+    }
+  }
+}
+
+int h3_split_rows(const float* x, const float* sub, const float* isqrt_of, int R, int Cc, __half* hi, __half* lo,
+                  float* unscale, const float* mul, cudaStream_t stream) {
+  if (Cc > 32768) return SCL_ERR_UNSUPPORTED;
+  h3_split_rows_kernel<<<R, 1024, 0, stream>>>(x, sub, isqrt_of, Cc, Cc, hi, lo, unscale, mul);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+// whole-matrix scale: maximum, then conversion (two small kernels; the matrix is converted once and re-used)
+__global__ void __launch_bounds__(256) h3_absmax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ out) {
+  float mx = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    mx = fmaxf(mx, fabsf(ldg_stream(x + i)));
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(mx));
+}
+__global__ void __launch_bounds__(256) h3_split_all_kernel(const float* __restrict__ x, long long n,
+                                                           const unsigned int* __restrict__ maxbits, __half* __restrict__ hi,
+                                                           __half* __restrict__ lo, float* __restrict__ unscale) {
+  const uint32_t mb = __float_as_uint(fmaxf(__uint_as_float(*maxbits), 7.8886090522101181e-31f)) & 0x7f800000u;
+  const float sc = __uint_as_float((268u << 23) - mb);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *unscale = __uint_as_float(mb - (14u << 23));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xs = ldg_stream(x + i) * sc;
+    const __half h = __float2half_rn(xs);
+    hi[i] = h;
+    lo[i] = __float2half_rn(xs - __half2float(h));
+  }
+}
+
+int h3_split_all(const float* x, long long n, unsigned int* maxbits, __half* hi, __half* lo, float* unscale,
+                 cudaStream_t stream) {
+  SCL_CUDA_TRY(cudaMemsetAsync(maxbits, 0, sizeof(unsigned int), stream));
+  const int grid = num_sms() * 8;
+  h3_absmax_kernel<<<grid, 256, 0, stream>>>(x, n, maxbits);
+  SCL_LAUNCH_CHECK();
+  h3_split_all_kernel<<<grid, 256, 0, stream>>>(x, n, maxbits, hi, lo, unscale);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+}  // namespace scl

@@ -79,6 +79,50 @@ def set_gemm_precision(mode):
     check(lib().scl_set_gemm_precision(int(mode)), "scl_set_gemm_precision")
 
 
+class PreparedPCA:
+    """The projection matrix split once into fp16 hi / lo halves on the device (``scl_pca_prepare``); projections then run
+    on the pre-split f16 tensor-core engine.  ``v`` is a fed constant in the reference (train/train.py:281-283), so
+    :func:`pca_project` builds this lazily and re-uses it while the tensor it was built from is unchanged."""
+
+    def __init__(self, v):
+        v2 = _f32(v.detach())
+        self.Dout, self.Din = v2.shape
+        n = C.c_size_t()
+        check(lib().scl_pca_shadow_bytes(self.Din, self.Dout, C.byref(n)), "scl_pca_shadow_bytes")
+        self.shadow = _ws(n.value, v2.device)
+        check(lib().scl_pca_prepare(_p(v2), self.Din, self.Dout, _p(self.shadow), self.shadow.numel(), _stream()),
+              "scl_pca_prepare")
+        self.key = _pca_key(v)
+
+    @staticmethod
+    def supported(Din, Dout):
+        return Din % 8 == 0 and Dout % 8 == 0 and 8 <= Din <= 32768 and Dout <= 32768
+
+
+def _pca_key(v):
+    return (v.data_ptr(), v._version, tuple(v.shape), str(v.device))
+
+
+_prepared = {}          # id(tensor) -> (weakref to the tensor, PreparedPCA)
+
+
+def _prepared_for(v):
+    """The PreparedPCA of a LIVE device tensor (same object, same version counter), built on first use.  Host arrays and
+    temporaries are not cached: a recycled device address must never resurrect another matrix's shadow."""
+    import weakref
+    if not (isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32 and v.dim() == 2 and v.is_contiguous()
+            and PreparedPCA.supported(v.shape[1], v.shape[0])):
+        return None
+    ent = _prepared.get(id(v))
+    if ent is not None and ent[0]() is v and ent[1].key == _pca_key(v):
+        return ent[1]
+    for k in [k for k, e in _prepared.items() if e[0]() is None]:
+        del _prepared[k]
+    p = PreparedPCA(v)
+    _prepared[id(v)] = (weakref.ref(v), p)
+    return p
+
+
 class _PcaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, v, m, var):
@@ -86,10 +130,19 @@ class _PcaFn(torch.autograd.Function):
         B, Din = x2.shape
         Dout = v2.shape[0]
         y = torch.empty((B, Dout), dtype=torch.float32, device=x2.device)
-        ws = _pca_ws(B, Din, Dout, x2.device)
-        check(lib().scl_pca_fwd(_p(x2), _p(v2), _p(m1), _p(var1), B, Din, Dout, _p(y), _p(ws), ws.numel(), _stream()),
-              "scl_pca_fwd")
+        prep = _prepared_for(v) if lib().scl_get_gemm_precision() == 0 else None
+        if prep is not None:
+            n = C.c_size_t()
+            check(lib().scl_pca_prepared_workspace_bytes(B, Din, Dout, C.byref(n)), "scl_pca_prepared_workspace_bytes")
+            ws = _ws(n.value, x2.device)
+            check(lib().scl_pca_fwd_prepared(_p(x2), _p(prep.shadow), _p(m1), _p(var1), B, Din, Dout, _p(y), _p(ws),
+                                             ws.numel(), _stream()), "scl_pca_fwd_prepared")
+        else:
+            ws = _pca_ws(B, Din, Dout, x2.device)
+            check(lib().scl_pca_fwd(_p(x2), _p(v2), _p(m1), _p(var1), B, Din, Dout, _p(y), _p(ws), ws.numel(), _stream()),
+                  "scl_pca_fwd")
         ctx.save_for_backward(v2, var1)
+        ctx.prep = prep
         ctx.dims = (B, Din, Dout)
         return y
 
@@ -99,9 +152,16 @@ class _PcaFn(torch.autograd.Function):
         B, Din, Dout = ctx.dims
         dy = _f32(dy)
         dx = torch.empty((B, Din), dtype=torch.float32, device=dy.device)
-        ws = _pca_ws(B, Din, Dout, dy.device)
-        check(lib().scl_pca_bwd(_p(dy), _p(v2), _p(var1), B, Din, Dout, _p(dx), _p(ws), ws.numel(), _stream()),
-              "scl_pca_bwd")
+        if ctx.prep is not None:
+            n = C.c_size_t()
+            check(lib().scl_pca_prepared_workspace_bytes(B, Din, Dout, C.byref(n)), "scl_pca_prepared_workspace_bytes")
+            ws = _ws(n.value, dy.device)
+            check(lib().scl_pca_bwd_prepared(_p(dy), _p(ctx.prep.shadow), _p(var1), B, Din, Dout, _p(dx), _p(ws), ws.numel(),
+                                             _stream()), "scl_pca_bwd_prepared")
+        else:
+            ws = _pca_ws(B, Din, Dout, dy.device)
+            check(lib().scl_pca_bwd(_p(dy), _p(v2), _p(var1), B, Din, Dout, _p(dx), _p(ws), ws.numel(), _stream()),
+                  "scl_pca_bwd")
         return dx, None, None, None          # v, m, var are fed placeholders, not trained (train.py:647-649)
 
 

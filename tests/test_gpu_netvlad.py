@@ -218,3 +218,45 @@ def test_gemm_engine_all_layouts(cuda_lib, M, N, K, a_mn, b_mn, precision):
     assert float((got - ref).abs().max() / ref.abs().max()) < tol
     if pad(N) != N:
         assert torch.isnan(out[:, N:]).all()               # nothing written past the logical width
+
+
+@pytest.mark.parametrize("B,Din,Dout", [(5, 1000, 72), (130, 4096, 264), (3, 32768, 128)])
+def test_pca_prepared_matches_float64_and_tracks_the_matrix(cuda_lib, measured, B, Din, Dout):
+    """The prepared projection (matrix split once into fp16 hi / lo halves, csrc/tc_gemm_h3.cu) against float64, ragged tile
+    shapes included, forward (matrix K-major) and backward (same shadow read MN-major); the shadow follows in-place updates
+    of the tensor it was built from (version counter) and other tensors never see it."""
+    from soft_contrastive_learning_b200 import netvlad
+    g = torch.Generator(device="cuda").manual_seed(Din + Dout)
+    x = torch.randn((B, Din), generator=g, device="cuda") * torch.logspace(-3, 2, B, device="cuda")[:, None]
+    V = torch.randn((Dout, Din), generator=g, device="cuda") / Din ** 0.5
+    m = 0.1 * torch.randn(Din, generator=g, device="cuda")
+    var = 0.5 + 1.5 * torch.rand(Dout, generator=g, device="cuda")
+    dy = torch.randn((B, Dout), generator=g, device="cuda")
+
+    def run(Vt):
+        xt = x.clone().requires_grad_(True)
+        y = netvlad.pca_project(xt, Vt, m, var)
+        (y * dy).sum().backward()
+        return y.detach(), xt.grad
+
+    def ref(Vt):
+        y = ((x.double() - m.double()) @ Vt.double().t()) / var.double().sqrt()
+        dx = (dy.double() / var.double().sqrt()) @ Vt.double()
+        return y, dx
+
+    assert netvlad._prepared_for(V) is not None            # this shape takes the prepared path
+    y, dx = run(V)
+    yr, dxr = ref(V)
+    rowrel = lambda a, b: float(((a.double() - b).abs().amax(1) / b.abs().amax(1).clamp_min(1e-300)).max())
+    errs = dict(y=rowrel(y, yr), dx=rowrel(dx, dxr))       # per row: the rows span five decades
+    measured(f"pca_prepared_B{B}_{Din}_to_{Dout}", **errs)
+    assert max(errs.values()) < NV_TOL, errs
+    p0 = netvlad._prepared_for(V)
+    assert netvlad._prepared_for(V) is p0                  # cached while unchanged
+    V.mul_(-2.0)                                           # in-place update: the shadow must be rebuilt
+    y2, dx2 = run(V)
+    assert netvlad._prepared_for(V) is not p0
+    yr2, dxr2 = ref(V)
+    assert rowrel(y2, yr2) < NV_TOL and rowrel(dx2, dxr2) < NV_TOL
+    W = V.clone()                                          # another tensor, same shape: its own shadow
+    assert netvlad._prepared_for(W) is not netvlad._prepared_for(V)
