@@ -72,7 +72,13 @@ struct NvFusedArgs {
   float* a;            // [B*HW, 64]
   float* vpart;        // [B][nslots][C*64]
   float* aspart;       // [B][nslots][4][64]
-  const float* wun;    // 2^-ew of the pre-split W
+  const float* wun;    // 2^-e of the pre-split B operand of pass 1: W (one value) / dV[b] (one per image, backward)
+  // backward only
+  const float* a_in;   // [B*HW, 64] soft assignments of the forward
+  const float* dasum;  // [B, 64]
+  float* ds_out;       // [B*HW, 64] d loss / d logits
+  float* rb_out;       // [B*HW] inv^2 * (xh . dxh): the projection term of the l2-normalisation backward
+  const float* dsscale;// [B] power-of-two scale of ds (fp16 range), from a per-image bound
   long long* trace;    // debug: [role][4096] clock stamps of CTA 0
 };
 
@@ -142,8 +148,12 @@ __device__ __forceinline__ void warp_colsum64(const float (&v)[64], int lane, fl
   c1 = t2[1];
 }
 
+// kBwd = false: forward (pass 1: logits, epilogue: soft-max, pass 2: V).  kBwd = true: the first half of the backward with the
+// same skeleton -- pass 1: da = Xn . dV[b] (the per-image dV^T arrives pre-split like W), epilogue: soft-max backward
+// ds = a (g - a.g), g = da + dasum, and the row term of the l2-normalisation backward, pass 2: dW[b] += Xn^T ds.
+template <bool kBwd>
 __global__ void __launch_bounds__(kFThreads, 1)
-    nv_fused_fwd_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+    nv_fused_kernel(const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
                         const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, NvFusedArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -226,8 +236,8 @@ __global__ void __launch_bounds__(kFThreads, 1)
       uint32_t wg = 0;
       // every CTA streams the same 128 KB of W once per tile: kWCopies replicas in global memory spread that over
       // kWCopies times as many L2 lines (and slices)
-      const int wrow = 64 * int(blockIdx.x % kWCopies);
-      for (int u = u0; u < u1; ++u)
+      for (int u = u0; u < u1; ++u) {
+        const int wrow = kBwd ? 64 * (u / g.tpi) : 64 * int(blockIdx.x % kWCopies);
         for (int kc = 0; kc < S1 / 2; ++kc, ++wg) {    // a W chunk covers 64 channels = two stages
           const int slot = wg & 1;
           mbar_wait(&tail->w_empty[slot], ((wg >> 1) & 1) ^ 1);
@@ -239,6 +249,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
           }
           __syncwarp();
         }
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (A operand from tensor memory) =====================
@@ -356,28 +367,69 @@ __global__ void __launch_bounds__(kFThreads, 1)
       }
       mbar_wait(&tail->norm_full, uint32_t(u - u0) & 1);
       const float iv = tail->inv[(u - u0) & 1][row];
-      float m = -INFINITY;
+      float bscale = kScale14;                          // scale of the pass-2 B operand
+      if constexpr (!kBwd) {
+        float m = -INFINITY;
 #pragma unroll
-      for (int k = 0; k < 64; ++k) {
-        acc[k] *= iv;
-        m = fmaxf(m, acc[k]);
+        for (int k = 0; k < 64; ++k) {
+          acc[k] *= iv;
+          m = fmaxf(m, acc[k]);
+        }
+        float s = 0.0f;
+        const float ml2 = m * 1.4426950408889634f;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+          acc[k] = exp2f(fmaf(acc[k], 1.4426950408889634f, -ml2));   // ex2.approx: 2 ulp, the exponent is <= 0
+          s += acc[k];
+        }
+        const float rs = valid ? 1.0f / s : 0.0f;      // rows past the map contribute nothing
+#pragma unroll
+        for (int k = 0; k < 64; ++k) acc[k] *= rs;
+      } else {
+        // acc = Xn . dV[b] (da without the centre path).  g = da + dasum; ds = a (g - a.g);
+        // xh . dxh = sum_k a_k da_k + sum_k ds_k logit_k, and sum_k ds_k = 0 turns the logits into log a_k.
+        bscale = g.dsscale[b];
+        float dot_ag = 0.0f, dot_ada = 0.0f, dot_dsl = 0.0f;
+        const float4* arow = reinterpret_cast<const float4*>(g.a_in + (size_t(b) * g.HW + (valid ? p : 0)) * 64);
+        const float4* das = reinterpret_cast<const float4*>(g.dasum + size_t(b) * 64);
+#pragma unroll
+        for (int k4 = 0; k4 < 16; ++k4) {
+          const float4 a4 = __ldg(arow + k4), d4 = __ldg(das + k4);
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float da = acc[4 * k4 + e] * iv;
+            dot_ada = fmaf(av[e], da, dot_ada);
+            acc[4 * k4 + e] = da + dv[e];               // g
+            dot_ag = fmaf(av[e], acc[4 * k4 + e], dot_ag);
+          }
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 16; ++k4) {               // the row of a again (L1): 64 fewer live registers
+          const float4 a4 = __ldg(arow + k4);
+          const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float ds = valid ? av[e] * (acc[4 * k4 + e] - dot_ag) : 0.0f;
+            acc[4 * k4 + e] = ds;
+            if (av[e] > 0.0f) dot_dsl = fmaf(ds, __logf(av[e]), dot_dsl);
+          }
+        }
+        if (valid) {
+          float* drow = g.ds_out + (size_t(b) * g.HW + p) * 64;
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) st_v8(drow + 8 * k8, acc + 8 * k8);
+          // below the clamp of tf.nn.l2_normalize the normalisation is a pure scale: no projection term
+          g.rb_out[size_t(b) * g.HW + p] = iv >= 1e6f * 0.999f ? 0.0f : iv * iv * (dot_ada + dot_dsl);
+        }
       }
-      float s = 0.0f;
-      const float ml2 = m * 1.4426950408889634f;
-#pragma unroll
-      for (int k = 0; k < 64; ++k) {
-        acc[k] = exp2f(fmaf(acc[k], 1.4426950408889634f, -ml2));   // ex2.approx: 2 ulp, the exponent is <= 0
-        s += acc[k];
-      }
-      const float rs = valid ? 1.0f / s : 0.0f;        // rows past the map contribute nothing
-#pragma unroll
-      for (int k = 0; k < 64; ++k) acc[k] *= rs;
-      // B operand of pass 2: a * 2^14 as fp16 hi / lo, MN-major rows of 128 bytes, chunk ^ (row & 7)
+      // B operand of pass 2: a * 2^14 (forward) / ds * 2^e_b (backward) as fp16 hi / lo, MN-major rows of 128 bytes,
+      // chunk ^ (row & 7)
 #pragma unroll
       for (int j8 = 0; j8 < 8; ++j8) {
         float t[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) t[e] = acc[8 * j8 + e] * kScale14;
+        for (int e = 0; e < 8; ++e) t[e] = acc[8 * j8 + e] * bscale;
         uint4 hi, lo;
         split8(t, hi, lo);
         const uint32_t off = uint32_t(row) * 128u + (uint32_t(j8 ^ (row & 7)) << 4);
@@ -388,13 +440,13 @@ __global__ void __launch_bounds__(kFThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->at_full);
       if (warp == 4 && lane == 0) NV_TRACE(7, u - u0);
-      if (valid) {
-        float* arow = g.a + (size_t(b) * g.HW + p) * 64;
+      if constexpr (!kBwd) {
+        if (valid) {
+          float* arow = g.a + (size_t(b) * g.HW + p) * 64;
 #pragma unroll
-        for (int k8 = 0; k8 < 8; ++k8) st_v8(arow + 8 * k8, acc + 8 * k8);
-        g.inv[size_t(b) * g.HW + p] = iv;
-      }
-      {
+          for (int k8 = 0; k8 < 8; ++k8) st_v8(arow + 8 * k8, acc + 8 * k8);
+          g.inv[size_t(b) * g.HW + p] = iv;
+        }
         float c0, c1;
         warp_colsum64(acc, lane, c0, c1);
         cs0 += c0;
@@ -406,7 +458,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
         mbar_wait(&tail->v_full, vdr & 1);
         tc_fence_after();
         float* vp = g.vpart + (size_t(b) * g.nslots + slot) * g.C * 64;
-        constexpr float kUn = 1.0f / (kScale14 * kScale14);
+        const float kUn = 1.0f / (kScale14 * bscale);
         for (int cg = 0; cg < NCG; ++cg) {
           float* vrow = vp + size_t(cg * 128 + row) * 64;
 #pragma unroll
@@ -423,9 +475,11 @@ __global__ void __launch_bounds__(kFThreads, 1)
             }
           }
         }
-        float* as = g.aspart + ((size_t(b) * g.nslots + slot) * 4 + lq) * 64;
-        *reinterpret_cast<float2*>(as + 2 * lane) = make_float2(cs0, cs1);
-        cs0 = cs1 = 0.0f;
+        if constexpr (!kBwd) {
+          float* as = g.aspart + ((size_t(b) * g.nslots + slot) * 4 + lq) * 64;
+          *reinterpret_cast<float2*>(as + 2 * lane) = make_float2(cs0, cs1);
+          cs0 = cs1 = 0.0f;
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tail->v_empty);
@@ -442,7 +496,6 @@ __global__ void __launch_bounds__(kFThreads, 1)
     const int grp = (warp - 8) >> 2;
     const int lq = warp & 3;
     const int row = lq * 32 + lane;
-    const float wun = __ldg(g.wun);
     const uint32_t tA0 = tmem_base + (uint32_t(lq * 32) << 16) + kFACol0;
     uint32_t sg = 0, wg = 0;
     // A stage's tcgen05.st are left in flight: its A slot is published (wait::st, fence, arrive) only after the loads of
@@ -461,6 +514,7 @@ __global__ void __launch_bounds__(kFThreads, 1)
     for (int u = u0; u < u1; ++u) {
       const int j = u % g.tpi;
       const int par = (u - u0) & 1;
+      const float wun = __ldg(g.wun + (kBwd ? u / g.tpi : 0));
       float ssq = 0.0f;
       // ---- pass 1: this thread's position, the stage's 32 channels = the row's eight 16-byte chunks.  Chunk c of row r
       // sits at c ^ (r & 7): the eight consecutive rows of a quarter-warp read eight different chunk positions, i.e. all
@@ -503,12 +557,14 @@ __global__ void __launch_bounds__(kFThreads, 1)
         // power-of-two scale putting the row's maximum in [2^14, 2^15); rows below 2^-100 are numerically zero
         const uint32_t mb = __float_as_uint(fmaxf(mx, 7.8886090522101181e-31f)) & 0x7f800000u;
         const float sc = __uint_as_float((268u << 23) - mb);
-        if (!(kc & 1)) tail->uns[(wg >> 1) & 3][row] = __uint_as_float(mb - (14u << 23)) * wun;
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) split2(x[2 * e] * sc, x[2 * e + 1] * sc, hi[e], lo[e]);
         mbar_wait(&tail->a_empty[sg & 3], ((sg >> 2) & 1) ^ 1);
         tc_fence_after();
+        // only now: this A slot being free means the MMAs of two pairs back have been issued, hence the flush of the pair
+        // four back -- the previous user of this uns entry -- is over (the landing ring alone would let us run further ahead)
+        if (!(kc & 1)) tail->uns[(wg >> 1) & 3][row] = __uint_as_float(mb - (14u << 23)) * wun;
         const uint32_t tA = tA0 + (sg & 3) * 32;
 #pragma unroll
         for (int qd = 0; qd < 2; ++qd) {                 // 16 channels = 8 TMEM columns of hi and 8 of lo
@@ -686,6 +742,99 @@ __global__ void __launch_bounds__(256, 4) nv_fused_tail_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backward helpers.
+// dV[b] [C,64] fp32 -> dV[b]^T as fp16 hi / lo [64, C] (the B operand of the backward's pass 1) with one power-of-two
+// scale per image, and the power-of-two scale of that image's ds: |ds_k| <= 2 max_k(|dV[:,k]|_2 + |dasum_k|).
+__global__ void __launch_bounds__(256) nv_dv_split_kernel(const float* __restrict__ dV, const float* __restrict__ dasum, int C,
+                                                          __half* __restrict__ dvt_hi, __half* __restrict__ dvt_lo,
+                                                          float* __restrict__ dvun, float* __restrict__ dsscale) {
+  __shared__ float s_col[4][64];
+  __shared__ float s_mx[8];
+  __shared__ float s_t[64][65];
+  __shared__ float s_sc;
+  const int b = blockIdx.x, k = threadIdx.x & 63, g4 = threadIdx.x >> 6;
+  const float* dvb = dV + size_t(b) * C * 64;
+  float mx = 0.0f, ss = 0.0f;
+  for (int c = g4; c < C; c += 4) {
+    const float v = dvb[size_t(c) * 64 + k];
+    mx = fmaxf(mx, fabsf(v));
+    ss = fmaf(v, v, ss);
+  }
+  s_col[g4][k] = ss;
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float m2 = threadIdx.x < 8 ? s_mx[threadIdx.x] : 0.0f;
+    m2 = warp_max(m2);
+    float gb = 0.0f;
+    for (int kk = threadIdx.x; kk < 64; kk += 32)
+      gb = fmaxf(gb, sqrtf((s_col[0][kk] + s_col[1][kk]) + (s_col[2][kk] + s_col[3][kk])) + fabsf(dasum[b * 64 + kk]));
+    gb = warp_max(gb);
+    if (threadIdx.x == 0) {
+      const uint32_t mb = __float_as_uint(fmaxf(m2, 7.8886090522101181e-31f)) & 0x7f800000u;
+      s_sc = __uint_as_float((267u << 23) - mb);                       // max |dV[b]| -> [2^13, 2^14)
+      dvun[b] = __uint_as_float(mb - (13u << 23));
+      const uint32_t gbits = __float_as_uint(fmaxf(gb, 7.8886090522101181e-31f)) & 0x7f800000u;
+      dsscale[b] = __uint_as_float((267u << 23) - gbits);              // 2 G_b * scale < 2^15
+    }
+  }
+  __syncthreads();
+  const float sc = s_sc;
+  for (int c0 = 0; c0 < C; c0 += 64) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int cl = g4 + 4 * i;
+      s_t[cl][k] = dvb[size_t(c0 + cl) * 64 + k] * sc;                  // coalesced along k
+    }
+    __syncthreads();
+    const int kr = threadIdx.x >> 2, cq = (threadIdx.x & 3) * 16;       // row k of the transpose, 16 consecutive channels
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) split2(s_t[cq + 2 * e][kr], s_t[cq + 2 * e + 1][kr], h[e], l[e]);
+    const size_t o = (size_t(b) * 64 + kr) * C + c0 + cq;
+    *reinterpret_cast<uint4*>(dvt_hi + o) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(dvt_hi + o + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4*>(dvt_lo + o) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(dvt_lo + o + 8) = make_uint4(l[4], l[5], l[6], l[7]);
+    __syncthreads();
+  }
+}
+
+// dW[i] = sum over images and their partial slots.  Two levels, fixed order (deterministic): kDwGroups partial sums over
+// contiguous image ranges (many CTAs, eight independent loads in flight per thread), then their sum.
+constexpr int kDwGroups = 16;
+__global__ void __launch_bounds__(256) nv_fused_dw_part_kernel(const float* __restrict__ vpart, int B, int C, int tpi, int units,
+                                                               int G, int nslots, float* __restrict__ part) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 64) return;
+  const int b0 = int((long long)blockIdx.y * B / kDwGroups), b1 = int((long long)(blockIdx.y + 1) * B / kDwGroups);
+  float acc = 0.0f;
+  for (int b = b0; b < b1; ++b) {
+    const int ns = nv_cta_of_unit((long long)b * tpi + tpi - 1, G, units) - nv_cta_of_unit((long long)b * tpi, G, units) + 1;
+    const float* vp = vpart + size_t(b) * nslots * C * 64 + i;
+    float t[8];
+    int s = 0;
+    for (; s + 8 <= ns; s += 8) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = ldg_stream(vp + size_t(s + e) * C * 64);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc += t[e];
+    }
+    for (; s < ns; ++s) acc += ldg_stream(vp + size_t(s) * C * 64);
+  }
+  part[size_t(blockIdx.y) * C * 64 + i] = acc;
+}
+__global__ void __launch_bounds__(256) nv_fused_dw_sum_kernel(const float* __restrict__ part, int C, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 64) return;
+  float acc = 0.0f;
+#pragma unroll
+  for (int gI = 0; gI < kDwGroups; ++gI) acc += part[size_t(gI) * C * 64 + i];
+  dw[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int kFMaxCtas = 160;
 
 static int nv_fused_slots(int B, int tpi) {
@@ -704,12 +853,81 @@ bool nv_fused_ok(int B, int HW, int C, int K) {
   return true;
 }
 
+struct FusedWs {
+  __half *wt_hi, *wt_lo;     // pre-split B operand of pass 1: kWCopies replicas of W^T (forward) / dV[b]^T per image (backward)
+  float *wun, *dsscale, *vpart, *aspart;
+};
+static size_t nv_fused_wt_halfs(int B, int C) { return size_t(64) * C * (B > 2 * kDwGroups ? B : 2 * kDwGroups); }   // also >= kDwGroups x [C,64] floats
+static FusedWs nv_fused_carve(void* ws, size_t ws_bytes, int B, int C, int nslots) {
+  Carver c(ws, ws_bytes);
+  FusedWs w;
+  w.wt_hi = c.take<__half>(nv_fused_wt_halfs(B, C));
+  w.wt_lo = c.take<__half>(nv_fused_wt_halfs(B, C));
+  w.wun = c.take<float>(B);
+  w.dsscale = c.take<float>(B);
+  w.vpart = c.take<float>(size_t(B) * nslots * C * 64);
+  w.aspart = c.take<float>(size_t(B) * nslots * 4 * 64);
+  return w;
+}
+
 size_t nv_fused_ws_bytes(int B, int HW, int C, int K) {
   (void)K;
   const int tpi = (HW + kFM - 1) / kFM;
   const int ns = nv_fused_slots(B, tpi);
-  return 2 * carve_bytes(size_t(kWCopies) * 64 * C, 2) + carve_bytes(1, 4) + carve_bytes(size_t(B) * ns * C * 64, 4) +
+  return 2 * carve_bytes(nv_fused_wt_halfs(B, C), 2) + 2 * carve_bytes(size_t(B), 4) + carve_bytes(size_t(B) * ns * C * 64, 4) +
          carve_bytes(size_t(B) * ns * 4 * 64, 4);
+}
+
+static int nv_fused_launch(bool bwd, const NvFusedArgs& g, const float* x, const __half* wt_hi, const __half* wt_lo, int wrows,
+                           int G, cudaStream_t stream) {
+  CUtensorMap tmX1, tmX2, tmWh, tmWl;
+  int rc;
+  const int B = g.B, HW = g.HW, C = g.C;
+  const uint64_t pitchX = uint64_t(C) * 4, batchX = uint64_t(HW) * C * 4;
+  if ((rc = make_tmap_3d(&tmX1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, uint64_t(C), uint64_t(HW), uint64_t(B), pitchX, batchX, 32, kFM, 0))) return rc;
+  if ((rc = make_tmap_3d(&tmX2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, uint64_t(C), uint64_t(HW), uint64_t(B), pitchX, batchX, 32, 32, 0))) return rc;
+  if ((rc = make_tmap_2d(&tmWh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wt_hi, uint64_t(C), uint64_t(wrows), uint64_t(C) * 2, 64, 64))) return rc;
+  if ((rc = make_tmap_2d(&tmWl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wt_lo, uint64_t(C), uint64_t(wrows), uint64_t(C) * 2, 64, 64))) return rc;
+  const size_t smem = 1024 + size_t(kOffTail) + sizeof(FSmemTail);
+  if (bwd) {
+    static SmemAttrCache configured;
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(nv_fused_kernel<true>), smem, &configured))) return rc;
+    nv_fused_kernel<true><<<G, kFThreads, smem, stream>>>(tmX1, tmX2, tmWh, tmWl, g);
+  } else {
+    static SmemAttrCache configured;
+    if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(nv_fused_kernel<false>), smem, &configured))) return rc;
+    nv_fused_kernel<false><<<G, kFThreads, smem, stream>>>(tmX1, tmX2, tmWh, tmWl, g);
+  }
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+static void nv_fused_trace_begin(NvFusedArgs& g, cudaStream_t stream) {
+  g.trace = nullptr;
+#ifdef SCL_NV_TRACE
+  static long long* s_trace = nullptr;
+  if (!s_trace) cudaMalloc(&s_trace, 8 * 4096 * sizeof(long long));
+  cudaMemsetAsync(s_trace, 0, 8 * 4096 * sizeof(long long), stream);
+  g.trace = s_trace;
+#else
+  (void)stream;
+#endif
+}
+static void nv_fused_trace_end(const NvFusedArgs& g, cudaStream_t stream) {
+#ifdef SCL_NV_TRACE
+  static long long h[8 * 4096];
+  cudaStreamSynchronize(stream);
+  cudaMemcpy(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost);
+  FILE* f = fopen("gpurun_out/nv_trace.txt", "w");
+  if (f) {
+    for (int r = 0; r < 8; ++r)
+      for (int i = 0; i < 4096; ++i)
+        if (h[r * 4096 + i]) fprintf(f, "%d %d %lld\n", r, i, h[r * 4096 + i]);
+    fclose(f);
+  }
+#else
+  (void)g; (void)stream;
+#endif
 }
 
 int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, int B, int HW, int C, float* inv, float* a,
@@ -719,53 +937,50 @@ int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, in
   const long long units = (long long)B * tpi;
   const int G = int(units < num_sms() ? units : num_sms());
   if (G > kFMaxCtas) return SCL_ERR_UNSUPPORTED;
-  Carver c(ws, ws_bytes);
-  NvFusedArgs g;
+  NvFusedArgs g = {};
   g.B = B; g.HW = HW; g.C = C; g.tpi = tpi; g.units = int(units); g.nslots = nv_fused_slots(B, tpi);
-  g.x = x; g.inv = inv; g.a = a;
-  g.trace = nullptr;
-#ifdef SCL_NV_TRACE
-  static long long* s_trace = nullptr;
-  if (!s_trace) cudaMalloc(&s_trace, 8 * 4096 * sizeof(long long));
-  cudaMemsetAsync(s_trace, 0, 8 * 4096 * sizeof(long long), stream);
-  g.trace = s_trace;
-#endif
-  __half* wt_hi = c.take<__half>(size_t(kWCopies) * 64 * C);
-  __half* wt_lo = c.take<__half>(size_t(kWCopies) * 64 * C);
-  float* wun = c.take<float>(1);
-  g.wun = wun;
-  g.vpart = c.take<float>(size_t(B) * g.nslots * C * 64);
-  g.aspart = c.take<float>(size_t(B) * g.nslots * 4 * 64);
-  nv_wprep_kernel<<<dim3(64, kWCopies), 256, 0, stream>>>(assign_w, C, wt_hi, wt_lo, wun);
+  const FusedWs w = nv_fused_carve(ws, ws_bytes, B, C, g.nslots);
+  g.x = x; g.inv = inv; g.a = a; g.vpart = w.vpart; g.aspart = w.aspart; g.wun = w.wun;
+  nv_fused_trace_begin(g, stream);
+  nv_wprep_kernel<<<dim3(64, kWCopies), 256, 0, stream>>>(assign_w, C, w.wt_hi, w.wt_lo, w.wun);
   SCL_LAUNCH_CHECK();
-  CUtensorMap tmX1, tmX2, tmWh, tmWl;
-  int rc;
-  const uint64_t pitchX = uint64_t(C) * 4, batchX = uint64_t(HW) * C * 4;
-  if ((rc = make_tmap_3d(&tmX1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, uint64_t(C), uint64_t(HW), uint64_t(B), pitchX, batchX, 32, kFM, 0))) return rc;
-  if ((rc = make_tmap_3d(&tmX2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, x, uint64_t(C), uint64_t(HW), uint64_t(B), pitchX, batchX, 32, 32, 0))) return rc;
-  if ((rc = make_tmap_2d(&tmWh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wt_hi, uint64_t(C), 64 * kWCopies, uint64_t(C) * 2, 64, 64))) return rc;
-  if ((rc = make_tmap_2d(&tmWl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, wt_lo, uint64_t(C), 64 * kWCopies, uint64_t(C) * 2, 64, 64))) return rc;
-  const size_t smem = 1024 + size_t(kOffTail) + sizeof(FSmemTail);
-  static SmemAttrCache configured;
-  if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(nv_fused_fwd_kernel), smem, &configured))) return rc;
-  nv_fused_fwd_kernel<<<G, kFThreads, smem, stream>>>(tmX1, tmX2, tmWh, tmWl, g);
-  SCL_LAUNCH_CHECK();
+  int rc = nv_fused_launch(false, g, x, w.wt_hi, w.wt_lo, 64 * kWCopies, G, stream);
+  if (rc) return rc;
   nv_fused_tail_kernel<<<B, 256, 0, stream>>>(g.vpart, g.aspart, centers, C, tpi, int(units), G, g.nslots, V, asum, nk, nt, out);
   SCL_LAUNCH_CHECK();
-#ifdef SCL_NV_TRACE
-  {
-    static long long h[8 * 4096];
-    cudaStreamSynchronize(stream);
-    cudaMemcpy(h, g.trace, sizeof(h), cudaMemcpyDeviceToHost);
-    FILE* f = fopen("gpurun_out/nv_trace.txt", "w");
-    if (f) {
-      for (int r = 0; r < 8; ++r)
-        for (int i = 0; i < 4096; ++i)
-          if (h[r * 4096 + i]) fprintf(f, "%d %d %lld\n", r, i, h[r * 4096 + i]);
-      fclose(f);
-    }
+  nv_fused_trace_end(g, stream);
+  return SCL_OK;
+}
+
+// First half of the backward: ds [B*HW,64] (d loss / d logits), rb [B*HW] (row term of the l2-norm backward) and
+// dW [C,64], from x, the forward's soft assignments a, dV [B,C,64] and dasum [B,64].  One pass over x from HBM.
+int nv_fused_bwd(const float* x, const float* a, const float* dV, const float* dasum, int B, int HW, int C, float* ds,
+                 float* rb, float* dW, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  if (ws_bytes < nv_fused_ws_bytes(B, HW, C, 64)) return SCL_ERR_WORKSPACE;
+  const int tpi = (HW + kFM - 1) / kFM;
+  const long long units = (long long)B * tpi;
+  const int G = int(units < num_sms() ? units : num_sms());
+  if (G > kFMaxCtas) return SCL_ERR_UNSUPPORTED;
+  NvFusedArgs g = {};
+  g.B = B; g.HW = HW; g.C = C; g.tpi = tpi; g.units = int(units); g.nslots = nv_fused_slots(B, tpi);
+  const FusedWs w = nv_fused_carve(ws, ws_bytes, B, C, g.nslots);
+  g.x = x; g.vpart = w.vpart; g.aspart = w.aspart; g.wun = w.wun;
+  g.a_in = a; g.dasum = dasum; g.ds_out = ds; g.rb_out = rb; g.dsscale = w.dsscale;
+  nv_fused_trace_begin(g, stream);
+  nv_dv_split_kernel<<<B, 256, 0, stream>>>(dV, dasum, C, w.wt_hi, w.wt_lo, w.wun, w.dsscale);
+  SCL_LAUNCH_CHECK();
+  int rc = nv_fused_launch(true, g, x, w.wt_hi, w.wt_lo, 64 * B, G, stream);
+  if (rc) return rc;
+  if (dW) {
+    // the pre-split dV^T is dead once the fused kernel has run: its buffer holds the level-one partial sums
+    float* part = reinterpret_cast<float*>(w.wt_hi);
+    nv_fused_dw_part_kernel<<<dim3((C * 64 + 255) / 256, kDwGroups), 256, 0, stream>>>(g.vpart, B, C, tpi, int(units), G,
+                                                                                     g.nslots, part);
+    SCL_LAUNCH_CHECK();
+    nv_fused_dw_sum_kernel<<<(C * 64 + 255) / 256, 256, 0, stream>>>(part, C, dW);
+    SCL_LAUNCH_CHECK();
   }
-#endif
+  nv_fused_trace_end(g, stream);
   return SCL_OK;
 }
 

@@ -12,4 +12,9 @@ size_t nv_fused_ws_bytes(int B, int HW, int C, int K);
 int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, int B, int HW, int C, float* inv, float* a,
                  float* V, float* asum, float* nk, float* nt, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
+// first half of the backward (da GEMM, soft-max backward, dW) in one pass over x: ds [B*HW,64], rb [B*HW], dW [C,64] (may be
+// NULL); same extra workspace as the forward
+int nv_fused_bwd(const float* x, const float* a, const float* dV, const float* dasum, int B, int HW, int C, float* ds,
+                 float* rb, float* dW, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 }  // namespace scl

@@ -260,3 +260,34 @@ def test_pca_prepared_matches_float64_and_tracks_the_matrix(cuda_lib, measured, 
     assert rowrel(y2, yr2) < NV_TOL and rowrel(dx2, dxr2) < NV_TOL
     W = V.clone()                                          # another tensor, same shape: its own shadow
     assert netvlad._prepared_for(W) is not netvlad._prepared_for(V)
+
+
+@pytest.mark.parametrize("B,H,W", [(40, 30, 40), (200, 16, 24), (37, 13, 17)])
+def test_netvlad_fused_kernels_against_the_generic_path(cuda_lib, measured, B, H, W):
+    """The one-pass kernels of csrc/netvlad_fused.cu (forward; first half of the backward) against the generic
+    rownorm / GEMM / softmax / GEMM path on batches where a persistent CTA walks several tiles and crosses image
+    boundaries (the per-image accumulators are drained mid-CTA there; the small oracle shapes never do that).  Both paths
+    are fp32-grade, so they agree to ~1e-6; repeated runs are bit-identical (no atomics)."""
+    from soft_contrastive_learning_b200 import _lib, netvlad
+    g = torch.Generator(device="cuda").manual_seed(B)
+    x = torch.randn((B, H, W, 512), generator=g, device="cuda") * (0.1 + 3.0 * torch.rand((B, 1, 1, 1), generator=g, device="cuda"))
+    aw = 0.05 * torch.randn((512, 64), generator=g, device="cuda")
+    cc = 0.05 * torch.randn((512, 64), generator=g, device="cuda")
+    dout = torch.randn((B, 512 * 64), generator=g, device="cuda") * torch.logspace(-2, 1, B, device="cuda")[:, None]
+
+    def run(fused):
+        with _lib.tuning(SCL_NV_FUSED=int(fused)):
+            xt, wt, ct = x.clone().requires_grad_(True), aw.clone().requires_grad_(True), cc.clone().requires_grad_(True)
+            out = netvlad.netVLAD(xt, wt, ct)
+            (out * dout).sum().backward()
+        return out.detach(), xt.grad, wt.grad, ct.grad
+
+    f, r = run(True), run(False)
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    # dx per image: the gradients of the images span three decades
+    dx_err = float(((f[1].double() - r[1].double()).abs().amax((1, 2, 3)) / r[1].double().abs().amax((1, 2, 3))).max())
+    errs = dict(out=rel(f[0], r[0]), dx=dx_err, dW=rel(f[2], r[2]), dC=rel(f[3], r[3]))
+    measured(f"netvlad_fused_vs_generic_B{B}_{H}x{W}", **errs)
+    assert max(errs.values()) < 5e-6, errs
+    f2 = run(True)
+    assert all(torch.equal(a, b) for a, b in zip(f, f2)), "fused kernels are not deterministic"
