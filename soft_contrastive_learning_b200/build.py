@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libscl_b200.so")
-SOURCES = ["runtime.cu", "wms_tuple.cu", "wms_tuple_resident.cu", "wms_tuple_stream.cu", "tuple_losses.cu", "flat_losses.cu", "knn.cu", "knn_tc.cu", "tc_gemm.cu", "tc_gemm_h3.cu", "netvlad.cu", "netvlad_fused.cu"]
+SOURCES = ["runtime.cu", "wms_tuple.cu", "wms_tuple_resident.cu", "wms_tuple_stream.cu", "tuple_losses.cu", "flat_losses.cu", "knn.cu", "knn_tc.cu", "tc_gemm.cu", "tc_gemm_h3.cu", "netvlad.cu", "netvlad_fused.cu", "netvlad_dx.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
 

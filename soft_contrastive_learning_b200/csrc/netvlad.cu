@@ -375,30 +375,14 @@ extern "C" int scl_netvlad_bwd(const float* x, const float* assign_w, const floa
   SCL_LAUNCH_CHECK();
   const int prec = tc_gemm_precision();
   if (nv_fused_ok(B, HW, C, K) && prec == 0 && workspace_bytes >= nv_ws_total(B, HW, C, K)) {
-    // One pass over x (netvlad_fused.cu, the forward's skeleton) replaces the da contraction, the soft-max backward, the
-    // row scaling and the dW contraction with its batch sum: da = Xn dV[b], ds, dW.  dx keeps the generic tail below
-    // ([A | dS] . [dV[b] | W]^T, then the l2-normalisation backward).  (Folding that last kernel into the contraction's
-    // epilogue as  dx = inv * acc - rb * x  was built and measured: the row-per-thread epilogue of tc_gemm.cu becomes
-    // latency-bound on the x loads, 0.75 ms against 0.42 + 0.27 ms; the fused kernel still leaves rb in the workspace.)
+    // Two kernels, one pass over x each.  netvlad_fused.cu (the forward's skeleton): da = Xn dV[b], the soft-max backward,
+    // the row term of the l2-normalisation backward, dW.  netvlad_dx.cu: dx = inv ([A | dS] . [dV[b] | W]^T) - rb x on
+    // operands that are already fp16 hi / lo halves, through a shared-memory tile (TMA in, TMA out).
+    if (dx && !aligned16(dx)) return SCL_ERR_ALIGN;
     const size_t base = nv_ws_bytes(B, HW, C, K);
-    rc = nv_fused_bwd(x, w.a, w.dV, w.dasum, B, HW, C, w.da, w.rb, dassign_w, static_cast<char*>(workspace) + base,
+    rc = nv_fused_bwd(x, w.a, w.inv, w.dV, w.dasum, B, HW, C, w.da, w.rb, dassign_w, dx, static_cast<char*>(workspace) + base,
                       workspace_bytes - base, stream);
-    if (rc != SCL_ERR_UNSUPPORTED) {
-      if (rc) return rc;
-      if (dx) {
-        if (!aligned16(dx)) return SCL_ERR_ALIGN;
-        TcGemmDesc e = {};
-        e.A = w.a; e.B = w.dV; e.C = dx; e.M = HW; e.N = C; e.K = K; e.lda = K; e.ldb = K; e.ldc = C;
-        e.a_mn = false; e.b_mn = false; e.precision = prec;
-        e.batch = B; e.sA = (long long)HW * K; e.sB = (long long)C * K; e.sC = (long long)HW * C;
-        e.A2 = w.da; e.B2 = assign_w; e.K2 = K; e.sB2 = 0;
-        rc = tc_gemm(e, stream);
-        if (rc) return rc;
-        nv_l2norm_bwd_kernel<<<unsigned((P + 7) / 8), 256, 0, stream>>>(x, w.inv, P, C, dx);
-        SCL_LAUNCH_CHECK();
-      }
-      return SCL_OK;
-    }
+    if (rc != SCL_ERR_UNSUPPORTED) return rc;
   }
   // da[b] = (X[b] dV[b]) * inv[row]      M = HW, N = K, contraction over C; dV[b] [C,K] read MN-major
   {

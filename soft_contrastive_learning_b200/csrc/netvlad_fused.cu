@@ -79,6 +79,9 @@ struct NvFusedArgs {
   float* ds_out;       // [B*HW, 64] d loss / d logits
   float* rb_out;       // [B*HW] inv^2 * (xh . dxh): the projection term of the l2-normalisation backward
   const float* dsscale;// [B] power-of-two scale of ds (fp16 range), from a per-image bound
+  // both directions: the pass-2 B operand (a * 2^14 / ds * dsscale[b]) as fp16 hi / lo rows [B*HW, 64] for netvlad_dx.cu
+  __half* t_hi;
+  __half* t_lo;
   long long* trace;    // debug: [role][4096] clock stamps of CTA 0
 };
 
@@ -435,6 +438,11 @@ __global__ void __launch_bounds__(kFThreads, 1)
         const uint32_t off = uint32_t(row) * 128u + (uint32_t(j8 ^ (row & 7)) << 4);
         *reinterpret_cast<uint4*>(at + off) = hi;
         *reinterpret_cast<uint4*>(at + 16384 + off) = lo;
+        if (valid && g.t_hi) {                          // the same halves, row-major, for the dx contraction
+          const size_t o = (size_t(b) * g.HW + p) * 64 + 8 * j8;
+          *reinterpret_cast<uint4*>(g.t_hi + o) = hi;
+          *reinterpret_cast<uint4*>(g.t_lo + o) = lo;
+        }
       }
       fence_proxy_async();
       __syncwarp();
@@ -643,7 +651,8 @@ __global__ void __launch_bounds__(kFThreads, 1)
 // W [C,64] fp32 -> W^T as fp16 hi / lo [64, C] (K-major rows for the B operand of pass 1) with one power-of-two scale.
 // One CTA per cluster (row of W^T); every CTA finds the global maximum itself (128 KB, L2-resident): no second launch.
 __global__ void __launch_bounds__(256) nv_wprep_kernel(const float* __restrict__ w, int C, __half* __restrict__ wt_hi,
-                                                       __half* __restrict__ wt_lo, float* __restrict__ wun) {
+                                                       __half* __restrict__ wt_lo, float* __restrict__ wun,
+                                                       __half* __restrict__ ws_hi, __half* __restrict__ ws_lo) {
   __shared__ float s_mx[8];
   float mx = 0.0f;
   const float4* w4 = reinterpret_cast<const float4*>(w);
@@ -664,8 +673,13 @@ __global__ void __launch_bounds__(256) nv_wprep_kernel(const float* __restrict__
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float xs = __ldg(w + size_t(c) * 64 + k) * sc;
     const __half h = __float2half_rn(xs);
+    const __half l = __float2half_rn(xs - __half2float(h));
     wt_hi[copy + size_t(k) * C + c] = h;
-    wt_lo[copy + size_t(k) * C + c] = __float2half_rn(xs - __half2float(h));
+    wt_lo[copy + size_t(k) * C + c] = l;
+    if (blockIdx.y == 0 && ws_hi) {                     // and once in the [C,64] layout (B operand of netvlad_dx.cu)
+      ws_hi[size_t(c) * 64 + k] = h;
+      ws_lo[size_t(c) * 64 + k] = l;
+    }
   }
 }
 
@@ -747,7 +761,8 @@ __global__ void __launch_bounds__(256, 4) nv_fused_tail_kernel(const float* __re
 // scale per image, and the power-of-two scale of that image's ds: |ds_k| <= 2 max_k(|dV[:,k]|_2 + |dasum_k|).
 __global__ void __launch_bounds__(256) nv_dv_split_kernel(const float* __restrict__ dV, const float* __restrict__ dasum, int C,
                                                           __half* __restrict__ dvt_hi, __half* __restrict__ dvt_lo,
-                                                          float* __restrict__ dvun, float* __restrict__ dsscale) {
+                                                          float* __restrict__ dvun, float* __restrict__ dsscale,
+                                                          __half* __restrict__ dvs_hi, __half* __restrict__ dvs_lo) {
   __shared__ float s_col[4][64];
   __shared__ float s_mx[8];
   __shared__ float s_t[64][65];
@@ -781,6 +796,12 @@ __global__ void __launch_bounds__(256) nv_dv_split_kernel(const float* __restric
   }
   __syncthreads();
   const float sc = s_sc;
+  for (int c = g4; c < C; c += 4) {                     // [C,64] layout: B operand of netvlad_dx.cu
+    const float xs = dvb[size_t(c) * 64 + k] * sc;
+    const __half hh = __float2half_rn(xs);
+    dvs_hi[(size_t(b) * C + c) * 64 + k] = hh;
+    dvs_lo[(size_t(b) * C + c) * 64 + k] = __float2half_rn(xs - __half2float(hh));
+  }
   for (int c0 = 0; c0 < C; c0 += 64) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -856,9 +877,13 @@ bool nv_fused_ok(int B, int HW, int C, int K) {
 struct FusedWs {
   __half *wt_hi, *wt_lo;     // pre-split B operand of pass 1: kWCopies replicas of W^T (forward) / dV[b]^T per image (backward)
   float *wun, *dsscale, *vpart, *aspart;
+  __half *a_hi, *a_lo, *ds_hi, *ds_lo;   // [B*HW,64] pass-2 B operands kept for the dx contraction
+  __half *dvs_hi, *dvs_lo;               // [B,C,64]
+  __half *ws_hi, *ws_lo;                 // [C,64]
+  float* wun_s;                          // 2^-e of W, kept from the forward
 };
 static size_t nv_fused_wt_halfs(int B, int C) { return size_t(64) * C * (B > 2 * kDwGroups ? B : 2 * kDwGroups); }   // also >= kDwGroups x [C,64] floats
-static FusedWs nv_fused_carve(void* ws, size_t ws_bytes, int B, int C, int nslots) {
+static FusedWs nv_fused_carve(void* ws, size_t ws_bytes, int B, int HW, int C, int nslots) {
   Carver c(ws, ws_bytes);
   FusedWs w;
   w.wt_hi = c.take<__half>(nv_fused_wt_halfs(B, C));
@@ -867,6 +892,15 @@ static FusedWs nv_fused_carve(void* ws, size_t ws_bytes, int B, int C, int nslot
   w.dsscale = c.take<float>(B);
   w.vpart = c.take<float>(size_t(B) * nslots * C * 64);
   w.aspart = c.take<float>(size_t(B) * nslots * 4 * 64);
+  w.a_hi = c.take<__half>(size_t(B) * HW * 64);
+  w.a_lo = c.take<__half>(size_t(B) * HW * 64);
+  w.ds_hi = c.take<__half>(size_t(B) * HW * 64);
+  w.ds_lo = c.take<__half>(size_t(B) * HW * 64);
+  w.dvs_hi = c.take<__half>(size_t(B) * C * 64);
+  w.dvs_lo = c.take<__half>(size_t(B) * C * 64);
+  w.ws_hi = c.take<__half>(size_t(C) * 64);
+  w.ws_lo = c.take<__half>(size_t(C) * 64);
+  w.wun_s = c.take<float>(1);
   return w;
 }
 
@@ -875,7 +909,8 @@ size_t nv_fused_ws_bytes(int B, int HW, int C, int K) {
   const int tpi = (HW + kFM - 1) / kFM;
   const int ns = nv_fused_slots(B, tpi);
   return 2 * carve_bytes(nv_fused_wt_halfs(B, C), 2) + 2 * carve_bytes(size_t(B), 4) + carve_bytes(size_t(B) * ns * C * 64, 4) +
-         carve_bytes(size_t(B) * ns * 4 * 64, 4);
+         carve_bytes(size_t(B) * ns * 4 * 64, 4) + 4 * carve_bytes(size_t(B) * HW * 64, 2) + 2 * carve_bytes(size_t(B) * C * 64, 2) +
+         2 * carve_bytes(size_t(C) * 64, 2) + carve_bytes(1, 4);
 }
 
 static int nv_fused_launch(bool bwd, const NvFusedArgs& g, const float* x, const __half* wt_hi, const __half* wt_lo, int wrows,
@@ -939,10 +974,11 @@ int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, in
   if (G > kFMaxCtas) return SCL_ERR_UNSUPPORTED;
   NvFusedArgs g = {};
   g.B = B; g.HW = HW; g.C = C; g.tpi = tpi; g.units = int(units); g.nslots = nv_fused_slots(B, tpi);
-  const FusedWs w = nv_fused_carve(ws, ws_bytes, B, C, g.nslots);
-  g.x = x; g.inv = inv; g.a = a; g.vpart = w.vpart; g.aspart = w.aspart; g.wun = w.wun;
+  const FusedWs w = nv_fused_carve(ws, ws_bytes, B, HW, C, g.nslots);
+  g.x = x; g.inv = inv; g.a = a; g.vpart = w.vpart; g.aspart = w.aspart; g.wun = w.wun_s;
+  g.t_hi = w.a_hi; g.t_lo = w.a_lo;
   nv_fused_trace_begin(g, stream);
-  nv_wprep_kernel<<<dim3(64, kWCopies), 256, 0, stream>>>(assign_w, C, w.wt_hi, w.wt_lo, w.wun);
+  nv_wprep_kernel<<<dim3(64, kWCopies), 256, 0, stream>>>(assign_w, C, w.wt_hi, w.wt_lo, w.wun_s, w.ws_hi, w.ws_lo);
   SCL_LAUNCH_CHECK();
   int rc = nv_fused_launch(false, g, x, w.wt_hi, w.wt_lo, 64 * kWCopies, G, stream);
   if (rc) return rc;
@@ -954,8 +990,8 @@ int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, in
 
 // First half of the backward: ds [B*HW,64] (d loss / d logits), rb [B*HW] (row term of the l2-norm backward) and
 // dW [C,64], from x, the forward's soft assignments a, dV [B,C,64] and dasum [B,64].  One pass over x from HBM.
-int nv_fused_bwd(const float* x, const float* a, const float* dV, const float* dasum, int B, int HW, int C, float* ds,
-                 float* rb, float* dW, void* ws, size_t ws_bytes, cudaStream_t stream) {
+int nv_fused_bwd(const float* x, const float* a, const float* inv, const float* dV, const float* dasum, int B, int HW, int C,
+                 float* ds, float* rb, float* dW, float* dx, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (ws_bytes < nv_fused_ws_bytes(B, HW, C, 64)) return SCL_ERR_WORKSPACE;
   const int tpi = (HW + kFM - 1) / kFM;
   const long long units = (long long)B * tpi;
@@ -963,11 +999,12 @@ int nv_fused_bwd(const float* x, const float* a, const float* dV, const float* d
   if (G > kFMaxCtas) return SCL_ERR_UNSUPPORTED;
   NvFusedArgs g = {};
   g.B = B; g.HW = HW; g.C = C; g.tpi = tpi; g.units = int(units); g.nslots = nv_fused_slots(B, tpi);
-  const FusedWs w = nv_fused_carve(ws, ws_bytes, B, C, g.nslots);
+  const FusedWs w = nv_fused_carve(ws, ws_bytes, B, HW, C, g.nslots);
   g.x = x; g.vpart = w.vpart; g.aspart = w.aspart; g.wun = w.wun;
   g.a_in = a; g.dasum = dasum; g.ds_out = ds; g.rb_out = rb; g.dsscale = w.dsscale;
+  g.t_hi = w.ds_hi; g.t_lo = w.ds_lo;
   nv_fused_trace_begin(g, stream);
-  nv_dv_split_kernel<<<B, 256, 0, stream>>>(dV, dasum, C, w.wt_hi, w.wt_lo, w.wun, w.dsscale);
+  nv_dv_split_kernel<<<B, 256, 0, stream>>>(dV, dasum, C, w.wt_hi, w.wt_lo, w.wun, w.dsscale, w.dvs_hi, w.dvs_lo);
   SCL_LAUNCH_CHECK();
   int rc = nv_fused_launch(true, g, x, w.wt_hi, w.wt_lo, 64 * B, G, stream);
   if (rc) return rc;
@@ -979,6 +1016,13 @@ int nv_fused_bwd(const float* x, const float* a, const float* dV, const float* d
     SCL_LAUNCH_CHECK();
     nv_fused_dw_sum_kernel<<<(C * 64 + 255) / 256, 256, 0, stream>>>(part, C, dW);
     SCL_LAUNCH_CHECK();
+  }
+  if (dx) {
+    // second half (netvlad_dx.cu): every operand is already there as fp16 hi / lo halves -- a from the forward's epilogue,
+    // ds from the kernel above, dV[b] and W from their split kernels
+    rc = nv_dx(x, w.a_hi, w.a_lo, w.ds_hi, w.ds_lo, w.dvs_hi, w.dvs_lo, w.ws_hi, w.ws_lo, inv, rb, w.wun, w.dsscale, w.wun_s, B,
+               HW, C, dx, stream);
+    if (rc) return rc;
   }
   nv_fused_trace_end(g, stream);
   return SCL_OK;

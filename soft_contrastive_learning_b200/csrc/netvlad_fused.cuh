@@ -1,5 +1,7 @@
 // netvlad_fused.cuh -- interface of the fused NetVLAD kernels (netvlad_fused.cu) used by netvlad.cu.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace scl {
@@ -12,9 +14,14 @@ size_t nv_fused_ws_bytes(int B, int HW, int C, int K);
 int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, int B, int HW, int C, float* inv, float* a,
                  float* V, float* asum, float* nk, float* nt, float* out, void* ws, size_t ws_bytes, cudaStream_t stream);
 
-// first half of the backward (da GEMM, soft-max backward, dW) in one pass over x: ds [B*HW,64], rb [B*HW], dW [C,64] (may be
-// NULL); same extra workspace as the forward
-int nv_fused_bwd(const float* x, const float* a, const float* dV, const float* dasum, int B, int HW, int C, float* ds,
-                 float* rb, float* dW, void* ws, size_t ws_bytes, cudaStream_t stream);
+// the backward in two kernels, one pass over x each: ds [B*HW,64] (d loss / d logits), rb [B*HW] (row term of the
+// l2-normalisation backward), dW [C,64] and dx [B,HW,C] (either may be NULL); same extra workspace as the forward, which
+// must have been run on it (it leaves the fp16 halves of the soft assignments and of W there)
+int nv_fused_bwd(const float* x, const float* a, const float* inv, const float* dV, const float* dasum, int B, int HW, int C,
+                 float* ds, float* rb, float* dW, float* dx, void* ws, size_t ws_bytes, cudaStream_t stream);
+// netvlad_dx.cu
+int nv_dx(const float* x, const __half* a_hi, const __half* a_lo, const __half* ds_hi, const __half* ds_lo, const __half* dv_hi,
+          const __half* dv_lo, const __half* w_hi, const __half* w_lo, const float* inv, const float* rb, const float* dvun,
+          const float* dsscale, const float* wun, int B, int HW, int C, float* dx, cudaStream_t stream);
 
 }  // namespace scl
