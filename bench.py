@@ -662,7 +662,8 @@ def bench_netvlad_pca(args, torch, pk, B=256, H=30, W=40, Cc=512, K=64, Dout=409
             "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                          "frac": ach / pk["tf_sustained"], "peak_source": pk["source"] + " cuBLAS bf16 sustained (no tf32 peak measured; "
                          "kind::tf32 is nominally half the bf16 rate and the fp32-grade mode issues 3 MMAs per product)",
-                         "algorithmic_flops_per_step": tot_flops, "kernel": "tc_gemm_kernel", "traffic": None,
+                         "algorithmic_flops_per_step": tot_flops,
+                         "kernel": "nv_fused_kernel<0/1>, nv_dx_kernel, tc_gemm_h3_kernel", "traffic": None,
                          "hbm_view": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_gbs": hbm_gbs, "peak_gbs": pk["hbm_gbs"],
                                       "frac": hbm_gbs / pk["hbm_gbs"],
                                       "note": "with fp32 X the step is HBM-bound, not tensor-bound (SURVEY 8d): this is the binding roofline"}},
@@ -775,6 +776,13 @@ def main():
                     return r
                 w = secondary(bench_wms, args, torch, pk)
                 if "error" not in w:
+                    # metric B of BASELINE.json as a top-level object (the same numbers also sit in `config` as flat keys)
+                    line["wms"] = {"t4096": {"tuples_per_s": w["value"], "ms_per_step": w["ms_per_step"], "roofline": w["roofline"],
+                                             "e2e": w["e2e"], "cpu_baseline": w["cpu_baseline"]},
+                                   "config1_t32": {"us_per_launch": w["config"]["config1_T32_us_per_launch"],
+                                                   "us_per_launch_cuda_graph": w["config"]["config1_T32_us_per_launch_cuda_graph"],
+                                                   "tuples_per_s": w["config"]["config1_T32_tuples_per_s"],
+                                                   "hbm_frac_cuda_graph": w["config"]["config1_T32_hbm_frac_cuda_graph"]}}
                     cfg.update({"wms_t4096_tuples_per_s": w["value"], "wms_t4096_ms": w["ms_per_step"],
                                 "wms_t4096_hbm_frac": w["roofline"]["frac"],
                                 "wms_config1_t32_us_per_launch": w["config"]["config1_T32_us_per_launch"],

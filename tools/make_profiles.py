@@ -5,7 +5,7 @@
 
 launch list  -> profiles/<tag>_launch_list_summary.txt   (per-kernel totals and shares of the default bench step)
 clocks.csv   -> profiles/<tag>_clocks_summary.txt
-*.ncu-rep    -> profiles/<tag>_ncu_{knn_tc,wms,gemm}.txt  (tools/ncu_digest.py)
+*.ncu-rep    -> profiles/<tag>_ncu_{knn_tc,wms,netvlad_fused_fwd,netvlad_fused_bwd,netvlad_dx,gemm_h3_pca}.txt  (tools/ncu_digest.py)
 bench line   -> profiles/<tag>_bench_full_n1.json
 """
 import collections, csv, os, shutil, statistics, subprocess, sys
@@ -84,7 +84,9 @@ def clocks(tag):
 
 
 def digests(tag):
-    for rep, name in (("prof_knn_tc", "ncu_knn_tc"), ("prof_wms", "ncu_wms"), ("prof_gemm", "ncu_gemm")):
+    for rep, name in (("prof_knn_tc", "ncu_knn_tc"), ("prof_wms", "ncu_wms"), ("prof_gemm", "ncu_gemm"),
+                      ("prof_nvfwd", "ncu_netvlad_fused_fwd"), ("prof_nvbwd", "ncu_netvlad_fused_bwd"),
+                      ("prof_nvdx", "ncu_netvlad_dx"), ("prof_h3", "ncu_gemm_h3_pca")):
         path = os.path.join(OUT, rep + ".ncu-rep")
         if os.path.exists(path):
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_digest.py"), path], capture_output=True, text=True).stdout

@@ -19,6 +19,10 @@ WANT = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data pipe, LSU %"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "L1 data pipe, tensor-core operand reads %"),
+    ("sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor-core unit busy %"),
+    ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", "alu pipe active %"),
     ("launch__registers_per_thread", "registers/thread"),
     ("launch__shared_mem_per_block_dynamic", "dyn smem/block"),
     ("launch__grid_size", "grid"),
