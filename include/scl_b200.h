@@ -229,7 +229,8 @@ int scl_gemm_tf32(const float* A, const float* B, float* C, int M, int N, int K,
  *                          bound, or resolved by the second tensor stage (all rows inside the bound collected and
  *                          rescored), or recomputed by the exact fp32->fp64 scan.
  *                          stats (optional, device i32[8]): {n_queries, n_certified, n_refused by the first pass,
- *                          path, n_resolved_by_stage2, n_exact_scan, pipeline_chunks, 0}
+ *                          path, n_resolved_by_stage2, n_exact_scan, pipeline_chunks, n_settled_by_the_bound
+ *                          (scl_knn_query_end only)}
  *   force_path: 0 auto, 1 exact scan only, 2 tensor pass (+ stage 2 / scan as needed), 3 tensor pass with every query
  *               forced through the exact scan as well, 4 ... through stage 2 as well (test hooks).
  * Requires D % 4 == 0, k <= 1024.  The tensor pass keeps k' = 64 candidates per query and needs slack above k: it is
@@ -245,6 +246,31 @@ int scl_knn_query_workspace_bytes(int64_t R, int D, int Q, int k, size_t* bytes)
 int scl_knn_query(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
                   int64_t idx_offset, int force_path, double* dist, int64_t* idx, int32_t* stats,
                   void* workspace, size_t workspace_bytes, scl_stream_t stream);
+
+/* Sharded retrieval in two phases (the all-gather + merge of evaluation/top-n.py:106's one query
+ * call when the database rows are split over the GPUs of a box).  A rank's exact rescore of k..64 candidates per query
+ * does not shrink with its shard, and of the G*k rows the ranks return only k survive the merge.  Split in two:
+ *   scl_knn_query_begin   tensor pass + candidate selection; ub (device f32 [Q,k], ascending per query) = upper bounds,
+ *                         in the units of |r|^2 - 2 q.r, on the exact distances of this shard's k best candidates
+ *                         (+inf where it has fewer).  Asynchronous on `stream`.
+ *   -- the caller all-gathers `ub` over the ranks ([G,Q,k], 4*Q*k bytes per rank) --
+ *   scl_knn_bound_reduce  bound[q] = k-th smallest of the G*k gathered values: k rows of the whole database are at or
+ *                         below it.
+ *   scl_knn_query_end     given that bound, rescores only the candidates of this shard that can still be among the
+ *                         GLOBAL k nearest and returns them sorted by (distance, index); the rest of the k slots is
+ *                         padded with (inf, -1).  Merged over the ranks (scl_topk_merge) the lists give the exact global
+ *                         top-k, ties by index: every row left out is STRICTLY farther than k other rows.  Queries whose
+ *                         shard holds more than 64 rows inside the bound fall back to the exact local top-k of
+ *                         scl_knn_query (certificate / second tensor stage / exact scan).  Same workspace (and the SAME
+ *                         workspace contents: no other call on it in between), shadow, queries and sizes as `begin`.
+ * SCL_ERR_UNSUPPORTED when this shard's sizes do not take the tensor pass (see scl_knn_query): such a rank contributes
+ * +inf to the gather and calls scl_knn_query instead.  stats as in scl_knn_query. */
+int scl_knn_query_begin(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                        float* ub, void* workspace, size_t workspace_bytes, scl_stream_t stream);
+int scl_knn_bound_reduce(const float* ub_all, int G, int Q, int k, float* bound, scl_stream_t stream);
+int scl_knn_query_end(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                      int64_t idx_offset, const float* bound, double* dist, int64_t* idx, int32_t* stats,
+                      void* workspace, size_t workspace_bytes, scl_stream_t stream);
 
 /* Test hook: when set (per host thread) and capacity_floats >= Q*R, the tensor pass of the following scl_knn_query
  * calls on this thread also writes its raw fp16-pass scores [Q,R] there.  NULL switches it off. */

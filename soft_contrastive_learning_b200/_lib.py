@@ -82,6 +82,11 @@ PROTOTYPES = {
     "scl_knn_query_workspace_bytes": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.c_int, _SIZE_P]),
     "scl_knn_query": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int64, C.c_int, c_ptr,
                                 c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "scl_knn_query_begin": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t,
+                                      c_ptr]),
+    "scl_knn_bound_reduce": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "scl_knn_query_end": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int64, c_ptr, c_ptr,
+                                    c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_knn_timing": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "scl_knn_set_debug_scores": (C.c_int, [c_ptr, C.c_size_t]),
     "scl_topk_merge": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int64, c_ptr, c_ptr, c_ptr]),

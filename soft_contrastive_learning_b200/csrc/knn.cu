@@ -198,7 +198,13 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
                                                              const double* __restrict__ qn2, const int* __restrict__ qexp,
                                                              const ShadowHeader* __restrict__ h,
                                                              uint32_t* __restrict__ sel_idx, float* __restrict__ sel_T,
-                                                             int* __restrict__ sel_n) {
+                                                             int* __restrict__ sel_n, float* __restrict__ sel_score,
+                                                             float* __restrict__ bound_out) {
+  // sel_score / bound_out != nullptr: first phase of the sharded two-phase query (scl_knn_query_begin): every one of
+  // the kKeep best candidates is kept with its fp16 score (the cut is applied later, against the bound the ranks agree
+  // on), and bound_out[q, j] = s_j + eps for the k best (ascending): each an upper bound, in score units, on the exact
+  // distance of one actual row of this shard (+inf where the shard has fewer).
+  const bool two_phase = sel_score != nullptr;
   __shared__ unsigned long long mkeys[kMergeCap];
   __shared__ int s_cnt[64];
   __shared__ int s_hist[256];
@@ -296,7 +302,15 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   const float t_sel = kept >= kKeep ? key64_score(mkeys[kKeep - 1]) : INFINITY;
   float T = fminf(t_sel, t_pub);
   int n_sel = kept < kKeep ? kept : kKeep;
-  if (total > k && (long long)total < h->R) {
+  if (two_phase) {
+    if (threadIdx.x < kKeep)
+      sel_score[size_t(q) * kKeep + threadIdx.x] = threadIdx.x < n_sel ? key64_score(mkeys[threadIdx.x]) : INFINITY;
+    if (threadIdx.x == 0) s_cut = knn_eps(sqrt(qn2[q]), qexp[q], h);
+    __syncthreads();
+    if (threadIdx.x < k)                                // rounded up: a larger bound only keeps more candidates
+      bound_out[size_t(q) * k + threadIdx.x] = (threadIdx.x < n_sel && !overflow)
+          ? __double2float_ru(double(key64_score(mkeys[threadIdx.x])) + s_cut) : INFINITY;
+  } else if (total > k && (long long)total < h->R) {
     if (threadIdx.x == 0) {                            // float64 evaluation of the bound: one thread, not 256
       s_need = 0;
       s_cut = double(key64_score(mkeys[k - 1])) + 2.0 * knn_eps(sqrt(qn2[q]), qexp[q], h);
@@ -356,7 +370,7 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __res
                                                            int Q, int k, long long idx_offset, int force_all, int q0,
                                                            double* __restrict__ out_d, long long* __restrict__ out_i,
                                                            double* __restrict__ kth_d2, int* __restrict__ flag_list,
-                                                           int* __restrict__ stats) {
+                                                           int* __restrict__ stats, const int* __restrict__ cut_mode) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
@@ -374,7 +388,8 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __res
       const double od = __shfl_sync(0xffffffffu, md[su], src);
       const uint32_t oi = __shfl_sync(0xffffffffu, mi[su], src);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) rank[u] += (od < md[u] || (od == md[u] && oi < mi[u])) ? 1 : 0;
+      for (int u = 0; u < 2; ++u)           // empty slots (all idx 0xffffffff, d2 inf) are ordered by position
+        rank[u] += (od < md[u] || (od == md[u] && (oi < mi[u] || (oi == mi[u] && src + 32 * su < lane + 32 * u)))) ? 1 : 0;
     }
   }
   double kth = INFINITY;
@@ -397,6 +412,9 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __res
       const double eps = knn_eps(sqrt(qn2[q]), qexp[q], h);
       ok = kth < double(sel_T[q]) + qn2[q] - eps;
     }
+    // two-phase query: the cutoff kernel has already established that every row of this shard that can be in the GLOBAL
+    // top-k was rescored (knn_apply_cutoff_kernel); the list may then hold fewer than k rows
+    if (cut_mode != nullptr && cut_mode[q]) ok = true;
     if (force_all) ok = false;
     kth_d2[q] = kth;                                // k-th smallest exact d^2 among the rescored candidates (inf: fewer than k)
     if (ok) {
@@ -405,6 +423,71 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __res
       const int slot = atomicAdd(&stats[2], 1);
       flag_list[slot] = q0 + q;                     // all pointers of this launch are chunk-relative; the list is global
     }
+  }
+}
+
+// Two-phase (sharded) query, between the phases: ub_all [G,Q,k] = the ranks' per-query lists of upper bounds (ascending,
+// each the bound of one actual row); bound[q] = the k-th smallest of the G*k values: k distinct rows of the database have an
+// exact distance at or below it.  One warp per query; every element finds its rank in the union by binary search in
+// the other lists (ties: by list, then position), the one of rank k-1 is the answer.
+__global__ void __launch_bounds__(256) knn_bound_reduce_kernel(const float* __restrict__ ub_all, int G, int Q, int k,
+                                                               float* __restrict__ bound) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  for (int e = lane; e < G * k; e += 32) {
+    const int g = e / k, j = e - g * k;
+    const float v = ub_all[(size_t(g) * Q + q) * k + j];
+    int rank = j;
+    for (int g2 = 0; g2 < G && rank < k; ++g2) {
+      if (g2 == g) continue;
+      const float* l = ub_all + (size_t(g2) * Q + q) * k;
+      int lo = 0, hi = k;              // entries of list g2 ordered before (v, g): < v, or == v when g2 < g
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float o = l[mid];
+        if (o < v || (o == v && g2 < g)) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank == k - 1) bound[q] = v;
+  }
+}
+
+// Two-phase (sharded) query, second phase.  bound[q] as above (each rank's k best fp16 scores + its eps, k-th smallest
+// of the union): at least k rows somewhere have an exact distance <= bound (score units), so a row of THIS shard whose fp16 score exceeds
+// cut = bound + eps_here is strictly farther than k rows and cannot be in the global top-k.  If the shard's bound on
+// everything that is NOT a candidate (sel_T) also exceeds the cut, the candidates at or below it are all this shard can
+// contribute: they alone are rescored (a few per query at 8 shards instead of k..64) and the query is certified here.
+// Otherwise (more than kKeep rows of the shard inside the cut) the query keeps every candidate and goes through the
+// single-rank certificate / fallback chain, which returns its exact local top-k.
+__global__ void __launch_bounds__(256) knn_apply_cutoff_kernel(const float* __restrict__ bound, const float* __restrict__ sel_score,
+                                                               const float* __restrict__ sel_T, const int* __restrict__ sel_n,
+                                                               const double* __restrict__ qn2, const int* __restrict__ qexp,
+                                                               const ShadowHeader* __restrict__ h, int Q,
+                                                               uint32_t* __restrict__ sel_idx, int* __restrict__ cut_mode,
+                                                               int* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  float cut = INFINITY;
+  if (lane == 0) {
+    const float b = bound[q];
+    if (isfinite(b)) cut = __double2float_ru(double(b) + knn_eps(sqrt(qn2[q]), qexp[q], h));
+  }
+  cut = __shfl_sync(0xffffffffu, cut, 0);
+  const bool all_rows = sel_n[q] <= kKeep && (long long)sel_n[q] >= h->R;    // every row of the shard is a candidate
+  const bool mode = isfinite(cut) && (sel_T[q] > cut || all_rows);
+  if (mode) {
+#pragma unroll
+    for (int u = 0; u < kKeep / 32; ++u) {
+      const int t = lane + 32 * u;
+      if (sel_score[size_t(q) * kKeep + t] > cut) sel_idx[size_t(q) * kKeep + t] = 0xffffffffu;
+    }
+  }
+  if (lane == 0) {
+    cut_mode[q] = mode ? 1 : 0;
+    if (mode) atomicAdd(&stats[7], 1);
   }
 }
 
@@ -801,6 +884,8 @@ struct QueryWs {
   int* sel_n;
   double* d2;
   double* kth_d2;
+  float* sel_score;
+  int* cut_mode;
   int* flag_list;
   int* flag2_list;
   int* stats;
@@ -887,6 +972,8 @@ static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* 
   o->sel_n = c.take<int>(Q);
   o->d2 = c.take<double>(size_t(Q) * kKeep);
   o->kth_d2 = c.take<double>(Q);
+  o->sel_score = c.take<float>(size_t(Q) * kKeep);
+  o->cut_mode = c.take<int>(Q);
   o->flag_list = c.take<int>(Q);
   o->flag2_list = c.take<int>(Q);
   const int slots = o->nchunks > 1 ? 2 : 1;
@@ -963,6 +1050,62 @@ static int launch_tensor(const QueryWs& w, int slot, const __half* qh, const flo
 }  // namespace scl
 
 using namespace scl;
+
+// Queries the first pass refused (hs = host copy of the counters, read after the stream was synchronised): second tensor
+// stage, then the exact scan for what is left; finally the counters go out.  Shared by scl_knn_query and scl_knn_query_end.
+static int resolve_refused(int (&hs)[8], const float* db, int64_t R, int D, const float* queries, int Q, int k,
+                           int64_t idx_offset, int force_path, double* dist, int64_t* idx, int32_t* stats, const QueryWs& w,
+                           const ShadowHeader* h, const float* rn, const __half* dbh, int Dp, int nchunks,
+                           cudaStream_t stream) {
+  int rc;
+  const int nflag = hs[2];
+  int n_stage2 = 0, n_scan = 0;
+  if (nflag > 0) {
+    // force_path 3: every query through the exact scan; 4: every query through stage 2 (test hooks)
+    const bool stage2 = force_path != 3 && knob_or(KNOB_KNN_STAGE2, 1) != 0;
+    if (!stage2) {
+      rc = run_exact(db, R, D, queries, w.flag_list, nflag, k, idx_offset, dist, idx, w, stream);
+      if (rc) return rc;
+      n_scan = nflag;
+    } else {
+      static SmemAttrCache sel2_cfg;
+      constexpr size_t sel2_smem = size_t(kCollectCap) * sizeof(SelKey);
+      if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(knn_stage2_select_kernel), sel2_smem, &sel2_cfg))) return rc;
+      for (int f0 = 0; f0 < nflag; f0 += w.q2max) {
+        const int n2 = std::min(w.q2max, nflag - f0);
+        knn_stage2_gather_kernel<<<n2, 256, 0, stream>>>(w.flag_list, f0, n2, Dp, w.qh, w.qmul, w.qn2, w.qexp, w.kth_d2, h,
+                                                         w.qh2, w.qmul2, w.thr2, w.cnt2);
+        SCL_LAUNCH_CHECK();
+        rc = launch_tensor(w, 0, w.qh2, w.qmul2, w.q_thr, n2, R, Dp, rn, dbh, nullptr, true, stream);
+        if (rc) return rc;
+        const long long pairs = (long long)n2 * kCollectCap;
+        knn_stage2_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, stream>>>(db, queries, D, w.flag_list, f0, w.coll_idx,
+                                                                                w.cnt2, pairs, w.coll_d2);
+        SCL_LAUNCH_CHECK();
+        knn_stage2_select_kernel<<<n2, 256, sel2_smem, stream>>>(w.flag_list, f0, w.coll_idx, w.cnt2, w.coll_d2, k,
+                                                                 idx_offset, dist, reinterpret_cast<long long*>(idx),
+                                                                 w.flag2_list, w.stats);
+        SCL_LAUNCH_CHECK();
+      }
+      // how many lists overflowed decides whether the exact scan runs at all: second (and last) host read
+      SCL_CUDA_TRY(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
+      SCL_CUDA_TRY(cudaStreamSynchronize(stream));
+      n_stage2 = hs[4];
+      n_scan = hs[5];
+      if (n_scan > 0) {
+        rc = run_exact(db, R, D, queries, w.flag2_list, n_scan, k, idx_offset, dist, idx, w, stream);
+        if (rc) return rc;
+      }
+    }
+  }
+  if (stats) {
+    const StatsOut so = {{Q, hs[1], nflag, 2, n_stage2, n_scan, nchunks, hs[7]}};
+    knn_stats_out_kernel<<<1, 8, 0, stream>>>(stats, so);
+    SCL_LAUNCH_CHECK();
+  }
+  return SCL_OK;
+}
+
 
 extern "C" int scl_knn_shadow_bytes(int64_t R, int D, size_t* bytes) {
   if (!bytes || R < 1 || D < 4 || (D & 3)) return SCL_ERR_BAD_ARG;
@@ -1081,7 +1224,7 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
     knn_tc_tiling(nq, R, Dp, &mb, &nt, &NR, &tpr, &gm);
     knn_cand_merge_kernel<<<nq, 256, 0, ps>>>(w.cand_s[slot], w.cand_i[slot], w.cand_cnt[slot], w.q_thr + q0, NR, k,
                                               w.qn2 + q0, w.qexp + q0, h, w.sel_idx + size_t(q0) * kKeep, w.sel_T + q0,
-                                              w.sel_n + q0);
+                                              w.sel_n + q0, nullptr, nullptr);
     SCL_LAUNCH_CHECK();
     const long long pairs = (long long)nq * kKeep;
     knn_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, ps>>>(db, queries + size_t(q0) * D, D,
@@ -1092,7 +1235,7 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
                                                       w.sel_n + q0, w.qn2 + q0, w.qexp + q0, h, nq, k, idx_offset,
                                                       force_path >= 3 ? 1 : 0, q0, dist + size_t(q0) * k,
                                                       reinterpret_cast<long long*>(idx) + size_t(q0) * k, w.kth_d2 + q0,
-                                                      w.flag_list, w.stats);
+                                                      w.flag_list, w.stats, nullptr);
     SCL_LAUNCH_CHECK();
     if (nchunks > 1) SCL_CUDA_TRY(cudaEventRecord(ev_post, hc.h));
   }
@@ -1114,52 +1257,115 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
     g_knn_tc_ms_sum += sum;
     g_knn_tc_calls += 1;
   }
-  const int nflag = hs[2];
-  int n_stage2 = 0, n_scan = 0;
-  if (nflag > 0) {
-    // force_path 3: every query through the exact scan; 4: every query through stage 2 (test hooks)
-    const bool stage2 = force_path != 3 && knob_or(KNOB_KNN_STAGE2, 1) != 0;
-    if (!stage2) {
-      rc = run_exact(db, R, D, queries, w.flag_list, nflag, k, idx_offset, dist, idx, w, stream);
-      if (rc) return rc;
-      n_scan = nflag;
-    } else {
-      static SmemAttrCache sel2_cfg;
-      constexpr size_t sel2_smem = size_t(kCollectCap) * sizeof(SelKey);
-      if ((rc = ensure_dyn_smem(reinterpret_cast<const void*>(knn_stage2_select_kernel), sel2_smem, &sel2_cfg))) return rc;
-      for (int f0 = 0; f0 < nflag; f0 += w.q2max) {
-        const int n2 = std::min(w.q2max, nflag - f0);
-        knn_stage2_gather_kernel<<<n2, 256, 0, stream>>>(w.flag_list, f0, n2, Dp, w.qh, w.qmul, w.qn2, w.qexp, w.kth_d2, h,
-                                                         w.qh2, w.qmul2, w.thr2, w.cnt2);
-        SCL_LAUNCH_CHECK();
-        rc = launch_tensor(w, 0, w.qh2, w.qmul2, w.q_thr, n2, R, Dp, rn, dbh, nullptr, true, stream);
-        if (rc) return rc;
-        const long long pairs = (long long)n2 * kCollectCap;
-        knn_stage2_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, stream>>>(db, queries, D, w.flag_list, f0, w.coll_idx,
-                                                                                w.cnt2, pairs, w.coll_d2);
-        SCL_LAUNCH_CHECK();
-        knn_stage2_select_kernel<<<n2, 256, sel2_smem, stream>>>(w.flag_list, f0, w.coll_idx, w.cnt2, w.coll_d2, k,
-                                                                 idx_offset, dist, reinterpret_cast<long long*>(idx),
-                                                                 w.flag2_list, w.stats);
-        SCL_LAUNCH_CHECK();
-      }
-      // how many lists overflowed decides whether the exact scan runs at all: second (and last) host read
-      SCL_CUDA_TRY(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
-      SCL_CUDA_TRY(cudaStreamSynchronize(stream));
-      n_stage2 = hs[4];
-      n_scan = hs[5];
-      if (n_scan > 0) {
-        rc = run_exact(db, R, D, queries, w.flag2_list, n_scan, k, idx_offset, dist, idx, w, stream);
-        if (rc) return rc;
-      }
+  return resolve_refused(hs, db, R, D, queries, Q, k, idx_offset, force_path, dist, idx, stats, w, h, rn, dbh, Dp, nchunks, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded retrieval in two phases: between them the ranks agree on a per-query bound (all-reduce MIN), so
+// that each rank rescoring exactly only the candidates that can still enter the GLOBAL top-k -- k/G of them on average,
+// not the k..64 its own top-k would need.  The rescore is the part of a rank's work that does not shrink with the shard.
+static int two_phase_ok(int64_t R, int D, int Q, int k) {
+  return use_tensor_pass(R, D, Q, k, 2) ? SCL_OK : SCL_ERR_UNSUPPORTED;
+}
+
+extern "C" int scl_knn_query_begin(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                                   float* ub, void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
+  if (!db || !shadow || !queries || !ub || !workspace) return SCL_ERR_BAD_ARG;
+  if (R < 1 || Q < 1 || k < 1 || D < 4 || (D & 3)) return SCL_ERR_BAD_SHAPE;
+  if (!aligned16(db) || !aligned16(queries) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return SCL_ERR_ALIGN;
+  int rc = two_phase_ok(R, D, Q, k);
+  if (rc) return rc;
+  if ((rc = check_device())) return rc;
+  QueryWs w;
+  const size_t need = query_ws_layout(R, D, Q, k, &w, workspace, workspace_bytes);
+  if (workspace_bytes < need) return SCL_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const char* sb = static_cast<const char*>(shadow);
+  const ShadowHeader* h = reinterpret_cast<const ShadowHeader*>(sb);
+  const float* rn = reinterpret_cast<const float*>(sb + shadow_norm_off());
+  const __half* dbh = reinterpret_cast<const __half*>(sb + shadow_data_off(R));
+  const int Dp = pad64(D);
+  SCL_CUDA_TRY(cudaMemsetAsync(w.stats, 0, 8 * sizeof(int), stream));
+  knn_query_prep_kernel<<<Q, 256, 0, stream>>>(queries, Q, D, Dp, h, w.qh, w.qmul, w.qn2, w.qexp);
+  SCL_LAUNCH_CHECK();
+  SCL_CUDA_TRY(cudaMemsetAsync(w.q_thr, 0xff, size_t(Q) * sizeof(unsigned int), stream));
+  // one tensor pass over all queries (chunks, if the workspace was laid out for them, run back to back on this stream:
+  // there is nothing to overlap them with before the ranks have agreed on the bound)
+  HelperCtx& hc = t_helper[device_slot()];
+  const bool timing = g_knn_timing.load(std::memory_order_relaxed) != 0;
+  for (int c = 0; c < w.nchunks; ++c) {
+    const int q0 = c * w.chunk_q, nq = std::min(w.chunk_q, Q - q0), slot = c & 1;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (timing) {
+      if ((rc = hc.get(hc.tev, size_t(2 * c), cudaEventDefault, &t0))) return rc;
+      if ((rc = hc.get(hc.tev, size_t(2 * c + 1), cudaEventDefault, &t1))) return rc;
+      SCL_CUDA_TRY(cudaEventRecord(t0, stream));
     }
-  }
-  if (stats) {
-    const StatsOut so = {{Q, hs[1], nflag, 2, n_stage2, n_scan, nchunks, 0}};
-    knn_stats_out_kernel<<<1, 8, 0, stream>>>(stats, so);
+    rc = launch_tensor(w, slot, w.qh + size_t(q0) * Dp, w.qmul + q0, w.q_thr + q0, nq, R, Dp, rn, dbh, nullptr, false, stream);
+    if (rc) return rc;
+    if (timing) SCL_CUDA_TRY(cudaEventRecord(t1, stream));
+    int mb, nt, NR, tpr, gm;
+    knn_tc_tiling(nq, R, Dp, &mb, &nt, &NR, &tpr, &gm);
+    knn_cand_merge_kernel<<<nq, 256, 0, stream>>>(w.cand_s[slot], w.cand_i[slot], w.cand_cnt[slot], w.q_thr + q0, NR, k,
+                                                  w.qn2 + q0, w.qexp + q0, h, w.sel_idx + size_t(q0) * kKeep, w.sel_T + q0,
+                                                  w.sel_n + q0, w.sel_score + size_t(q0) * kKeep, ub + size_t(q0) * k);
     SCL_LAUNCH_CHECK();
   }
   return SCL_OK;
+}
+
+extern "C" int scl_knn_bound_reduce(const float* ub_all, int G, int Q, int k, float* bound, scl_stream_t stream) {
+  if (!ub_all || !bound || G < 1 || Q < 1 || k < 1) return SCL_ERR_BAD_ARG;
+  int rc = check_device();
+  if (rc) return rc;
+  knn_bound_reduce_kernel<<<(Q + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(ub_all, G, Q, k, bound);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+extern "C" int scl_knn_query_end(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                                 int64_t idx_offset, const float* bound, double* dist, int64_t* idx, int32_t* stats,
+                                 void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
+  if (!db || !shadow || !queries || !bound || !dist || !idx || !workspace) return SCL_ERR_BAD_ARG;
+  if (R < 1 || Q < 1 || k < 1 || D < 4 || (D & 3)) return SCL_ERR_BAD_SHAPE;
+  int rc = two_phase_ok(R, D, Q, k);
+  if (rc) return rc;
+  if ((rc = check_device())) return rc;
+  QueryWs w;
+  const size_t need = query_ws_layout(R, D, Q, k, &w, workspace, workspace_bytes);
+  if (workspace_bytes < need) return SCL_ERR_WORKSPACE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const char* sb = static_cast<const char*>(shadow);
+  const ShadowHeader* h = reinterpret_cast<const ShadowHeader*>(sb);
+  const float* rn = reinterpret_cast<const float*>(sb + shadow_norm_off());
+  const __half* dbh = reinterpret_cast<const __half*>(sb + shadow_data_off(R));
+  const int Dp = pad64(D);
+  knn_apply_cutoff_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(bound, w.sel_score, w.sel_T, w.sel_n, w.qn2, w.qexp, h, Q, w.sel_idx,
+                                                           w.cut_mode, w.stats);
+  SCL_LAUNCH_CHECK();
+  const long long pairs = (long long)Q * kKeep;
+  knn_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, stream>>>(db, queries, D, w.sel_idx, pairs, w.d2);
+  SCL_LAUNCH_CHECK();
+  knn_finalize_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(w.sel_idx, w.d2, w.sel_T, w.sel_n, w.qn2, w.qexp, h, Q, k, idx_offset, 0, 0,
+                                                       dist, reinterpret_cast<long long*>(idx), w.kth_d2, w.flag_list, w.stats,
+                                                       w.cut_mode);
+  SCL_LAUNCH_CHECK();
+  int hs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  SCL_CUDA_TRY(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
+  SCL_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (g_knn_timing.load(std::memory_order_relaxed) != 0) {
+    HelperCtx& hc = t_helper[device_slot()];
+    double sum = 0.0;
+    for (int c = 0; c < w.nchunks && size_t(2 * c + 1) < hc.tev.size(); ++c) {
+      float ms = 0.0f;
+      SCL_CUDA_TRY(cudaEventElapsedTime(&ms, hc.tev[2 * c], hc.tev[2 * c + 1]));
+      sum += double(ms);
+    }
+    std::lock_guard<std::mutex> lk(g_knn_timing_mu);
+    g_knn_tc_ms_sum += sum;
+    g_knn_tc_calls += 1;
+  }
+  return resolve_refused(hs, db, R, D, queries, Q, k, idx_offset, 2, dist, idx, stats, w, h, rn, dbh, Dp, w.nchunks, stream);
 }
 
 extern "C" int scl_knn_timing(int enable, double* tensor_pass_ms_sum, int* tensor_pass_calls) {

@@ -81,6 +81,35 @@ class KDTree:
         self.last_stats = stats
         return dist, idx
 
+    # -- sharded two-phase query (scl_knn_query_begin / _end): see ShardedKDTree.query_device --------------------------
+    UNSUPPORTED = -7
+
+    def query_begin(self, q, k, bound):
+        """First phase on device queries ``q`` [Q,D] f32: fills ``bound`` [Q,k] f32 (upper bounds on the distances of this
+        shard's k best candidates) and returns the state to hand to ``query_end``; None (bounds = +inf) when this shard
+        does not take the tensor pass."""
+        Q = q.shape[0]
+        L = lib()
+        nbytes = C.c_size_t()
+        check(L.scl_knn_query_workspace_bytes(self.R, self.D, Q, k, C.byref(nbytes)), "scl_knn_query_workspace_bytes")
+        ws = _ws(nbytes.value, q.device)
+        rc = L.scl_knn_query_begin(_p(self.db), _p(self.shadow), self.R, self.D, _p(q), Q, k, _p(bound), _p(ws), ws.numel(),
+                                   _stream())
+        if rc == self.UNSUPPORTED:
+            bound.fill_(float("inf"))
+            return None
+        check(rc, "scl_knn_query_begin")
+        return ws
+
+    def query_end(self, state, q, k, bound, out):
+        dist, idx = out
+        Q = q.shape[0]
+        stats = torch.zeros(8, dtype=torch.int32, device=q.device)
+        check(lib().scl_knn_query_end(_p(self.db), _p(self.shadow), self.R, self.D, _p(q), Q, k, self.index_offset, _p(bound),
+                                      _p(dist), _p(idx), _p(stats), _p(state), state.numel(), _stream()), "scl_knn_query_end")
+        self.last_stats = stats
+        return dist, idx
+
     def query(self, X, k=1, return_distance=True, sort_results=True, force_path=0):
         """``KDTree.query`` as called at evaluation/top-n.py:106.  Results are always sorted ascending."""
         dist, idx = self.query_device(X, k, force_path)
@@ -92,10 +121,18 @@ class KDTree:
     def stats(self):
         """Counters of the last query (path 1 = exact scan, 2 = tensor pass).  ``n_fallback`` = queries the first tensor
         pass could not certify; of those ``n_stage2`` were resolved by the second tensor stage and ``n_scan`` went to
-        the exact float64 scan."""
+        the exact float64 scan; ``n_bound`` = queries of a two-phase (sharded) call settled by the reduced bound."""
         s = self.last_stats.cpu().tolist()
         return {"n_queries": s[0], "n_certified": s[1], "n_fallback": s[2], "path": s[3], "n_stage2": s[4],
-                "n_scan": s[5], "chunks": s[6]}
+                "n_scan": s[5], "chunks": s[6], "n_bound": s[7]}
+
+
+def bound_reduce(ub_all):
+    """[G,Q,k] gathered upper bounds (ascending per rank and query) -> [Q] k-th smallest of each query's union."""
+    G, Q, k = ub_all.shape
+    bound = torch.empty(Q, dtype=torch.float32, device=ub_all.device)
+    check(lib().scl_knn_bound_reduce(_p(ub_all), G, Q, k, _p(bound), _stream()), "scl_knn_bound_reduce")
+    return bound
 
 
 def topk_merge(d_all, i_all):
@@ -124,11 +161,15 @@ class ShardedKDTree:
     """Database rows split contiguously over the ranks of ``group``; queries replicated.
 
     Each rank answers against its shard (global indices = local + offset); one all-gather of the [Q,k] lists
-    (NCCL over NVLink) followed by the merge kernel gives every rank the exact global top-k."""
+    (NCCL over NVLink) followed by the merge kernel gives every rank the exact global top-k.  With ``two_phase`` (default)
+    the ranks first exchange their candidates' score bounds so that each rescores only what can reach the GLOBAL top-k."""
 
-    def __init__(self, X_local, index_offset, group=None):
+    TWO_PHASE_MAX_K = 32          # the tensor pass serves k <= 32 (scl_knn_query)
+
+    def __init__(self, X_local, index_offset, group=None, two_phase=True):
         import torch.distributed as dist
         self.group = group
+        self.two_phase = bool(two_phase)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local = KDTree(X_local, index_offset=index_offset)
 
@@ -143,7 +184,22 @@ class ShardedKDTree:
         Q = q.shape[0]
         # one packed message per rank: [2, Q, k] 8-byte words (float64 distances | int64 indices), ONE all-gather
         mine = torch.empty((2, Q, k), dtype=torch.int64, device=q.device)
-        self.local.query_device(q, k, force_path, out=(mine[0].view(torch.float64), mine[1]))
+        out = (mine[0].view(torch.float64), mine[1])
+        if self.two_phase and force_path == 0 and k <= self.TWO_PHASE_MAX_K and q.shape[1] == self.local.D:
+            # Two phases (include/scl_b200.h: scl_knn_query_begin): the ranks agree on a per-query bound on the k-th
+            # global distance (all-gather of [Q,k] floats, k-th smallest of the union) and each then rescores only what
+            # can still make the global top-k.  The condition above depends only on values every rank shares, so all of them take this branch.
+            ub_all = torch.empty((self.world, Q, k), dtype=torch.float32, device=q.device)
+            ub = ub_all[dist.get_rank(self.group)]
+            state = self.local.query_begin(q, k, ub)
+            dist.all_gather_into_tensor(ub_all.view(self.world * Q, k), ub, group=self.group)
+            bound = bound_reduce(ub_all)
+            if state is None:
+                self.local.query_device(q, k, 0, out=out)
+            else:
+                self.local.query_end(state, q, k, bound, out)
+        else:
+            self.local.query_device(q, k, force_path, out=out)
         packed = torch.empty((self.world, 2, Q, k), dtype=torch.int64, device=q.device)
         dist.all_gather_into_tensor(packed.view(self.world * 2 * Q, k), mine.view(2 * Q, k), group=self.group)
         return topk_merge_packed(packed, self.world, Q, k)

@@ -95,6 +95,88 @@ def test_exact_ties_across_shards_and_the_merge(cuda_lib):
     assert (i[:, :4].cpu().numpy() == np.arange(50)[:, None] + 1500 * np.arange(4)[None]).all()
 
 
+def _two_phase(db, qry, G, k, bounds=None):
+    """G shards of `db` on ONE GPU through scl_knn_query_begin -> scl_knn_bound_reduce -> scl_knn_query_end -> merge: the
+    sharded protocol of retrieval.ShardedKDTree with the all-gather replaced by torch.stack."""
+    from soft_contrastive_learning_b200 import retrieval
+    R, Q = db.shape[0], qry.shape[0]
+    q = torch.tensor(qry, device="cuda")
+    trees, states, bnds = [], [], []
+    for r in range(G):
+        lo, hi = bounds[r] if bounds else retrieval.shard_bounds(R, G, r)
+        trees.append(retrieval.KDTree(db[lo:hi], index_offset=lo))
+        b = torch.empty((Q, k), dtype=torch.float32, device="cuda")
+        states.append(trees[-1].query_begin(q, k, b))
+        bnds.append(b)
+    ub_all = torch.stack(bnds)
+    bound = retrieval.bound_reduce(ub_all)
+    assert torch.equal(bound, ub_all.permute(1, 0, 2).reshape(Q, G * k).sort(1).values[:, k - 1])
+    packed = torch.empty((G, 2, Q, k), dtype=torch.int64, device="cuda")
+    stats = []
+    for r in range(G):
+        out = (packed[r, 0].view(torch.float64), packed[r, 1])
+        if states[r] is None:
+            trees[r].query_device(q, k, 0, out=out)
+        else:
+            trees[r].query_end(states[r], q, k, bound, out)
+        stats.append(trees[r].stats())
+    d, i = retrieval.topk_merge_packed(packed, G, Q, k)
+    real = (packed[:, 1] >= 0).sum().item()
+    return d.cpu().numpy(), i.cpu().numpy(), real, stats
+
+
+@pytest.mark.parametrize("R,Q,D,k,G", [(40000, 300, 256, 25, 4), (24000, 129, 4096, 25, 3), (64000, 64, 128, 5, 8),
+                                       (9000, 257, 64, 32, 2)])
+def test_two_phase_sharded_query_is_exact(cuda_lib, R, Q, D, k, G):
+    """Between the two phases the shards agree on a bound on the k-th global distance; each rescoring only what can
+    still reach the global top-k.  Result = float64 brute force over the whole database, and the shards together return
+    far fewer than G*k rows per query."""
+    db, qry, *_ = synth.retrieval_problem(R=R, Q=Q, D=D, seed=15)
+    d, i, real, stats = _two_phase(db, qry, G, k)
+    rd, ri = orr.knn_bruteforce(db, qry, k)
+    check_exact(d, i, rd, ri)
+    assert Q * k <= real <= 2 * Q * k, (real, Q * k, G)          # plain protocol: G * Q * k
+    for st in stats:
+        assert st["path"] == 2 and st["n_certified"] + st["n_fallback"] == Q, st
+
+
+def test_two_phase_ties_duplicates_and_refusals(cuda_lib):
+    """Adversarial for the bound: exact duplicates that straddle shard borders (equal scores at the cut; the row left out
+    must be STRICTLY farther), near-duplicate clusters living on ONE shard (that shard has more than 64 rows inside the
+    bound: it falls back to its exact local top-k through the second tensor stage / scan while the others trim), a shard
+    too small for the tensor pass (contributes +inf, answers with the plain query) and a ragged last shard."""
+    from soft_contrastive_learning_b200 import retrieval
+    rng = np.random.default_rng(16)
+    D, k = 128, 25
+    base = rng.standard_normal((3000, D)).astype(np.float32)
+    centers = rng.standard_normal((6, D)).astype(np.float32)
+    near = (centers[:, None, :] + 1e-4 * rng.standard_normal((6, 150, D))).reshape(-1, D).astype(np.float32)
+    db = np.concatenate([base, base, near, base[:1700], rng.standard_normal((500, D)).astype(np.float32)], 0)
+    qry = np.concatenate([base[:40], centers, base[100:120] + 0.2 * rng.standard_normal((20, D)).astype(np.float32)], 0)
+    R = db.shape[0]                                                  # 9100 rows
+    bounds = [(0, 2500), (2500, 5000), (5000, 8600), (8600, 9100)]   # last shard: 500 rows < 1024 -> unsupported
+    d, i, real, stats = _two_phase(db, qry, 4, k, bounds)
+    rd, ri = orr.knn_bruteforce_exact(db, qry, k)
+    check_exact(d, i, rd, ri)
+    assert (i[:40, :3] == np.arange(40)[:, None] + np.array([0, 3000, 6900])[None]).all() and (d[:40, :3] == 0).all()
+    assert stats[3]["path"] == 1                                     # the small shard took the plain exact scan
+    assert stats[2]["n_fallback"] >= 6, stats[2]                     # the cluster shard refused the cluster queries
+    # the same database through ONE index gives the same bits
+    d1, i1 = retrieval.KDTree(db).query(qry, k=k, force_path=2)
+    assert np.array_equal(i1, i) and np.array_equal(d1, d)
+
+
+def test_two_phase_large_shards_match_single_index(cuda_lib, tune):
+    """Config-4-like sizes (D = 4096, 10 000 queries in two pipelined chunks) on 2 shards of one GPU."""
+    from soft_contrastive_learning_b200 import retrieval
+    db, qry, *_ = synth.retrieval_problem(R=60000, Q=6000, D=4096, seed=17)
+    d, i, real, stats = _two_phase(db, qry, 2, 25)
+    assert stats[0]["chunks"] >= 1
+    d1, i1 = retrieval.KDTree(db).query(qry, k=25)
+    assert np.array_equal(i1, i) and np.array_equal(d1, d)
+    assert real <= 0.85 * 2 * 6000 * 25                       # plain protocol: 2 * Q * k; here ~25 + the rows within 2 eps
+
+
 @pytest.fixture(params=["1", "2", "3"], ids=["cta_group1", "cta_pair", "cta_pair_wide"])
 def tc_variant(request, tune):
     """The tensor-pass kernels: single-CTA 128x256 tiles and cta_group::2 CTA pairs (256x256, 256x512)."""

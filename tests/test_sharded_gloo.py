@@ -1,5 +1,6 @@
 """CPU, world_size 2 over gloo: the sharded-retrieval host protocol (contiguous row shards, global index offsets,
-ONE all-gather of the packed per-shard [2,Q,k] messages, merge by (distance, index)) returns the exact global top-k.
+the all-gather of the per-rank score bounds between the two phases of the local query, ONE all-gather of the packed
+per-shard [2,Q,k] messages, merge by (distance, index)) returns the exact global top-k.
 
 The two device-side pieces (local kNN, merge kernel) are replaced by oracle stand-ins injected from here; what is
 exercised is the product's distributed plumbing in soft_contrastive_learning_b200.retrieval."""
@@ -24,7 +25,31 @@ def _free_port():
 class _OracleLocal:
     def __init__(self, X, index_offset=0):
         self.X, self.off = np.asarray(X), index_offset
+        self.D = self.X.shape[1]
         self.db = torch.zeros(1)                 # the device the shard lives on (CPU in this test)
+
+    # two-phase protocol (scl_knn_query_begin / _end) restated exactly: the bounds are the shard's k smallest exact squared
+    # distances, the second phase returns the shard's rows at or below the reduced bound, padded with (inf, -1)
+    def query_begin(self, q, k, bound):
+        from oracle import retrieval as orr
+        if self.X.shape[0] < max(k, self.min_rows):           # "this shard does not take the tensor pass"
+            bound.fill_(float("inf"))
+            return None
+        d, _ = orr.knn_bruteforce_exact(self.X, np.asarray(q), k)
+        bound.copy_(torch.from_numpy((d ** 2).astype(np.float32) * (1 + 1e-6)))
+        return "state"
+
+    def query_end(self, state, q, k, bound, out):
+        from oracle import retrieval as orr
+        assert state == "state"
+        d, i = orr.knn_bruteforce_exact(self.X, np.asarray(q), k)
+        keep = d ** 2 <= bound.numpy()[:, None].astype(np.float64)
+        self.kept = int(keep.sum())
+        out[0].copy_(torch.from_numpy(np.where(keep, d, np.inf)))
+        out[1].copy_(torch.from_numpy(np.where(keep, i + self.off, -1)))
+        return out
+
+    min_rows = 0
 
     def query_device(self, q, k=1, force_path=0, out=None):
         from oracle import retrieval as orr
@@ -64,11 +89,26 @@ def _worker(rank, world, port, R, D, Q, k, out):
         lo, hi = retrieval.shard_bounds(R, world, rank)
         retrieval.KDTree = _OracleLocal            # test doubles for the two CUDA pieces
         retrieval.topk_merge = _numpy_merge
+        retrieval.bound_reduce = lambda ub_all: torch.from_numpy(                  # [G,Q,k] -> k-th smallest of the union
+            np.sort(ub_all.permute(1, 0, 2).reshape(ub_all.shape[1], -1).numpy(), axis=1)[:, ub_all.shape[2] - 1].copy())
         # the packed message [G, 2, Q, k] of 8-byte words, as ONE all-gather delivers it
         retrieval.topk_merge_packed = lambda packed, G, Q, k: _numpy_merge(packed[:, 0].contiguous().view(torch.float64),
                                                                          packed[:, 1].contiguous())
         tree = retrieval.ShardedKDTree(db[lo:hi], index_offset=lo)
         d, i = tree.query_device(qry, k)
+        if hi - lo >= k:                           # the two-phase protocol ran and trimmed the per-rank lists
+            kept = torch.tensor([tree.local.kept])
+            dist.all_reduce(kept)
+            assert Q * k <= int(kept) < 1.2 * Q * k
+        # same answer from the single-phase protocol, and with one rank's shard refusing the first phase
+        plain = retrieval.ShardedKDTree(db[lo:hi], index_offset=lo, two_phase=False)
+        d1, i1 = plain.query_device(qry, k)
+        assert torch.equal(i1, i) and torch.equal(d1, d)
+        if rank == 1:
+            tree.local.min_rows = 10 ** 9
+        d1, i1 = tree.query_device(qry, k)
+        assert torch.equal(i1, i) and torch.equal(d1, d)
+        tree.local.min_rows = 0
         # queries in host memory: every rank copies its 1/G slice (ragged: Q = 9 over 2 ranks) and the slices are all-gathered
         d2, i2 = tree.query_from_host(torch.from_numpy(qry), k)
         assert torch.equal(i2, i) and torch.equal(d2, d)
