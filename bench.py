@@ -300,7 +300,7 @@ def retrieval_run(args, torch, dist_mod, rank, world, R, Q, data="gaussian", ste
     torch.cuda.synchronize()
     if dist_mod is not None:
         index = retrieval.ShardedKDTree.__new__(retrieval.ShardedKDTree)
-        index.group, index.world, index.local = None, world, tree
+        index.group, index.world, index.local, index.two_phase = None, world, tree, not args.single_phase
     else:
         index = tree
 
@@ -379,7 +379,10 @@ def retrieval_run(args, torch, dist_mod, rank, world, R, Q, data="gaussian", ste
     # launches of this repo's kernels per step: prep + per chunk (tensor pass, candidate merge, rescore, certificate) +
     # stats (+ shard merge); refused queries add the second stage (gather, tensor pass, rescore, select)
     nf = stats["n_fallback"]
+    # sharded (two-phase): prep, tensor pass, candidate merge | bound reduce | cutoff, rescore, certificate, stats | shard merge
     launches = 1 + 4 * max(1, stats["chunks"]) + 1 + (1 if world > 1 else 0) + (4 * -(-nf // 2048) if nf else 0)
+    if world > 1 and not args.single_phase:
+        launches += 2
     return {"ms": ms, "ms_e2e": ms_e2e, "tc_ms": tc_avg_ms, "flops_per_launch": flops, "stats": stats, "clocks": clk,
             "rows_local": rows_local, "build_s": t_build_h2d, "launches_per_step": launches, "info": info, "steps": steps,
             "warmup": warmup}
@@ -393,7 +396,9 @@ def bench_retrieval(args, torch, dist_mod, rank, world, pk):
     cfg = workload_config(R, Q, world)
     cfg.update({"data_kind": args.data, "rows_per_gpu": m["rows_local"],
                 "l2": "inputs larger than L2 (db shard fp32+fp16 >> 126 MB); no flush",
-                "merge": "one packed NCCL all-gather of [dist|idx] + merge kernel" if world > 1 else "single shard",
+                "merge": (("two-phase: all-gather of the ranks' [Q,k] score bounds, bound-limited rescore, " if not args.single_phase else "")
+                          + "one packed NCCL all-gather of [dist|idx] + merge kernel") if world > 1 else "single shard",
+                "n_settled_by_the_bound": stats.get("n_bound", 0),
                 "n_certified": stats["n_certified"], "n_refused_first_pass": stats["n_fallback"],
                 "n_resolved_by_stage2": stats["n_stage2"], "n_exact_scan": stats["n_scan"],
                 "pipeline_chunks": stats["chunks"], "index_build_from_host_s": m["build_s"]})
@@ -728,6 +733,8 @@ def main():
     ap.add_argument("--rows", type=int, default=R_FULL)
     ap.add_argument("--queries", type=int, default=Q_STEP)
     ap.add_argument("--data", default="gaussian", choices=["gaussian", "clustered"])
+    ap.add_argument("--single-phase", action="store_true",
+                    help="N > 1: the plain sharded protocol (every rank returns its full local top-k) instead of the two-phase one")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--time-build", action="store_true", default=True)

@@ -191,7 +191,7 @@ __device__ __forceinline__ uint32_t score_key32(float s) {
   uint32_t u = __float_as_uint(s);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-__global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __restrict__ cand_s,
+__global__ void __launch_bounds__(256, 3) knn_cand_merge_kernel(const float* __restrict__ cand_s,
                                                              const uint32_t* __restrict__ cand_i,
                                                              const int* __restrict__ cand_cnt,
                                                              const unsigned int* __restrict__ q_thr, int NR, int k,
@@ -225,13 +225,20 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   const uint32_t* qi = cand_i + size_t(q) * NR * kCandCap;
   uint32_t ku[kMergeSlots];                           // monotone keys of this thread's slots
   uint32_t live = 0;                                  // bit it: slot holds a survivor
-#pragma unroll
-  for (int it = 0; it < kMergeSlots; ++it) {
-    const int slot = it * 256 + threadIdx.x, r = slot / kCandCap, e = slot % kCandCap;
+  // the slot loops run over the groups of 8 slots per thread that the NR ranges of this launch reach (fully unrolled:
+  // ku stays in registers); NR = 37 at an 8-way shard of config 4 -> 3 of the 4 groups
+  const int nslots = (NR * kCandCap + 255) / 256;
+#define SCL_FOR_SLOTS(body)                                                  \
+  _Pragma("unroll") for (int qd = 0; qd < kMergeSlots / 8; ++qd) {           \
+    if (qd * 8 < nslots) {                                                   \
+      _Pragma("unroll") for (int j = 0; j < 8; ++j) { const int it = qd * 8 + j; body }  \
+    }                                                                        \
+  }
+  SCL_FOR_SLOTS(
+    const int slot = it * 256 + threadIdx.x; const int r = slot / kCandCap; const int e = slot % kCandCap;
     const float sc = (r < NR && e < s_cnt[r]) ? qs[slot] : NAN;          // NaN: never <= anything
     ku[it] = score_key32(sc);
-    live |= (sc <= t_pub) ? (1u << it) : 0u;
-  }
+    live |= (sc <= t_pub) ? (1u << it) : 0u;)
   if (live) atomicAdd(&s_surv, __popc(live));
   __syncthreads();
   const int kept = s_surv;                            // survivors of the threshold
@@ -244,10 +251,8 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
       s_hist[threadIdx.x] = 0;
       __syncthreads();
       const uint32_t prefix = s_prefix;
-#pragma unroll
-      for (int it = 0; it < kMergeSlots; ++it)
-        if (((live >> it) & 1u) && (shift == 24 || (ku[it] >> (shift + 8)) == prefix))
-          atomicAdd(&s_hist[(ku[it] >> shift) & 255u], 1);
+      SCL_FOR_SLOTS(if (((live >> it) & 1u) && (shift == 24 || (ku[it] >> (shift + 8)) == prefix))
+                      atomicAdd(&s_hist[(ku[it] >> shift) & 255u], 1);)
       __syncthreads();
       if (threadIdx.x < 32) {
         // bins 8*lane .. 8*lane+7 per lane, exclusive scan across lanes, then locate the bin holding rank s_rank
@@ -276,15 +281,13 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   }
   // gather the selected keys (everything when the survivors fit)
   int mine = 0;
-#pragma unroll
-  for (int it = 0; it < kMergeSlots; ++it) mine += (((live >> it) & 1u) && ku[it] <= tau) ? 1 : 0;
+  SCL_FOR_SLOTS(mine += (((live >> it) & 1u) && ku[it] <= tau) ? 1 : 0;)
   int o = mine ? atomicAdd(&s_need, mine) : 0;
-#pragma unroll
-  for (int it = 0; it < kMergeSlots; ++it)
-    if (((live >> it) & 1u) && ku[it] <= tau) {
-      if (o < kMergeCap) mkeys[o] = (static_cast<unsigned long long>(ku[it]) << 32) | qi[it * 256 + threadIdx.x];
-      ++o;
-    }
+  SCL_FOR_SLOTS(if (((live >> it) & 1u) && ku[it] <= tau) {
+    if (o < kMergeCap) mkeys[o] = (static_cast<unsigned long long>(ku[it]) << 32) | qi[it * 256 + threadIdx.x];
+    ++o;
+  })
+#undef SCL_FOR_SLOTS
   __syncthreads();
   const int total = s_total;
   const bool overflow = s_need > kMergeCap;          // too many score ties at the boundary: handed to the exact path
@@ -332,34 +335,46 @@ __global__ void __launch_bounds__(256) knn_cand_merge_kernel(const float* __rest
   }
 }
 
-// exact squared distances of the selected candidates: one warp per (query, candidate), float64 accumulation of
-// direct differences (what KDTree's leaf scan computes)
+// exact squared distances of the selected candidates, float64 accumulation of direct differences (what KDTree's leaf
+// scan computes).  One CTA per query, one warp per candidate row, the warps striding over the list: the selected
+// candidates are a PREFIX of the kKeep slots (sorted by score, cut from the top), so a warp stops at its first empty slot
+// -- a two-phase (sharded) call rescoring ~k/G rows per query launches no work for the other slots.  Empty slots are not
+// written (knn_finalize_kernel reads them as +inf from sel_idx).
 __global__ void __launch_bounds__(256) knn_rescore_kernel(const float* __restrict__ db, const float* __restrict__ q,
-                                                          int D, const uint32_t* __restrict__ sel_idx, long long pairs,
+                                                          int D, const uint32_t* __restrict__ sel_idx,
                                                           double* __restrict__ d2) {
-  const int lane = threadIdx.x & 31;
-  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (p >= pairs) return;
-  const uint32_t r = sel_idx[p];
-  if (r == 0xffffffffu) {
-    if (lane == 0) d2[p] = INFINITY;
-    return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t qi = blockIdx.x;
+  const float4* qr = reinterpret_cast<const float4*>(q + qi * D);
+  const int nv = D >> 2;
+  for (int s = warp; s < kKeep; s += 8) {
+    const uint32_t r = sel_idx[qi * kKeep + s];
+    if (r == 0xffffffffu) break;
+    const float4* rr = reinterpret_cast<const float4*>(db + size_t(r) * D);
+    double acc = 0.0;
+    int c = lane;
+    for (; c + 96 < nv; c += 128) {                     // four independent 16-byte loads in flight per lane
+      const float4 b0 = ldg_stream(rr + c), b1 = ldg_stream(rr + c + 32), b2 = ldg_stream(rr + c + 64),
+                   b3 = ldg_stream(rr + c + 96);
+      const float4 a0 = __ldg(qr + c), a1 = __ldg(qr + c + 32), a2 = __ldg(qr + c + 64), a3 = __ldg(qr + c + 96);
+      double d;
+#define SCL_ACC4(a, b)                                              \
+      d = double(a.x) - double(b.x); acc = fma(d, d, acc);          \
+      d = double(a.y) - double(b.y); acc = fma(d, d, acc);          \
+      d = double(a.z) - double(b.z); acc = fma(d, d, acc);          \
+      d = double(a.w) - double(b.w); acc = fma(d, d, acc);
+      SCL_ACC4(a0, b0) SCL_ACC4(a1, b1) SCL_ACC4(a2, b2) SCL_ACC4(a3, b3)
+    }
+    for (; c < nv; c += 32) {
+      const float4 a0 = __ldg(qr + c);
+      const float4 b0 = ldg_stream(rr + c);
+      double d;
+      SCL_ACC4(a0, b0)
+    }
+#undef SCL_ACC4
+    acc = warp_sum(acc);
+    if (lane == 0) d2[qi * kKeep + s] = acc;
   }
-  const long long qi = p / kKeep;
-  const float4* qr = reinterpret_cast<const float4*>(q + size_t(qi) * D);
-  const float4* rr = reinterpret_cast<const float4*>(db + size_t(r) * D);
-  double acc = 0.0;
-  for (int c = lane; c < (D >> 2); c += 32) {
-    const float4 a = __ldg(qr + c);
-    const float4 b = ldg_stream(rr + c);
-    double d;
-    d = double(a.x) - double(b.x); acc = fma(d, d, acc);
-    d = double(a.y) - double(b.y); acc = fma(d, d, acc);
-    d = double(a.z) - double(b.z); acc = fma(d, d, acc);
-    d = double(a.w) - double(b.w); acc = fma(d, d, acc);
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) d2[p] = acc;
 }
 
 // order the kKeep rescored candidates of one query by (d^2, idx), emit the top-k, certify.  One warp per query.
@@ -378,8 +393,8 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __res
   uint32_t mi[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    md[u] = d2[size_t(q) * kKeep + lane + 32 * u];
     mi[u] = sel_idx[size_t(q) * kKeep + lane + 32 * u];
+    md[u] = mi[u] != 0xffffffffu ? d2[size_t(q) * kKeep + lane + 32 * u] : INFINITY;      // empty slots are not rescored
   }
   int rank[2] = {0, 0};
   for (int src = 0; src < 32; ++src) {
@@ -430,18 +445,25 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const uint32_t* __res
 // each the bound of one actual row); bound[q] = the k-th smallest of the G*k values: k distinct rows of the database have an
 // exact distance at or below it.  One warp per query; every element finds its rank in the union by binary search in
 // the other lists (ties: by list, then position), the one of rank k-1 is the answer.
+constexpr int kBoundStage = 512;                     // G * k values per query staged in shared memory (8 ranks x k <= 32: 256)
 __global__ void __launch_bounds__(256) knn_bound_reduce_kernel(const float* __restrict__ ub_all, int G, int Q, int k,
                                                                float* __restrict__ bound) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ float s_ub[8][kBoundStage];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
   if (q >= Q) return;
+  const bool staged = G * k <= kBoundStage;          // the query's G lists side by side in shared memory
+  if (staged) {
+    for (int e = lane; e < G * k; e += 32) s_ub[warp][e] = ub_all[(size_t(e / k) * Q + q) * k + (e % k)];
+    __syncwarp();
+  }
   for (int e = lane; e < G * k; e += 32) {
     const int g = e / k, j = e - g * k;
-    const float v = ub_all[(size_t(g) * Q + q) * k + j];
+    const float v = staged ? s_ub[warp][e] : ub_all[(size_t(g) * Q + q) * k + j];
     int rank = j;
     for (int g2 = 0; g2 < G && rank < k; ++g2) {
       if (g2 == g) continue;
-      const float* l = ub_all + (size_t(g2) * Q + q) * k;
+      const float* l = staged ? &s_ub[warp][g2 * k] : ub_all + (size_t(g2) * Q + q) * k;
       int lo = 0, hi = k;              // entries of list g2 ordered before (v, g): < v, or == v when g2 < g
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -644,32 +666,62 @@ __device__ __forceinline__ bool pair_less(double d0, long long i0, double d1, lo
 
 // shard g's lists start at d_all + g*stride / i_all + g*stride (elements): lets one packed all-gather buffer
 // [G][dist Q*k | idx Q*k] feed the merge without a repack
+// One warp per query.  The query's G lists (G*k (distance, index) pairs; 8 ranks x 25: 3.2 KB) are staged in shared
+// memory when they fit, so that the G-1 binary searches of every entry run there instead of in global memory; the
+// searches cover only the real prefix of a list (a two-phase call returns ~k/G rows per rank, the rest is (inf, -1)
+// padding), and padding is ranked only when the lists together hold fewer than k rows.
+constexpr int kMergeStage = 256;                     // staged pairs per query (8 warps x 256 x 16 B = 32 KB per CTA)
+constexpr int kMergeLists = 64;                      // staged list lengths
 __global__ void __launch_bounds__(256) topk_merge_kernel(const double* __restrict__ d_all, const long long* __restrict__ i_all,
                                                          int G, int Q, int k, long long stride, double* __restrict__ d,
                                                          long long* __restrict__ i) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)G * Q * k) return;
-  const int g = int(e / ((long long)Q * k));
-  const long long rem = e - (long long)g * Q * k;
-  const int q = int(rem / k), j = int(rem - (long long)q * k);
-  const double md = d_all[(size_t)g * stride + rem];
-  const long long mi = i_all[(size_t)g * stride + rem];
-  // rank = number of entries, over all shard lists of this query, that order before (md, mi)
-  int rank = j;    // entries before it in its own (sorted) list
-  for (int g2 = 0; g2 < G; ++g2) {
-    if (g2 == g) continue;
-    const double* ld = d_all + (size_t)g2 * stride + (size_t)q * k;
-    const long long* li = i_all + (size_t)g2 * stride + (size_t)q * k;
-    int lo = 0, hi = k;                 // first position whose entry is NOT less than mine
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (pair_less(ld[mid], li[mid], md, mi)) lo = mid + 1; else hi = mid;
+  __shared__ double s_d[8][kMergeStage];
+  __shared__ long long s_i[8][kMergeStage];
+  __shared__ int s_real[8][kMergeLists];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * 8 + warp;
+  if (q >= Q) return;
+  const int n = G * k;
+  const bool staged = n <= kMergeStage && G <= kMergeLists;
+  int total_real = 0;
+  if (staged) {
+    for (int g = lane; g < G; g += 32) s_real[warp][g] = 0;
+    __syncwarp();
+    for (int e = lane; e < n; e += 32) {
+      const int g = e / k, j = e - g * k;
+      s_d[warp][e] = d_all[(size_t)g * stride + (size_t)q * k + j];
+      const long long v = i_all[(size_t)g * stride + (size_t)q * k + j];
+      s_i[warp][e] = v;
+      if (v >= 0) atomicAdd(&s_real[warp][g], 1);
     }
-    rank += lo;
+    __syncwarp();
+    for (int g = lane; g < G; g += 32) total_real += s_real[warp][g];
+    total_real = __reduce_add_sync(0xffffffffu, total_real);
   }
-  if (rank < k) {
-    d[(size_t)q * k + rank] = mi < 0 ? INFINITY : md;
-    i[(size_t)q * k + rank] = mi < 0 ? -1ll : mi;
+  for (int e = lane; e < n; e += 32) {
+    const int g = e / k, j = e - g * k;
+    const double md = staged ? s_d[warp][e] : d_all[(size_t)g * stride + (size_t)q * k + j];
+    const long long mi = staged ? s_i[warp][e] : i_all[(size_t)g * stride + (size_t)q * k + j];
+    if (staged && mi < 0 && total_real >= k) continue;         // padding cannot reach the output
+    // rank = number of entries, over all shard lists of this query, that order before (md, mi)
+    int rank = j;    // entries before it in its own (sorted) list
+    for (int g2 = 0; g2 < G && rank < k; ++g2) {
+      if (g2 == g) continue;
+      const double* ld = staged ? &s_d[warp][g2 * k] : d_all + (size_t)g2 * stride + (size_t)q * k;
+      const long long* li = staged ? &s_i[warp][g2 * k] : i_all + (size_t)g2 * stride + (size_t)q * k;
+      // first position whose entry is NOT less than mine; padding (inf, -1) orders after every real entry and ties with
+      // other padding, so for a real entry the search stops at the real prefix
+      int lo = 0, hi = (staged && mi >= 0) ? s_real[warp][g2] : k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pair_less(ld[mid], li[mid], md, mi)) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      d[(size_t)q * k + rank] = mi < 0 ? INFINITY : md;
+      i[(size_t)q * k + rank] = mi < 0 ? -1ll : mi;
+    }
   }
 }
 
@@ -946,12 +998,14 @@ static int chunk_queries(int Q, int64_t R, int Dp) {
   return int(cq);
 }
 
-static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* base, size_t bytes) {
+// one_chunk: the layout of the two-phase (sharded) query, whose first phase has nothing to pipeline the chunks against and
+// runs ONE tensor launch over all queries; scl_knn_query_workspace_bytes returns the larger of the two layouts.
+static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* base, size_t bytes, bool one_chunk = false) {
   Carver c(base, bytes);
   const int Dp = pad64(D);
   QueryWs tmp;
   QueryWs* o = w ? w : &tmp;
-  o->chunk_q = chunk_queries(Q, R, Dp);
+  o->chunk_q = one_chunk ? Q : chunk_queries(Q, R, Dp);
   o->nchunks = (Q + o->chunk_q - 1) / o->chunk_q;
   int mb, nt, NR, tpr, gm;
   knn_tc_tiling(o->chunk_q, R, Dp, &mb, &nt, &NR, &tpr, &gm);
@@ -1142,7 +1196,7 @@ extern "C" int scl_knn_build(const float* db, int64_t R, int D, void* shadow, si
 
 extern "C" int scl_knn_query_workspace_bytes(int64_t R, int D, int Q, int k, size_t* bytes) {
   if (!bytes || R < 1 || Q < 1 || k < 1 || D < 4 || (D & 3)) return SCL_ERR_BAD_ARG;
-  *bytes = query_ws_layout(R, D, Q, k, nullptr, nullptr, 0);
+  *bytes = std::max(query_ws_layout(R, D, Q, k, nullptr, nullptr, 0), query_ws_layout(R, D, Q, k, nullptr, nullptr, 0, true));
   return SCL_OK;
 }
 
@@ -1226,10 +1280,8 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
                                               w.qn2 + q0, w.qexp + q0, h, w.sel_idx + size_t(q0) * kKeep, w.sel_T + q0,
                                               w.sel_n + q0, nullptr, nullptr);
     SCL_LAUNCH_CHECK();
-    const long long pairs = (long long)nq * kKeep;
-    knn_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, ps>>>(db, queries + size_t(q0) * D, D,
-                                                                 w.sel_idx + size_t(q0) * kKeep, pairs,
-                                                                 w.d2 + size_t(q0) * kKeep);
+    knn_rescore_kernel<<<nq, 256, 0, ps>>>(db, queries + size_t(q0) * D, D, w.sel_idx + size_t(q0) * kKeep,
+                                           w.d2 + size_t(q0) * kKeep);
     SCL_LAUNCH_CHECK();
     knn_finalize_kernel<<<(nq + 7) / 8, 256, 0, ps>>>(w.sel_idx + size_t(q0) * kKeep, w.d2 + size_t(q0) * kKeep, w.sel_T + q0,
                                                       w.sel_n + q0, w.qn2 + q0, w.qexp + q0, h, nq, k, idx_offset,
@@ -1277,7 +1329,7 @@ extern "C" int scl_knn_query_begin(const float* db, const void* shadow, int64_t 
   if (rc) return rc;
   if ((rc = check_device())) return rc;
   QueryWs w;
-  const size_t need = query_ws_layout(R, D, Q, k, &w, workspace, workspace_bytes);
+  const size_t need = query_ws_layout(R, D, Q, k, &w, workspace, workspace_bytes, true);
   if (workspace_bytes < need) return SCL_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const char* sb = static_cast<const char*>(shadow);
@@ -1289,8 +1341,7 @@ extern "C" int scl_knn_query_begin(const float* db, const void* shadow, int64_t 
   knn_query_prep_kernel<<<Q, 256, 0, stream>>>(queries, Q, D, Dp, h, w.qh, w.qmul, w.qn2, w.qexp);
   SCL_LAUNCH_CHECK();
   SCL_CUDA_TRY(cudaMemsetAsync(w.q_thr, 0xff, size_t(Q) * sizeof(unsigned int), stream));
-  // one tensor pass over all queries (chunks, if the workspace was laid out for them, run back to back on this stream:
-  // there is nothing to overlap them with before the ranks have agreed on the bound)
+  // ONE tensor launch over all queries (one_chunk layout: nchunks == 1; the loop is the general form)
   HelperCtx& hc = t_helper[device_slot()];
   const bool timing = g_knn_timing.load(std::memory_order_relaxed) != 0;
   for (int c = 0; c < w.nchunks; ++c) {
@@ -1332,7 +1383,7 @@ extern "C" int scl_knn_query_end(const float* db, const void* shadow, int64_t R,
   if (rc) return rc;
   if ((rc = check_device())) return rc;
   QueryWs w;
-  const size_t need = query_ws_layout(R, D, Q, k, &w, workspace, workspace_bytes);
+  const size_t need = query_ws_layout(R, D, Q, k, &w, workspace, workspace_bytes, true);
   if (workspace_bytes < need) return SCL_ERR_WORKSPACE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const char* sb = static_cast<const char*>(shadow);
@@ -1343,8 +1394,7 @@ extern "C" int scl_knn_query_end(const float* db, const void* shadow, int64_t R,
   knn_apply_cutoff_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(bound, w.sel_score, w.sel_T, w.sel_n, w.qn2, w.qexp, h, Q, w.sel_idx,
                                                            w.cut_mode, w.stats);
   SCL_LAUNCH_CHECK();
-  const long long pairs = (long long)Q * kKeep;
-  knn_rescore_kernel<<<unsigned((pairs + 7) / 8), 256, 0, stream>>>(db, queries, D, w.sel_idx, pairs, w.d2);
+  knn_rescore_kernel<<<Q, 256, 0, stream>>>(db, queries, D, w.sel_idx, w.d2);
   SCL_LAUNCH_CHECK();
   knn_finalize_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(w.sel_idx, w.d2, w.sel_T, w.sel_n, w.qn2, w.qexp, h, Q, k, idx_offset, 0, 0,
                                                        dist, reinterpret_cast<long long*>(idx), w.kth_d2, w.flag_list, w.stats,
@@ -1387,8 +1437,7 @@ extern "C" int scl_topk_merge(const double* d_all, const int64_t* i_all, int G, 
   if (shard_stride < (int64_t)Q * k) return SCL_ERR_BAD_SHAPE;
   int rc = check_device();
   if (rc) return rc;
-  const long long n = (long long)G * Q * k;
-  topk_merge_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  topk_merge_kernel<<<(Q + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_all, reinterpret_cast<const long long*>(i_all), G, Q, k, (long long)shard_stride, d, reinterpret_cast<long long*>(i));
   SCL_LAUNCH_CHECK();
   return SCL_OK;
