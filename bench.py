@@ -300,7 +300,8 @@ def retrieval_run(args, torch, dist_mod, rank, world, R, Q, data="gaussian", ste
     torch.cuda.synchronize()
     if dist_mod is not None:
         index = retrieval.ShardedKDTree.__new__(retrieval.ShardedKDTree)
-        index.group, index.world, index.local, index.two_phase = None, world, tree, not args.single_phase
+        index.group, index.world, index.local, index.two_phase, index._side = None, world, tree, not args.single_phase, None
+        index.pipelined = not args.no_group_pipeline
     else:
         index = tree
 
@@ -735,6 +736,8 @@ def main():
     ap.add_argument("--data", default="gaussian", choices=["gaussian", "clustered"])
     ap.add_argument("--single-phase", action="store_true",
                     help="N > 1: the plain sharded protocol (every rank returns its full local top-k) instead of the two-phase one")
+    ap.add_argument("--no-group-pipeline", action="store_true",
+                    help="N > 1, two-phase: second phase after the whole tensor launch instead of per query group under it")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--time-build", action="store_true", default=True)

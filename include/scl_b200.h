@@ -264,13 +264,33 @@ int scl_knn_query(const float* db, const void* shadow, int64_t R, int D, const f
  *                         scl_knn_query (certificate / second tensor stage / exact scan).  Same workspace (and the SAME
  *                         workspace contents: no other call on it in between), shadow, queries and sizes as `begin`.
  * SCL_ERR_UNSUPPORTED when this shard's sizes do not take the tensor pass (see scl_knn_query): such a rank contributes
- * +inf to the gather and calls scl_knn_query instead.  stats as in scl_knn_query. */
+ * +inf to the gather and calls scl_knn_query instead.  stats as in scl_knn_query.
+ *
+ * Pipelined form.  The first phase is ONE persistent tensor launch that works through the queries in groups
+ * (scl_knn_query_groups: n_groups groups of group_queries queries, the last possibly shorter; a function of D and Q
+ * only, so every rank sees the same groups) and signals the completion of each group in device memory:
+ *   scl_knn_query_launch       query preparation + the tensor launch, on `stream`
+ *   scl_knn_query_begin_group  makes ITS stream wait for the signal of `group` (cuStreamWaitValue32 -- no SM is held
+ *                              while waiting), then selects the candidates of the group's queries; ub = the group's rows
+ *   scl_knn_query_end_group    as scl_knn_query_end for the group's queries; bound / dist / idx = the group's rows
+ * Called on a second stream, the selection, the exchange, the rescore and the shard merge of group g overlap the tensor
+ * kernel's work on group g+1.  group = -1 addresses all queries (begin = launch + begin_group(-1), end = end_group(-1)).
+ * launch, begin_group and end_group of one query belong to ONE host thread; the next launch on the same workspace must
+ * be ordered after the last end_group (e.g. the launch stream waits for the second stream). */
 int scl_knn_query_begin(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
                         float* ub, void* workspace, size_t workspace_bytes, scl_stream_t stream);
 int scl_knn_bound_reduce(const float* ub_all, int G, int Q, int k, float* bound, scl_stream_t stream);
 int scl_knn_query_end(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
                       int64_t idx_offset, const float* bound, double* dist, int64_t* idx, int32_t* stats,
                       void* workspace, size_t workspace_bytes, scl_stream_t stream);
+int scl_knn_query_groups(int D, int Q, int* n_groups, int* group_queries);
+int scl_knn_query_launch(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                         void* workspace, size_t workspace_bytes, scl_stream_t stream);
+int scl_knn_query_begin_group(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                              int group, float* ub, void* workspace, size_t workspace_bytes, scl_stream_t stream);
+int scl_knn_query_end_group(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                            int64_t idx_offset, int group, const float* bound, double* dist, int64_t* idx, int32_t* stats,
+                            void* workspace, size_t workspace_bytes, scl_stream_t stream);
 
 /* Test hook: when set (per host thread) and capacity_floats >= Q*R, the tensor pass of the following scl_knn_query
  * calls on this thread also writes its raw fp16-pass scores [Q,R] there.  NULL switches it off. */

@@ -84,6 +84,12 @@ PROTOTYPES = {
                                 c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_knn_query_begin": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_size_t,
                                       c_ptr]),
+    "scl_knn_query_groups": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "scl_knn_query_launch": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr, C.c_size_t, c_ptr]),
+    "scl_knn_query_begin_group": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr,
+                                            C.c_size_t, c_ptr]),
+    "scl_knn_query_end_group": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int64, C.c_int, c_ptr,
+                                          c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "scl_knn_bound_reduce": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "scl_knn_query_end": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int64, c_ptr, c_ptr,
                                     c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),

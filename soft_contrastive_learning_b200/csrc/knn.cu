@@ -12,6 +12,7 @@
 //                |fp16 score - exact score|, every row that is not a candidate has d^2 >= T + |q|^2 - eps, so
 //                when the k-th exact candidate distance is below that, the exact top-k is inside the candidate set.
 //                Queries that fail the certificate are recomputed by the exact scan.  No approximation is returned.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
 
@@ -910,6 +911,7 @@ static thread_local size_t t_dbg_capacity = 0;
 // i run while the tensor pass of chunk i+1 occupies the launching stream, and the events that order the two.
 struct HelperCtx {
   cudaStream_t h = nullptr;
+  cudaEvent_t armed = nullptr;          // scl_knn_query_launch: group counters zeroed (consumer streams wait on it)
   std::vector<cudaEvent_t> ev;          // ordering events (timing disabled)
   std::vector<cudaEvent_t> tev;         // timing events (scl_knn_timing)
   int get(std::vector<cudaEvent_t>& pool, size_t i, unsigned flags, cudaEvent_t* out) {
@@ -946,6 +948,8 @@ struct QueryWs {
   uint32_t* cand_i[2];
   int* cand_cnt[2];
   unsigned int* sync_ctr[2];
+  unsigned int* sync_ctr2;      // pacing counters of the stage-2 launches (may run while a first pass is still in flight)
+  unsigned int* group_done;     // [kMaxGroups] completion counters of the first pass (TcArgs::group_done)
   // stage 2
   __half* qh2;
   float* qmul2;
@@ -1042,6 +1046,8 @@ static size_t query_ws_layout(int64_t R, int D, int Q, int k, QueryWs* w, void* 
       o->sync_ctr[sl] = o->sync_ctr[0];
     }
   }
+  o->sync_ctr2 = c.take<unsigned int>(kSyncMax);
+  o->group_done = c.take<unsigned int>(kMaxGroups);
   o->qh2 = c.take<__half>(size_t(o->q2max) * Dp);
   o->qmul2 = c.take<float>(o->q2max);
   o->thr2 = c.take<float>(o->q2max);
@@ -1087,13 +1093,14 @@ static int run_exact(const float* db, int64_t R, int D, const float* queries, co
 // tiling + launch of the tensor pass for `nq` queries whose per-query arrays start at qh / qmul / q_thr
 static int launch_tensor(const QueryWs& w, int slot, const __half* qh, const float* qmul, unsigned int* q_thr, int nq,
                          int64_t R, int Dp, const float* rn, const __half* dbh, float* dbg, bool collect,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, bool signal_groups = false) {
   TcArgs a = {};
   a.rn = rn; a.qmul = qmul; a.Q = nq; a.R = int(R); a.Dp = Dp;
   knn_tc_tiling(nq, R, Dp, &a.num_m_blocks, &a.num_n_tiles, &a.NR, &a.tiles_per_range, &a.group_m);
   a.cand_s = w.cand_s[slot]; a.cand_i = w.cand_i[slot]; a.cand_cnt = w.cand_cnt[slot]; a.q_thr = q_thr;
-  a.sync_ctr = w.sync_ctr[slot];
+  a.sync_ctr = collect ? w.sync_ctr2 : w.sync_ctr[slot];
   SCL_CUDA_TRY(cudaMemsetAsync(a.sync_ctr, 0, size_t(kSyncMax) * sizeof(unsigned int), stream));
+  if (signal_groups) a.group_done = w.group_done;      // zeroed by the caller
   a.dbg_scores = dbg;
   if (collect) {
     a.collect = 1; a.fixed_thr = w.thr2; a.coll_idx = w.coll_idx; a.coll_cnt = w.cnt2; a.coll_cap = kCollectCap;
@@ -1313,56 +1320,165 @@ extern "C" int scl_knn_query(const float* db, const void* shadow, int64_t R, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sharded retrieval in two phases: between them the ranks agree on a per-query bound (all-reduce MIN), so
-// that each rank rescoring exactly only the candidates that can still enter the GLOBAL top-k -- k/G of them on average,
-// not the k..64 its own top-k would need.  The rescore is the part of a rank's work that does not shrink with the shard.
+// Sharded retrieval in two phases: between them the ranks exchange the score bounds of their k best
+// candidates, so that each rank rescoring exactly only the candidates that can still enter the GLOBAL top-k -- ~k/G of
+// them, not the k..64 its own top-k would need.  The first phase is ONE persistent tensor launch over all queries; it
+// signals the completion of every query group (TcArgs::group_done), and the per-group entry points below wait for that
+// signal ON THEIR STREAM (cuStreamWaitValue32): launched on a second stream, the merge / exchange / rescore / shard merge
+// of group g run while the tensor kernel streams the database for group g+1.
 static int two_phase_ok(int64_t R, int D, int Q, int k) {
   return use_tensor_pass(R, D, Q, k, 2) ? SCL_OK : SCL_ERR_UNSUPPORTED;
 }
 
-extern "C" int scl_knn_query_begin(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
-                                   float* ub, void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
-  if (!db || !shadow || !queries || !ub || !workspace) return SCL_ERR_BAD_ARG;
+struct Groups {
+  int n, group_q;          // number of query groups, queries per group (the last may hold fewer)
+  int unit_q, group_m;     // queries per work unit, units per group
+  int arrivals_per_item;   // epilogue warps that signal one work item
+};
+// depends on Q and D only (knn_tc_tiling's group_m does not look at R): every rank of a sharded call sees the same groups
+static Groups group_layout(int Q, int Dp) {
+  int mb, nt, NR, tpr, gm;
+  knn_tc_tiling(Q, 1 << 20, Dp, &mb, &nt, &NR, &tpr, &gm);
+  const bool pair = knob_or(KNOB_KNN_TC_VARIANT, 2) >= 2;
+  const int mu = pair ? (mb + 1) / 2 : mb;
+  Groups g;
+  g.unit_q = pair ? 256 : 128;
+  g.group_m = gm;
+  g.n = (mu + gm - 1) / gm;
+  g.group_q = gm * g.unit_q;
+  g.arrivals_per_item = pair ? 8 : 4;
+  return g;
+}
+
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static int stream_wait_geq(cudaStream_t stream, const unsigned int* addr, unsigned int value) {
+  static StreamWaitValue32Fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SCL_CUDA_TRY(cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !p) {
+      set_last_error("cuStreamWaitValue32 entry point", cudaErrorUnknown);
+      return SCL_ERR_CUDA;
+    }
+    fn = reinterpret_cast<StreamWaitValue32Fn>(p);
+  }
+  const CUresult r = fn(reinterpret_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuStreamWaitValue32", cudaErrorUnknown);
+    return SCL_ERR_CUDA;
+  }
+  return SCL_OK;
+}
+
+struct ShardView {
+  const ShadowHeader* h;
+  const float* rn;
+  const __half* dbh;
+  int Dp;
+};
+static ShardView shard_view(const void* shadow, int64_t R, int D) {
+  const char* sb = static_cast<const char*>(shadow);
+  return {reinterpret_cast<const ShadowHeader*>(sb), reinterpret_cast<const float*>(sb + shadow_norm_off()),
+          reinterpret_cast<const __half*>(sb + shadow_data_off(R)), pad64(D)};
+}
+
+// query range of a group (group < 0: all queries)
+static void group_range(const Groups& g, int Q, int group, int* q0, int* nq) {
+  if (group < 0) { *q0 = 0; *nq = Q; return; }
+  *q0 = group * g.group_q;
+  *nq = std::min(g.group_q, Q - *q0);
+}
+
+static int two_phase_args(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                          void* workspace, size_t workspace_bytes, QueryWs* w) {
+  if (!db || !shadow || !queries || !workspace) return SCL_ERR_BAD_ARG;
   if (R < 1 || Q < 1 || k < 1 || D < 4 || (D & 3)) return SCL_ERR_BAD_SHAPE;
   if (!aligned16(db) || !aligned16(queries) || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return SCL_ERR_ALIGN;
   int rc = two_phase_ok(R, D, Q, k);
   if (rc) return rc;
+  if (group_layout(Q, pad64(D)).n > kMaxGroups) return SCL_ERR_UNSUPPORTED;     // > 64 x ~5120 queries at D = 4096: split the call
   if ((rc = check_device())) return rc;
+  const size_t need = query_ws_layout(R, D, Q, k, w, workspace, workspace_bytes, true);
+  return workspace_bytes < need ? SCL_ERR_WORKSPACE : SCL_OK;
+}
+
+extern "C" int scl_knn_query_groups(int D, int Q, int* n_groups, int* group_queries) {
+  if (!n_groups || !group_queries || Q < 1 || D < 4 || (D & 3)) return SCL_ERR_BAD_ARG;
+  const Groups g = group_layout(Q, pad64(D));
+  *n_groups = g.n;
+  *group_queries = g.n == 1 ? Q : g.group_q;
+  return SCL_OK;
+}
+
+extern "C" int scl_knn_query_launch(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                                    void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
   QueryWs w;
-  const size_t need = query_ws_layout(R, D, Q, k, &w, workspace, workspace_bytes, true);
-  if (workspace_bytes < need) return SCL_ERR_WORKSPACE;
+  int rc = two_phase_args(db, shadow, R, D, queries, Q, k, workspace, workspace_bytes, &w);
+  if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const char* sb = static_cast<const char*>(shadow);
-  const ShadowHeader* h = reinterpret_cast<const ShadowHeader*>(sb);
-  const float* rn = reinterpret_cast<const float*>(sb + shadow_norm_off());
-  const __half* dbh = reinterpret_cast<const __half*>(sb + shadow_data_off(R));
-  const int Dp = pad64(D);
-  SCL_CUDA_TRY(cudaMemsetAsync(w.stats, 0, 8 * sizeof(int), stream));
-  knn_query_prep_kernel<<<Q, 256, 0, stream>>>(queries, Q, D, Dp, h, w.qh, w.qmul, w.qn2, w.qexp);
+  const ShardView sv = shard_view(shadow, R, D);
+  knn_query_prep_kernel<<<Q, 256, 0, stream>>>(queries, Q, D, sv.Dp, sv.h, w.qh, w.qmul, w.qn2, w.qexp);
   SCL_LAUNCH_CHECK();
   SCL_CUDA_TRY(cudaMemsetAsync(w.q_thr, 0xff, size_t(Q) * sizeof(unsigned int), stream));
-  // ONE tensor launch over all queries (one_chunk layout: nchunks == 1; the loop is the general form)
   HelperCtx& hc = t_helper[device_slot()];
   const bool timing = g_knn_timing.load(std::memory_order_relaxed) != 0;
-  for (int c = 0; c < w.nchunks; ++c) {
-    const int q0 = c * w.chunk_q, nq = std::min(w.chunk_q, Q - q0), slot = c & 1;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    if (timing) {
-      if ((rc = hc.get(hc.tev, size_t(2 * c), cudaEventDefault, &t0))) return rc;
-      if ((rc = hc.get(hc.tev, size_t(2 * c + 1), cudaEventDefault, &t1))) return rc;
-      SCL_CUDA_TRY(cudaEventRecord(t0, stream));
-    }
-    rc = launch_tensor(w, slot, w.qh + size_t(q0) * Dp, w.qmul + q0, w.q_thr + q0, nq, R, Dp, rn, dbh, nullptr, false, stream);
-    if (rc) return rc;
-    if (timing) SCL_CUDA_TRY(cudaEventRecord(t1, stream));
-    int mb, nt, NR, tpr, gm;
-    knn_tc_tiling(nq, R, Dp, &mb, &nt, &NR, &tpr, &gm);
-    knn_cand_merge_kernel<<<nq, 256, 0, stream>>>(w.cand_s[slot], w.cand_i[slot], w.cand_cnt[slot], w.q_thr + q0, NR, k,
-                                                  w.qn2 + q0, w.qexp + q0, h, w.sel_idx + size_t(q0) * kKeep, w.sel_T + q0,
-                                                  w.sel_n + q0, w.sel_score + size_t(q0) * kKeep, ub + size_t(q0) * k);
-    SCL_LAUNCH_CHECK();
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  if (timing) {
+    if ((rc = hc.get(hc.tev, 0, cudaEventDefault, &t0))) return rc;
+    if ((rc = hc.get(hc.tev, 1, cudaEventDefault, &t1))) return rc;
+    SCL_CUDA_TRY(cudaEventRecord(t0, stream));
   }
+  // ONE tensor launch over all queries (one_chunk layout), signalling the completion of every query group.  The
+  // counters are zeroed on this stream first; a consumer stream must not look at them before that (ev_armed).
+  SCL_CUDA_TRY(cudaMemsetAsync(w.group_done, 0, size_t(kMaxGroups) * sizeof(unsigned int), stream));
+  if (!hc.armed) SCL_CUDA_TRY(cudaEventCreateWithFlags(&hc.armed, cudaEventDisableTiming));
+  SCL_CUDA_TRY(cudaEventRecord(hc.armed, stream));
+  rc = launch_tensor(w, 0, w.qh, w.qmul, w.q_thr, Q, R, sv.Dp, sv.rn, sv.dbh, nullptr, false, stream, true);
+  if (rc) return rc;
+  if (timing) SCL_CUDA_TRY(cudaEventRecord(t1, stream));
   return SCL_OK;
+}
+
+extern "C" int scl_knn_query_begin_group(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q,
+                                         int k, int group, float* ub, void* workspace, size_t workspace_bytes,
+                                         scl_stream_t stream_) {
+  if (!ub) return SCL_ERR_BAD_ARG;
+  QueryWs w;
+  int rc = two_phase_args(db, shadow, R, D, queries, Q, k, workspace, workspace_bytes, &w);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const ShardView sv = shard_view(shadow, R, D);
+  const Groups g = group_layout(Q, sv.Dp);
+  if (group >= g.n) return SCL_ERR_BAD_ARG;
+  int mb, nt, NR, tpr, gm;
+  knn_tc_tiling(Q, R, sv.Dp, &mb, &nt, &NR, &tpr, &gm);
+  // wait, on THIS stream, until the launch of this thread has armed the counters and the tensor kernel has signalled
+  // every work item of the group(s)
+  HelperCtx& hc = t_helper[device_slot()];
+  if (!hc.armed) return SCL_ERR_BAD_ARG;                   // no scl_knn_query_launch on this thread
+  SCL_CUDA_TRY(cudaStreamWaitEvent(stream, hc.armed, 0));
+  const int mu = g.unit_q == 256 ? (mb + 1) / 2 : mb;
+  for (int gg = 0; gg < g.n; ++gg) {
+    if (group >= 0 && gg != group) continue;
+    const int units = std::min(gm, mu - gg * gm);
+    if ((rc = stream_wait_geq(stream, w.group_done + gg, unsigned(units) * unsigned(NR) * unsigned(g.arrivals_per_item)))) return rc;
+  }
+  int q0, nq;
+  group_range(g, Q, group, &q0, &nq);
+  knn_cand_merge_kernel<<<nq, 256, 0, stream>>>(w.cand_s[0] + size_t(q0) * NR * kCandCap, w.cand_i[0] + size_t(q0) * NR * kCandCap,
+                                                w.cand_cnt[0] + size_t(q0) * NR, w.q_thr + q0, NR, k, w.qn2 + q0, w.qexp + q0, sv.h,
+                                                w.sel_idx + size_t(q0) * kKeep, w.sel_T + q0, w.sel_n + q0,
+                                                w.sel_score + size_t(q0) * kKeep, ub);
+  SCL_LAUNCH_CHECK();
+  return SCL_OK;
+}
+
+extern "C" int scl_knn_query_begin(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                                   float* ub, void* workspace, size_t workspace_bytes, scl_stream_t stream) {
+  int rc = scl_knn_query_launch(db, shadow, R, D, queries, Q, k, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return scl_knn_query_begin_group(db, shadow, R, D, queries, Q, k, -1, ub, workspace, workspace_bytes, stream);
 }
 
 extern "C" int scl_knn_bound_reduce(const float* ub_all, int G, int Q, int k, float* bound, scl_stream_t stream) {
@@ -1374,48 +1490,59 @@ extern "C" int scl_knn_bound_reduce(const float* ub_all, int G, int Q, int k, fl
   return SCL_OK;
 }
 
-extern "C" int scl_knn_query_end(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
-                                 int64_t idx_offset, const float* bound, double* dist, int64_t* idx, int32_t* stats,
-                                 void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
-  if (!db || !shadow || !queries || !bound || !dist || !idx || !workspace) return SCL_ERR_BAD_ARG;
-  if (R < 1 || Q < 1 || k < 1 || D < 4 || (D & 3)) return SCL_ERR_BAD_SHAPE;
-  int rc = two_phase_ok(R, D, Q, k);
-  if (rc) return rc;
-  if ((rc = check_device())) return rc;
+extern "C" int scl_knn_query_end_group(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                                       int64_t idx_offset, int group, const float* bound, double* dist, int64_t* idx,
+                                       int32_t* stats, void* workspace, size_t workspace_bytes, scl_stream_t stream_) {
+  if (!bound || !dist || !idx) return SCL_ERR_BAD_ARG;
   QueryWs w;
-  const size_t need = query_ws_layout(R, D, Q, k, &w, workspace, workspace_bytes, true);
-  if (workspace_bytes < need) return SCL_ERR_WORKSPACE;
+  int rc = two_phase_args(db, shadow, R, D, queries, Q, k, workspace, workspace_bytes, &w);
+  if (rc) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const char* sb = static_cast<const char*>(shadow);
-  const ShadowHeader* h = reinterpret_cast<const ShadowHeader*>(sb);
-  const float* rn = reinterpret_cast<const float*>(sb + shadow_norm_off());
-  const __half* dbh = reinterpret_cast<const __half*>(sb + shadow_data_off(R));
-  const int Dp = pad64(D);
-  knn_apply_cutoff_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(bound, w.sel_score, w.sel_T, w.sel_n, w.qn2, w.qexp, h, Q, w.sel_idx,
-                                                           w.cut_mode, w.stats);
+  const ShardView sv = shard_view(shadow, R, D);
+  const Groups g = group_layout(Q, sv.Dp);
+  if (group >= g.n) return SCL_ERR_BAD_ARG;
+  int q0, nq;
+  group_range(g, Q, group, &q0, &nq);
+  // everything below indexes the per-query arrays of the workspace with GLOBAL query numbers (the refused-query lists
+  // hold global numbers); the caller's bound / dist / idx hold the group's rows only, so their bases are shifted back
+  double* dist0 = dist - size_t(q0) * k;
+  int64_t* idx0 = idx - size_t(q0) * k;
+  SCL_CUDA_TRY(cudaMemsetAsync(w.stats, 0, 8 * sizeof(int), stream));
+  knn_apply_cutoff_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(bound, w.sel_score + size_t(q0) * kKeep, w.sel_T + q0, w.sel_n + q0,
+                                                            w.qn2 + q0, w.qexp + q0, sv.h, nq, w.sel_idx + size_t(q0) * kKeep,
+                                                            w.cut_mode + q0, w.stats);
   SCL_LAUNCH_CHECK();
-  knn_rescore_kernel<<<Q, 256, 0, stream>>>(db, queries, D, w.sel_idx, w.d2);
+  knn_rescore_kernel<<<nq, 256, 0, stream>>>(db, queries + size_t(q0) * D, D, w.sel_idx + size_t(q0) * kKeep,
+                                             w.d2 + size_t(q0) * kKeep);
   SCL_LAUNCH_CHECK();
-  knn_finalize_kernel<<<(Q + 7) / 8, 256, 0, stream>>>(w.sel_idx, w.d2, w.sel_T, w.sel_n, w.qn2, w.qexp, h, Q, k, idx_offset, 0, 0,
-                                                       dist, reinterpret_cast<long long*>(idx), w.kth_d2, w.flag_list, w.stats,
-                                                       w.cut_mode);
+  knn_finalize_kernel<<<(nq + 7) / 8, 256, 0, stream>>>(w.sel_idx + size_t(q0) * kKeep, w.d2 + size_t(q0) * kKeep, w.sel_T + q0,
+                                                        w.sel_n + q0, w.qn2 + q0, w.qexp + q0, sv.h, nq, k, idx_offset, 0, q0, dist,
+                                                        reinterpret_cast<long long*>(idx), w.kth_d2 + q0, w.flag_list, w.stats,
+                                                        w.cut_mode + q0);
   SCL_LAUNCH_CHECK();
   int hs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   SCL_CUDA_TRY(cudaMemcpyAsync(hs, w.stats, sizeof(hs), cudaMemcpyDeviceToHost, stream));
   SCL_CUDA_TRY(cudaStreamSynchronize(stream));
-  if (g_knn_timing.load(std::memory_order_relaxed) != 0) {
+  const bool last = group < 0 || group == g.n - 1;
+  if (last && g_knn_timing.load(std::memory_order_relaxed) != 0) {
     HelperCtx& hc = t_helper[device_slot()];
-    double sum = 0.0;
-    for (int c = 0; c < w.nchunks && size_t(2 * c + 1) < hc.tev.size(); ++c) {
+    if (hc.tev.size() >= 2) {
+      SCL_CUDA_TRY(cudaEventSynchronize(hc.tev[1]));      // the tensor kernel may still be retiring on ITS stream
       float ms = 0.0f;
-      SCL_CUDA_TRY(cudaEventElapsedTime(&ms, hc.tev[2 * c], hc.tev[2 * c + 1]));
-      sum += double(ms);
+      SCL_CUDA_TRY(cudaEventElapsedTime(&ms, hc.tev[0], hc.tev[1]));
+      std::lock_guard<std::mutex> lk(g_knn_timing_mu);
+      g_knn_tc_ms_sum += double(ms);
+      g_knn_tc_calls += 1;
     }
-    std::lock_guard<std::mutex> lk(g_knn_timing_mu);
-    g_knn_tc_ms_sum += sum;
-    g_knn_tc_calls += 1;
   }
-  return resolve_refused(hs, db, R, D, queries, Q, k, idx_offset, 2, dist, idx, stats, w, h, rn, dbh, Dp, w.nchunks, stream);
+  return resolve_refused(hs, db, R, D, queries, nq, k, idx_offset, 2, dist0, idx0, stats, w, sv.h, sv.rn, sv.dbh, sv.Dp, 1, stream);
+}
+
+extern "C" int scl_knn_query_end(const float* db, const void* shadow, int64_t R, int D, const float* queries, int Q, int k,
+                                 int64_t idx_offset, const float* bound, double* dist, int64_t* idx, int32_t* stats,
+                                 void* workspace, size_t workspace_bytes, scl_stream_t stream) {
+  return scl_knn_query_end_group(db, shadow, R, D, queries, Q, k, idx_offset, -1, bound, dist, idx, stats, workspace,
+                                 workspace_bytes, stream);
 }
 
 extern "C" int scl_knn_timing(int enable, double* tensor_pass_ms_sum, int* tensor_pass_calls) {

@@ -47,7 +47,13 @@ struct TcArgs {
   // and found in L2 by everybody else.  nullptr / sync_total == 0 disables it.
   unsigned int* sync_ctr;   // [kSyncMax], zeroed before the launch
   int sync_total, sync_window, sync_subs;
+  // Completion signal per query group (optional, zeroed before the launch): every epilogue warp bumps group_done[g] after
+  // it has written the candidate lists of one work item of group g (release: fence, then the atomic), so that a consumer
+  // on ANOTHER stream (cuStreamWaitValue32 on the counter) can merge / rescore the queries of a finished group while
+  // this kernel is still streaming the database for the next one.  Arrivals per item: 4 warps x CTAs of the worker.
+  unsigned int* group_done;
 };
+constexpr int kMaxGroups = 64;
 constexpr int kSyncMax = 1 << 16;
 constexpr int kCollectCap = 2048;   // stage-2 list capacity per query
 

@@ -444,6 +444,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
       // end of the item: publish the list length (<= kCandCap entries, unsorted; knn_cand_merge_kernel filters them by
       // the final published threshold and sorts what is left)
       if (valid && !collect) a.cand_cnt[size_t(q) * a.NR + range] = cnt;
+      if (a.group_done != nullptr) {
+        __threadfence();                     // this lane's list entries and count are visible device-wide ...
+        __syncwarp();
+        if (lane == 0) {                     // ... before the warp's arrival is
+          const int groups = (m_units + a.group_m - 1) / a.group_m;
+          int g = item / (a.group_m * a.NR);
+          if (g > groups - 1) g = groups - 1;
+          atomicAdd(a.group_done + g, 1u);
+        }
+      }
     }
   }
 

@@ -10,6 +10,7 @@ over the ranks and merges per-shard lists after one NCCL all-gather (SURVEY.md s
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -81,34 +82,62 @@ class KDTree:
         self.last_stats = stats
         return dist, idx
 
-    # -- sharded two-phase query (scl_knn_query_begin / _end): see ShardedKDTree.query_device --------------------------
+    # -- sharded two-phase query (include/scl_b200.h: scl_knn_query_launch / _begin_group / _end_group) -----------------
     UNSUPPORTED = -7
 
-    def query_begin(self, q, k, bound):
-        """First phase on device queries ``q`` [Q,D] f32: fills ``bound`` [Q,k] f32 (upper bounds on the distances of this
-        shard's k best candidates) and returns the state to hand to ``query_end``; None (bounds = +inf) when this shard
-        does not take the tensor pass."""
+    @staticmethod
+    def query_groups(D, Q):
+        """(n_groups, queries per group) of the first phase's tensor launch; the same on every rank."""
+        n, gq = C.c_int(), C.c_int()
+        check(lib().scl_knn_query_groups(int(D), int(Q), C.byref(n), C.byref(gq)), "scl_knn_query_groups")
+        return n.value, gq.value
+
+    def query_launch(self, q, k):
+        """Query preparation + the tensor launch over all of ``q`` [Q,D] f32 on the current stream.  Returns the state to
+        hand to ``query_begin_group`` / ``query_end_group``; None when this shard does not take the tensor pass."""
         Q = q.shape[0]
         L = lib()
         nbytes = C.c_size_t()
         check(L.scl_knn_query_workspace_bytes(self.R, self.D, Q, k, C.byref(nbytes)), "scl_knn_query_workspace_bytes")
         ws = _ws(nbytes.value, q.device)
-        rc = L.scl_knn_query_begin(_p(self.db), _p(self.shadow), self.R, self.D, _p(q), Q, k, _p(bound), _p(ws), ws.numel(),
-                                   _stream())
+        rc = L.scl_knn_query_launch(_p(self.db), _p(self.shadow), self.R, self.D, _p(q), Q, k, _p(ws), ws.numel(), _stream())
         if rc == self.UNSUPPORTED:
-            bound.fill_(float("inf"))
             return None
-        check(rc, "scl_knn_query_begin")
+        check(rc, "scl_knn_query_launch")
+        self._group_stats = []
         return ws
 
-    def query_end(self, state, q, k, bound, out):
+    def query_begin_group(self, state, q, k, group, ub):
+        """On the CURRENT stream: wait for the tensor kernel's completion signal of ``group`` (-1: all queries), then
+        fill ``ub`` [nq,k] f32 with the upper bounds on the distances of this shard's k best candidates."""
+        check(lib().scl_knn_query_begin_group(_p(self.db), _p(self.shadow), self.R, self.D, _p(q), q.shape[0], k, int(group),
+                                              _p(ub), _p(state), state.numel(), _stream()), "scl_knn_query_begin_group")
+
+    def query_end_group(self, state, q, k, group, bound, out):
+        """Second phase for the queries of ``group``: ``bound`` [nq] f32, ``out`` = (dist [nq,k] f64, idx [nq,k] i64)."""
         dist, idx = out
-        Q = q.shape[0]
         stats = torch.zeros(8, dtype=torch.int32, device=q.device)
-        check(lib().scl_knn_query_end(_p(self.db), _p(self.shadow), self.R, self.D, _p(q), Q, k, self.index_offset, _p(bound),
-                                      _p(dist), _p(idx), _p(stats), _p(state), state.numel(), _stream()), "scl_knn_query_end")
-        self.last_stats = stats
+        check(lib().scl_knn_query_end_group(_p(self.db), _p(self.shadow), self.R, self.D, _p(q), q.shape[0], k,
+                                            self.index_offset, int(group), _p(bound), _p(dist), _p(idx), _p(stats), _p(state),
+                                            state.numel(), _stream()), "scl_knn_query_end_group")
+        self._group_stats.append(stats)
+        tot = torch.stack(self._group_stats).sum(0)
+        tot[3], tot[6] = 2, len(self._group_stats)          # path; "chunks" = groups processed
+        self.last_stats = tot
         return dist, idx
+
+    def query_begin(self, q, k, bound):
+        """Unpipelined first phase: launch + candidates of all queries; ``bound`` [Q,k] f32.  None (bounds = +inf) when this
+        shard does not take the tensor pass."""
+        state = self.query_launch(q, k)
+        if state is None:
+            bound.fill_(float("inf"))
+            return None
+        self.query_begin_group(state, q, k, -1, bound)
+        return state
+
+    def query_end(self, state, q, k, bound, out):
+        return self.query_end_group(state, q, k, -1, bound, out)
 
     def query(self, X, k=1, return_distance=True, sort_results=True, force_path=0):
         """``KDTree.query`` as called at evaluation/top-n.py:106.  Results are always sorted ascending."""
@@ -145,12 +174,16 @@ def topk_merge(d_all, i_all):
     return d, i
 
 
-def topk_merge_packed(packed, G, Q, k):
+def topk_merge_packed(packed, G, Q, k, out=None):
     """Merge G packed per-rank messages ``packed`` [G, 2, Q, k] (8-byte words: [g,0] = float64 distances, [g,1] = int64
-    indices) as one all-gather delivers them, without a repack."""
+    indices) as one all-gather delivers them, without a repack.  ``out`` = (d, i) contiguous [Q,k] destinations."""
     assert packed.is_contiguous() and packed.element_size() == 8 and packed.numel() == G * 2 * Q * k
-    d = torch.empty((Q, k), dtype=torch.float64, device=packed.device)
-    i = torch.empty((Q, k), dtype=torch.int64, device=packed.device)
+    if out is None:
+        d = torch.empty((Q, k), dtype=torch.float64, device=packed.device)
+        i = torch.empty((Q, k), dtype=torch.int64, device=packed.device)
+    else:
+        d, i = out
+        assert d.shape == (Q, k) and i.shape == (Q, k) and d.is_contiguous() and i.is_contiguous()
     base = packed.data_ptr()
     check(lib().scl_topk_merge(C.c_void_p(base), C.c_void_p(base + Q * k * 8), G, Q, k, 2 * Q * k, _p(d), _p(i), _stream()),
           "scl_topk_merge")
@@ -166,10 +199,12 @@ class ShardedKDTree:
 
     TWO_PHASE_MAX_K = 32          # the tensor pass serves k <= 32 (scl_knn_query)
 
-    def __init__(self, X_local, index_offset, group=None, two_phase=True):
+    def __init__(self, X_local, index_offset, group=None, two_phase=True, pipelined=True):
         import torch.distributed as dist
         self.group = group
         self.two_phase = bool(two_phase)
+        self.pipelined = bool(pipelined)      # two-phase: overlap the second phase of a query group with the tensor kernel
+        self._side = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local = KDTree(X_local, index_offset=index_offset)
 
@@ -182,27 +217,69 @@ class ShardedKDTree:
         if q.dim() == 1:
             q = q[None]
         Q = q.shape[0]
-        # one packed message per rank: [2, Q, k] 8-byte words (float64 distances | int64 indices), ONE all-gather
-        mine = torch.empty((2, Q, k), dtype=torch.int64, device=q.device)
-        out = (mine[0].view(torch.float64), mine[1])
-        if self.two_phase and force_path == 0 and k <= self.TWO_PHASE_MAX_K and q.shape[1] == self.local.D:
-            # Two phases (include/scl_b200.h: scl_knn_query_begin): the ranks agree on a per-query bound on the k-th
-            # global distance (all-gather of [Q,k] floats, k-th smallest of the union) and each then rescores only what
-            # can still make the global top-k.  The condition above depends only on values every rank shares, so all of them take this branch.
-            ub_all = torch.empty((self.world, Q, k), dtype=torch.float32, device=q.device)
-            ub = ub_all[dist.get_rank(self.group)]
-            state = self.local.query_begin(q, k, ub)
-            dist.all_gather_into_tensor(ub_all.view(self.world * Q, k), ub, group=self.group)
-            bound = bound_reduce(ub_all)
-            if state is None:
-                self.local.query_device(q, k, 0, out=out)
-            else:
-                self.local.query_end(state, q, k, bound, out)
-        else:
-            self.local.query_device(q, k, force_path, out=out)
-        packed = torch.empty((self.world, 2, Q, k), dtype=torch.int64, device=q.device)
-        dist.all_gather_into_tensor(packed.view(self.world * 2 * Q, k), mine.view(2 * Q, k), group=self.group)
-        return topk_merge_packed(packed, self.world, Q, k)
+        if not (self.two_phase and force_path == 0 and k <= self.TWO_PHASE_MAX_K):
+            # one packed message per rank: [2, Q, k] 8-byte words (float64 distances | int64 indices), ONE all-gather
+            mine = torch.empty((2, Q, k), dtype=torch.int64, device=q.device)
+            self.local.query_device(q, k, force_path, out=(mine[0].view(torch.float64), mine[1]))
+            packed = torch.empty((self.world, 2, Q, k), dtype=torch.int64, device=q.device)
+            dist.all_gather_into_tensor(packed.view(self.world * 2 * Q, k), mine.view(2 * Q, k), group=self.group)
+            return topk_merge_packed(packed, self.world, Q, k)
+        return self._query_two_phase(q, k)
+
+    def _query_two_phase(self, q, k):
+        """Two phases, pipelined over the query groups of ONE tensor launch (include/scl_b200.h: scl_knn_query_launch).
+
+        Phase 1 on the current stream: the tensor kernel works through the queries group by group and signals each group
+        in device memory.  On a second stream, per group: wait for the signal, select the candidates, all-gather the ranks'
+        [nq,k] score bounds, take the k-th smallest of the union as the bound on the global k-th distance, rescore only what
+        can still make the GLOBAL top-k, all-gather the packed lists, merge -- all of it under the tensor kernel's work on
+        the next group.  The branch condition and the groups depend only on values every rank shares (k, Q, D), so the
+        collectives match; a rank whose shard is too small for the tensor pass contributes +inf and answers with the
+        plain query."""
+        import torch.distributed as dist
+        G, rank = self.world, dist.get_rank(self.group)
+        Q, dev = q.shape[0], q.device
+        n_groups, gq = KDTree.query_groups(self.local.D, Q) if self.pipelined else (1, Q)
+        on_gpu = dev.type == "cuda" and n_groups > 1          # (one group, or the CPU protocol tests: no second stream)
+        if on_gpu:
+            main = torch.cuda.current_stream(dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(dev)
+            side = self._side
+        # every buffer is allocated on the main stream (its allocator pool) and main waits for the side stream at the end
+        d = torch.empty((Q, k), dtype=torch.float64, device=dev)
+        i = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        bufs = []
+        for g in range(n_groups):
+            nq = min(gq, Q - g * gq)
+            bufs.append((torch.empty((G, nq, k), dtype=torch.float32, device=dev),          # gathered score bounds
+                         torch.empty((2, nq, k), dtype=torch.int64, device=dev),            # this rank's packed lists
+                         torch.empty((G, 2, nq, k), dtype=torch.int64, device=dev)))        # gathered packed lists
+        state = self.local.query_launch(q, k)
+        if on_gpu and state is None:
+            side.wait_stream(main)                            # (tensor path: begin_group waits for the launch's own event)
+        with (torch.cuda.stream(side) if on_gpu else contextlib.nullcontext()):
+            for g in range(n_groups):
+                q0, nq = g * gq, min(gq, Q - g * gq)
+                ub_all, mine, packed = bufs[g]
+                ub = ub_all[rank]
+                gid = g if n_groups > 1 else -1
+                if state is None:
+                    ub.fill_(float("inf"))
+                else:
+                    self.local.query_begin_group(state, q, k, gid, ub)
+                dist.all_gather_into_tensor(ub_all.view(G * nq, k), ub, group=self.group)
+                bound = bound_reduce(ub_all)
+                out = (mine[0].view(torch.float64), mine[1])
+                if state is None:
+                    self.local.query_device(q[q0:q0 + nq], k, 0, out=out)
+                else:
+                    self.local.query_end_group(state, q, k, gid, bound, out)
+                dist.all_gather_into_tensor(packed.view(G * 2 * nq, k), mine.view(2 * nq, k), group=self.group)
+                topk_merge_packed(packed, G, nq, k, out=(d[q0:q0 + nq], i[q0:q0 + nq]))
+        if on_gpu:
+            main.wait_stream(side)
+        return d, i
 
     def query_from_host(self, q_host, k=1):
         """Queries that live in (pinned) host memory, identical on every rank: each rank copies only its 1/G slice over

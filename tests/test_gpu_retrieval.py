@@ -95,52 +95,86 @@ def test_exact_ties_across_shards_and_the_merge(cuda_lib):
     assert (i[:, :4].cpu().numpy() == np.arange(50)[:, None] + 1500 * np.arange(4)[None]).all()
 
 
-def _two_phase(db, qry, G, k, bounds=None):
-    """G shards of `db` on ONE GPU through scl_knn_query_begin -> scl_knn_bound_reduce -> scl_knn_query_end -> merge: the
-    sharded protocol of retrieval.ShardedKDTree with the all-gather replaced by torch.stack."""
+def _two_phase(db, qry, G, k, bounds=None, pipelined=False):
+    """G shards of `db` on ONE GPU through the two-phase protocol of retrieval.ShardedKDTree with the all-gathers replaced
+    by writes into one [G, ...] buffer: scl_knn_query_begin -> scl_knn_bound_reduce -> scl_knn_query_end -> merge, or
+    (pipelined) scl_knn_query_launch on the current stream and, per query group on a SECOND stream,
+    scl_knn_query_begin_group (stream wait on the tensor kernel's signal) -> bound reduce -> scl_knn_query_end_group."""
     from soft_contrastive_learning_b200 import retrieval
     R, Q = db.shape[0], qry.shape[0]
     q = torch.tensor(qry, device="cuda")
-    trees, states, bnds = [], [], []
+    trees = []
     for r in range(G):
         lo, hi = bounds[r] if bounds else retrieval.shard_bounds(R, G, r)
         trees.append(retrieval.KDTree(db[lo:hi], index_offset=lo))
-        b = torch.empty((Q, k), dtype=torch.float32, device="cuda")
-        states.append(trees[-1].query_begin(q, k, b))
-        bnds.append(b)
-    ub_all = torch.stack(bnds)
-    bound = retrieval.bound_reduce(ub_all)
-    assert torch.equal(bound, ub_all.permute(1, 0, 2).reshape(Q, G * k).sort(1).values[:, k - 1])
-    packed = torch.empty((G, 2, Q, k), dtype=torch.int64, device="cuda")
-    stats = []
-    for r in range(G):
-        out = (packed[r, 0].view(torch.float64), packed[r, 1])
-        if states[r] is None:
-            trees[r].query_device(q, k, 0, out=out)
-        else:
-            trees[r].query_end(states[r], q, k, bound, out)
-        stats.append(trees[r].stats())
-    d, i = retrieval.topk_merge_packed(packed, G, Q, k)
-    real = (packed[:, 1] >= 0).sum().item()
-    return d.cpu().numpy(), i.cpu().numpy(), real, stats
+    d = torch.empty((Q, k), dtype=torch.float64, device="cuda")
+    i = torch.empty((Q, k), dtype=torch.int64, device="cuda")
+    real, n_groups = 0, 1
+    if not pipelined:
+        ub_all = torch.empty((G, Q, k), dtype=torch.float32, device="cuda")
+        states = [trees[r].query_begin(q, k, ub_all[r]) for r in range(G)]
+        bound = retrieval.bound_reduce(ub_all)
+        assert torch.equal(bound, ub_all.permute(1, 0, 2).reshape(Q, G * k).sort(1).values[:, k - 1])
+        packed = torch.empty((G, 2, Q, k), dtype=torch.int64, device="cuda")
+        for r in range(G):
+            out = (packed[r, 0].view(torch.float64), packed[r, 1])
+            if states[r] is None:
+                trees[r].query_device(q, k, 0, out=out)
+            else:
+                trees[r].query_end(states[r], q, k, bound, out)
+        retrieval.topk_merge_packed(packed, G, Q, k, out=(d, i))
+        real = (packed[:, 1] >= 0).sum().item()
+    else:
+        n_groups, gq = retrieval.KDTree.query_groups(db.shape[1], Q)
+        main, side = torch.cuda.current_stream(), torch.cuda.Stream()
+        states = [trees[r].query_launch(q, k) for r in range(G)]          # G persistent tensor launches queued on `main`
+        if any(st is None for st in states):
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for g in range(n_groups):
+                q0, nq = g * gq, min(gq, Q - g * gq)
+                ub_all = torch.empty((G, nq, k), dtype=torch.float32, device="cuda")
+                for r in range(G):
+                    if states[r] is None:
+                        ub_all[r].fill_(float("inf"))
+                    else:
+                        trees[r].query_begin_group(states[r], q, k, g, ub_all[r])
+                bound = retrieval.bound_reduce(ub_all)
+                packed = torch.empty((G, 2, nq, k), dtype=torch.int64, device="cuda")
+                for r in range(G):
+                    out = (packed[r, 0].view(torch.float64), packed[r, 1])
+                    if states[r] is None:
+                        trees[r].query_device(q[q0:q0 + nq], k, 0, out=out)
+                    else:
+                        trees[r].query_end_group(states[r], q, k, g, bound, out)
+                retrieval.topk_merge_packed(packed, G, nq, k, out=(d[q0:q0 + nq], i[q0:q0 + nq]))
+                real += (packed[:, 1] >= 0).sum().item()
+        main.wait_stream(side)
+    torch.cuda.synchronize()
+    return d.cpu().numpy(), i.cpu().numpy(), real, [t.stats() for t in trees], n_groups
 
 
 @pytest.mark.parametrize("R,Q,D,k,G", [(40000, 300, 256, 25, 4), (24000, 129, 4096, 25, 3), (64000, 64, 128, 5, 8),
                                        (9000, 257, 64, 32, 2)])
-def test_two_phase_sharded_query_is_exact(cuda_lib, R, Q, D, k, G):
+@pytest.mark.parametrize("pipelined", [False, True], ids=["begin_end", "group_pipeline"])
+def test_two_phase_sharded_query_is_exact(cuda_lib, tune, R, Q, D, k, G, pipelined):
     """Between the two phases the shards agree on a bound on the k-th global distance; each rescoring only what can
     still reach the global top-k.  Result = float64 brute force over the whole database, and the shards together return
     far fewer than G*k rows per query."""
     db, qry, *_ = synth.retrieval_problem(R=R, Q=Q, D=D, seed=15)
-    d, i, real, stats = _two_phase(db, qry, G, k)
+    if pipelined:
+        tune("SCL_KNN_GROUP_M", 1)                               # one work unit (256 queries) per group: several groups
+    d, i, real, stats, n_groups = _two_phase(db, qry, G, k, pipelined=pipelined)
     rd, ri = orr.knn_bruteforce(db, qry, k)
     check_exact(d, i, rd, ri)
     assert Q * k <= real <= 2 * Q * k, (real, Q * k, G)          # plain protocol: G * Q * k
+    assert n_groups == (-(-Q // 256) if pipelined else 1)
     for st in stats:
         assert st["path"] == 2 and st["n_certified"] + st["n_fallback"] == Q, st
 
 
-def test_two_phase_ties_duplicates_and_refusals(cuda_lib):
+@pytest.mark.parametrize("pipelined", [False, True], ids=["begin_end", "group_pipeline"])
+def test_two_phase_ties_duplicates_and_refusals(cuda_lib, tune, pipelined):
     """Adversarial for the bound: exact duplicates that straddle shard borders (equal scores at the cut; the row left out
     must be STRICTLY farther), near-duplicate clusters living on ONE shard (that shard has more than 64 rows inside the
     bound: it falls back to its exact local top-k through the second tensor stage / scan while the others trim), a shard
@@ -155,23 +189,28 @@ def test_two_phase_ties_duplicates_and_refusals(cuda_lib):
     qry = np.concatenate([base[:40], centers, base[100:120] + 0.2 * rng.standard_normal((20, D)).astype(np.float32)], 0)
     R = db.shape[0]                                                  # 9100 rows
     bounds = [(0, 2500), (2500, 5000), (5000, 8600), (8600, 9100)]   # last shard: 500 rows < 1024 -> unsupported
-    d, i, real, stats = _two_phase(db, qry, 4, k, bounds)
+    if pipelined:
+        tune("SCL_KNN_GROUP_M", 1)
+    d, i, real, stats, _ = _two_phase(db, qry, 4, k, bounds, pipelined=pipelined)
     rd, ri = orr.knn_bruteforce_exact(db, qry, k)
     check_exact(d, i, rd, ri)
     assert (i[:40, :3] == np.arange(40)[:, None] + np.array([0, 3000, 6900])[None]).all() and (d[:40, :3] == 0).all()
     assert stats[3]["path"] == 1                                     # the small shard took the plain exact scan
     assert stats[2]["n_fallback"] >= 6, stats[2]                     # the cluster shard refused the cluster queries
     # the same database through ONE index gives the same bits
+    tune("SCL_KNN_GROUP_M", None)
     d1, i1 = retrieval.KDTree(db).query(qry, k=k, force_path=2)
     assert np.array_equal(i1, i) and np.array_equal(d1, d)
 
 
-def test_two_phase_large_shards_match_single_index(cuda_lib, tune):
-    """Config-4-like sizes (D = 4096, 10 000 queries in two pipelined chunks) on 2 shards of one GPU."""
+@pytest.mark.parametrize("pipelined", [False, True], ids=["begin_end", "group_pipeline"])
+def test_two_phase_large_shards_match_single_index(cuda_lib, pipelined):
+    """Config-4-like sizes (D = 4096; 6000 queries = two query groups of the tensor launch) on 2 shards of one GPU: the
+    second stream merges / rescoring group 0 while the tensor kernel works on group 1."""
     from soft_contrastive_learning_b200 import retrieval
     db, qry, *_ = synth.retrieval_problem(R=60000, Q=6000, D=4096, seed=17)
-    d, i, real, stats = _two_phase(db, qry, 2, 25)
-    assert stats[0]["chunks"] >= 1
+    d, i, real, stats, n_groups = _two_phase(db, qry, 2, 25, pipelined=pipelined)
+    assert n_groups == (2 if pipelined else 1) and stats[0]["chunks"] == n_groups
     d1, i1 = retrieval.KDTree(db).query(qry, k=25)
     assert np.array_equal(i1, i) and np.array_equal(d1, d)
     assert real <= 0.85 * 2 * 6000 * 25                       # plain protocol: 2 * Q * k; here ~25 + the rows within 2 eps

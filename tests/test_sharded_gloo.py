@@ -28,23 +28,33 @@ class _OracleLocal:
         self.D = self.X.shape[1]
         self.db = torch.zeros(1)                 # the device the shard lives on (CPU in this test)
 
-    # two-phase protocol (scl_knn_query_begin / _end) restated exactly: the bounds are the shard's k smallest exact squared
-    # distances, the second phase returns the shard's rows at or below the reduced bound, padded with (inf, -1)
-    def query_begin(self, q, k, bound):
+    # two-phase protocol (scl_knn_query_launch / _begin_group / _end_group) restated exactly: the bounds are the shard's k
+    # smallest exact squared distances, the second phase returns the shard's rows at or below the reduced bound, padded
+    # with (inf, -1); queries in two groups (ragged: 9 = 5 + 4)
+    @staticmethod
+    def query_groups(D, Q):
+        gq = (Q + 1) // 2
+        return (Q + gq - 1) // gq, gq
+
+    def query_launch(self, q, k):
         from oracle import retrieval as orr
         if self.X.shape[0] < max(k, self.min_rows):           # "this shard does not take the tensor pass"
-            bound.fill_(float("inf"))
             return None
-        d, _ = orr.knn_bruteforce_exact(self.X, np.asarray(q), k)
-        bound.copy_(torch.from_numpy((d ** 2).astype(np.float32) * (1 + 1e-6)))
-        return "state"
+        self.kept = 0
+        return orr.knn_bruteforce_exact(self.X, np.asarray(q), k)
 
-    def query_end(self, state, q, k, bound, out):
-        from oracle import retrieval as orr
-        assert state == "state"
-        d, i = orr.knn_bruteforce_exact(self.X, np.asarray(q), k)
+    def _rows(self, state, group):
+        gq = self.query_groups(self.D, state[0].shape[0])[1]
+        return slice(group * gq, min(state[0].shape[0], (group + 1) * gq))
+
+    def query_begin_group(self, state, q, k, group, ub):
+        d = state[0][self._rows(state, group)]
+        ub.copy_(torch.from_numpy((d ** 2).astype(np.float32) * (1 + 1e-6)))
+
+    def query_end_group(self, state, q, k, group, bound, out):
+        d, i = (a[self._rows(state, group)] for a in state)
         keep = d ** 2 <= bound.numpy()[:, None].astype(np.float64)
-        self.kept = int(keep.sum())
+        self.kept += int(keep.sum())
         out[0].copy_(torch.from_numpy(np.where(keep, d, np.inf)))
         out[1].copy_(torch.from_numpy(np.where(keep, i + self.off, -1)))
         return out
@@ -92,8 +102,14 @@ def _worker(rank, world, port, R, D, Q, k, out):
         retrieval.bound_reduce = lambda ub_all: torch.from_numpy(                  # [G,Q,k] -> k-th smallest of the union
             np.sort(ub_all.permute(1, 0, 2).reshape(ub_all.shape[1], -1).numpy(), axis=1)[:, ub_all.shape[2] - 1].copy())
         # the packed message [G, 2, Q, k] of 8-byte words, as ONE all-gather delivers it
-        retrieval.topk_merge_packed = lambda packed, G, Q, k: _numpy_merge(packed[:, 0].contiguous().view(torch.float64),
-                                                                         packed[:, 1].contiguous())
+        def merge_packed(packed, G, Q, k, out=None):
+            d, i = _numpy_merge(packed[:, 0].contiguous().view(torch.float64), packed[:, 1].contiguous())
+            if out is None:
+                return d, i
+            out[0].copy_(d)
+            out[1].copy_(i)
+            return out
+        retrieval.topk_merge_packed = merge_packed
         tree = retrieval.ShardedKDTree(db[lo:hi], index_offset=lo)
         d, i = tree.query_device(qry, k)
         if hi - lo >= k:                           # the two-phase protocol ran and trimmed the per-rank lists
