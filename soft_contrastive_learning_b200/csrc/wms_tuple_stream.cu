@@ -639,6 +639,14 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   // backward with 10 consumer warps x 160 columns x 5 stages at 80 registers (2 CTAs per SM) ran 1.24-1.26 ms.
   // cp.async.bulk.prefetch.L2 of the chunks 4 / 8 positions beyond the ring: 1.07 / 1.09 ms (the prefetched lines push
   // the tuples waiting for their re-read out of L2).
+  // Round 2, the store path: the gradient block written IN PLACE over the descriptor block it came from (st.shared.v2,
+  // 2 wavefronts per 256 bytes instead of 8 sectors) and the finished chunk stored by the producer warp with
+  // cp.async.bulk shared -> global (25 rows x 896 bytes, one bulk group in flight, loads held back one position so the
+  // warp never blocks on wait_group.read): every parity test passed, 1.16 ms.  By elimination (same build with pieces
+  // removed): without the proxy fence 1.16, without the in-place writes 1.14, WITHOUT THE BULK STORES 0.925, with no
+  // output at all 0.90 ms -- the bulk store engine is slow on 896-byte rows at a 944-byte pitch, and the whole direct
+  // st.global path of this kernel costs only 0.055 ms: the stores are not what holds the kernel at 0.54 of HBM.  The
+  // 0.90 ms is Gram + weights + tensor-core backward with the SM's two CTAs interleaved (HBM reads alone: 0.26 ms).
   const int cfg = knob_or(KNOB_WMS_STREAM_CFG, TS == 5 ? 6 : 2);
   if (cfg == 6) return stream_launch<TS, 7, 224, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   // the wider register tiles (S > 25) need more registers than 16+ warps leave per thread
