@@ -56,6 +56,30 @@ def knn():
         with _lib.tuning(SCL_KNN_TC_VARIANT=v):
             tree.query(qry[:130], k=5, force_path=2)
     retrieval.recall_at_n(np.abs(np.random.default_rng(0).standard_normal((20, 25))) * 10)
+    # sharded two-phase protocol on one GPU: 2 shards, tensor launch with group signals, second stream per query group
+    q = torch.tensor(qry, device="cuda")
+    trees = [retrieval.KDTree(db[:2500]), retrieval.KDTree(db[2500:], index_offset=2500)]
+    with _lib.tuning(SCL_KNN_GROUP_M=1):
+        n_groups, gq = retrieval.KDTree.query_groups(64, 300)
+        side = torch.cuda.Stream()
+        states = [t.query_launch(q, 25) for t in trees]
+        dd = torch.empty((300, 25), dtype=torch.float64, device="cuda")
+        ii = torch.empty((300, 25), dtype=torch.int64, device="cuda")
+        with torch.cuda.stream(side):
+            for g in range(n_groups):
+                q0, nq = g * gq, min(gq, 300 - g * gq)
+                ub = torch.empty((2, nq, 25), dtype=torch.float32, device="cuda")
+                for r in range(2):
+                    trees[r].query_begin_group(states[r], q, 25, g, ub[r])
+                bound = retrieval.bound_reduce(ub)
+                packed = torch.empty((2, 2, nq, 25), dtype=torch.int64, device="cuda")
+                for r in range(2):
+                    trees[r].query_end_group(states[r], q, 25, g, bound, (packed[r, 0].view(torch.float64), packed[r, 1]))
+                retrieval.topk_merge_packed(packed, 2, nq, 25, out=(dd[q0:q0 + nq], ii[q0:q0 + nq]))
+        torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert np.array_equal(ii.cpu().numpy(), i), "two-phase != single index"
+    print("knn two-phase groups", n_groups, trees[0].stats())
 
 
 cases = {"wms": wms, "tuples": tuples, "flat": flat, "netvlad": nv, "knn": knn}
