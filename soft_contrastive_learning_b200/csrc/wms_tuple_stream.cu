@@ -647,6 +647,10 @@ static int stream_dispatch(const float* emb, const float* dist, int T, int S, in
   // output at all 0.90 ms -- the bulk store engine is slow on 896-byte rows at a 944-byte pitch, and the whole direct
   // st.global path of this kernel costs only 0.055 ms: the stores are not what holds the kernel at 0.54 of HBM.  The
   // 0.90 ms is Gram + weights + tensor-core backward with the SM's two CTAs interleaved (HBM reads alone: 0.26 ms).
+  // Forward only (need_bwd = false) 0.467 ms; with the Gram's FFMA2 removed (operand loads kept) 0.417; with the whole
+  // Gram loop skipped 0.312 (HBM floor of the read 0.26) and forward + backward 0.830: the Gram costs 0.125-0.155 ms that
+  // do not overlap with the streaming, the backward adds ~0.5 ms against 0.38 ms of its own HBM traffic (gradient
+  // write + the half of the re-read that misses L2).
   const int cfg = knob_or(KNOB_WMS_STREAM_CFG, TS == 5 ? 6 : 2);
   if (cfg == 6) return stream_launch<TS, 7, 224, true, true>(emb, dist, T, S, D, p, per_tuple, demb, kept, loss, counter, stream);
   // the wider register tiles (S > 25) need more registers than 16+ warps leave per thread
