@@ -301,7 +301,7 @@ def retrieval_run(args, torch, dist_mod, rank, world, R, Q, data="gaussian", ste
     if dist_mod is not None:
         index = retrieval.ShardedKDTree.__new__(retrieval.ShardedKDTree)
         index.group, index.world, index.local, index.two_phase, index._side = None, world, tree, not args.single_phase, None
-        index.pipelined = not args.no_group_pipeline
+        index.pipelined = args.group_pipeline
     else:
         index = tree
 
@@ -383,7 +383,7 @@ def retrieval_run(args, torch, dist_mod, rank, world, R, Q, data="gaussian", ste
     # sharded (two-phase): prep, tensor pass, candidate merge | bound reduce | cutoff, rescore, certificate, stats | shard merge
     launches = 1 + 4 * max(1, stats["chunks"]) + 1 + (1 if world > 1 else 0) + (4 * -(-nf // 2048) if nf else 0)
     if world > 1 and not args.single_phase:
-        launches += 2
+        launches += 2 + (4 * (max(1, stats["chunks"]) - 1) if args.group_pipeline else 0)
     return {"ms": ms, "ms_e2e": ms_e2e, "tc_ms": tc_avg_ms, "flops_per_launch": flops, "stats": stats, "clocks": clk,
             "rows_local": rows_local, "build_s": t_build_h2d, "launches_per_step": launches, "info": info, "steps": steps,
             "warmup": warmup}
@@ -736,8 +736,8 @@ def main():
     ap.add_argument("--data", default="gaussian", choices=["gaussian", "clustered"])
     ap.add_argument("--single-phase", action="store_true",
                     help="N > 1: the plain sharded protocol (every rank returns its full local top-k) instead of the two-phase one")
-    ap.add_argument("--no-group-pipeline", action="store_true",
-                    help="N > 1, two-phase: second phase after the whole tensor launch instead of per query group under it")
+    ap.add_argument("--group-pipeline", action="store_true",
+                    help="N > 1, two-phase: second phase per query group on a second stream under the tensor launch")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--time-build", action="store_true", default=True)

@@ -102,6 +102,10 @@ __global__ void __launch_bounds__(256) knn_build_convert_kernel(const float* __r
 // ---------------------------------------------------------------------------------------------
 // query preparation: fp16 copy with a per-query power-of-two scale, |q|^2 in float64
 // ---------------------------------------------------------------------------------------------
+// One CTA per query, the row held in registers between the two steps (max |q| / sum q^2, then scale + convert): one
+// pass over HBM with 16-byte loads and 8-byte stores for D <= 4096 (kPrepVec float4 per thread); the tail of a longer
+// row is read a second time (L2).
+constexpr int kPrepVec = 4;                           // float4 per thread in registers: D <= 4096 in one pass
 __global__ void __launch_bounds__(256) knn_query_prep_kernel(const float* __restrict__ q, int Q, int D, int Dp,
                                                              const ShadowHeader* __restrict__ h, __half* __restrict__ qh,
                                                              float* __restrict__ qmul, double* __restrict__ qn2,
@@ -110,13 +114,27 @@ __global__ void __launch_bounds__(256) knn_query_prep_kernel(const float* __rest
   __shared__ double s_acc[8];
   const int qi = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* row = q + size_t(qi) * D;
+  const float4* row4 = reinterpret_cast<const float4*>(q + size_t(qi) * D);
+  const int nv = D >> 2;                              // D % 4 == 0 (checked by the entry points)
+  float4 v[kPrepVec];
   float mx = 0.0f;
   double acc = 0.0;
-  for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    const float v = row[c];
-    mx = fmaxf(mx, fabsf(v));
-    acc = fma(double(v), double(v), acc);
+#pragma unroll
+  for (int u = 0; u < kPrepVec; ++u) {
+    const int c = threadIdx.x + u * 256;
+    v[u] = c < nv ? __ldg(row4 + c) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+#pragma unroll
+  for (int u = 0; u < kPrepVec; ++u) {
+    mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+    acc = fma(double(v[u].x), double(v[u].x), acc); acc = fma(double(v[u].y), double(v[u].y), acc);
+    acc = fma(double(v[u].z), double(v[u].z), acc); acc = fma(double(v[u].w), double(v[u].w), acc);
+  }
+  for (int c = threadIdx.x + kPrepVec * 256; c < nv; c += 256) {       // rows longer than the register tile
+    const float4 t = __ldg(row4 + c);
+    mx = fmaxf(fmaxf(mx, fmaxf(fabsf(t.x), fabsf(t.y))), fmaxf(fabsf(t.z), fabsf(t.w)));
+    acc = fma(double(t.x), double(t.x), acc); acc = fma(double(t.y), double(t.y), acc);
+    acc = fma(double(t.z), double(t.z), acc); acc = fma(double(t.w), double(t.w), acc);
   }
   mx = warp_max(mx);
   acc = warp_sum(acc);
@@ -126,7 +144,18 @@ __global__ void __launch_bounds__(256) knn_query_prep_kernel(const float* __rest
   for (int w = 0; w < (blockDim.x >> 5); ++w) { mx = fmaxf(mx, s_mx[w]); acc += s_acc[w]; }
   const int e = scale_exp_for(mx);
   const float sc = ldexpf(1.0f, e);
-  for (int c = threadIdx.x; c < Dp; c += blockDim.x) qh[size_t(qi) * Dp + c] = __float2half_rn(c < D ? row[c] * sc : 0.0f);
+  uint2* out = reinterpret_cast<uint2*>(qh + size_t(qi) * Dp);         // Dp % 64 == 0: 8-byte groups of four halves
+  auto pack = [&](const float4& t) {
+    const __half2 lo = __floats2half2_rn(t.x * sc, t.y * sc), hi = __floats2half2_rn(t.z * sc, t.w * sc);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+  };
+#pragma unroll
+  for (int u = 0; u < kPrepVec; ++u) {
+    const int c = threadIdx.x + u * 256;
+    if (c < nv) out[c] = pack(v[u]);
+  }
+  for (int c = threadIdx.x + kPrepVec * 256; c < nv; c += 256) out[c] = pack(__ldg(row4 + c));
+  for (int c = nv + threadIdx.x; c < (Dp >> 2); c += 256) out[c] = make_uint2(0u, 0u);      // zero padding up to Dp
   if (threadIdx.x == 0) {
     qmul[qi] = -2.0f * ldexpf(1.0f, -(e + h->scale_exp));
     qn2[qi] = acc;

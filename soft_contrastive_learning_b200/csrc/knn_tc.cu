@@ -309,8 +309,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
         const int t0 = range * a.tiles_per_range, t1 = min(a.num_n_tiles, t0 + a.tiles_per_range);
         for (int t = t0; t < t1; ++t, ++tile_count) {
           const uint32_t buf = tile_count % kBufs, use = tile_count / kBufs;
-          mbar_wait(&tail->tmem_empty[buf], (use & 1) ^ 1);       // epilogue(s) drained this accumulator
-          tc_fence_after();
+          // kNSub == 1: two accumulators, tile i+1 goes to the one the epilogue drained two tiles ago.
+          // kNSub == 2: ONE 512-column accumulator whose halves are released separately (tmem_empty[0] / [1]): the
+          // epilogue drains the first half, the MMAs of the next tile start on it while the second half is drained
+          if (kNSub == 1) {
+            mbar_wait(&tail->tmem_empty[buf], (use & 1) ^ 1);     // epilogue(s) drained this accumulator
+            tc_fence_after();
+          }
           const uint32_t d_tmem = tmem_base + buf * kBN;
           for (int kc = 0; kc < num_k; ++kc) {
             mbar_wait(&tail->full[stage], phase);
@@ -319,6 +324,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
             const uint64_t da = smem_desc_sw128(sa);
 #pragma unroll
             for (int sub = 0; sub < kNSub; ++sub) {
+              if (kNSub == 2 && kc == 0) {
+                mbar_wait(&tail->tmem_empty[sub], (use & 1) ^ 1);  // this half of the accumulator is drained
+                tc_fence_after();
+              }
               const uint64_t db = smem_desc_sw128(sa + kABytes + sub * Cfg::kBBytes);
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
@@ -432,13 +441,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_tc_kernel(const __grid_cons
             prune_row_fast(L, lane, a.cand_s, a.cand_i, base, cnt, thr, keys, thr_slot, my_thr);
             need &= need - 1;
           }
+          if (kNSub == 2 && (c & (kBN / 32 - 1)) == kBN / 32 - 1) {
+            // a 256-column half of the accumulator has been read by this warp: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              const int half = c / (kBN / 32);
+              if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tmem_empty[half]), 0));
+              else mbar_arrive(&tail->tmem_empty[half]);
+            }
+          }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          // the accumulator of BOTH CTAs must be drained before the leader's MMA warp may overwrite it
-          if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tmem_empty[buf]), 0));
-          else mbar_arrive(&tail->tmem_empty[buf]);
+        if (kNSub == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            // the accumulator of BOTH CTAs must be drained before the leader's MMA warp may overwrite it
+            if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tail->tmem_empty[buf]), 0));
+            else mbar_arrive(&tail->tmem_empty[buf]);
+          }
         }
       }
       // end of the item: publish the list length (<= kCandCap entries, unsorted; knn_cand_merge_kernel filters them by

@@ -199,11 +199,14 @@ class ShardedKDTree:
 
     TWO_PHASE_MAX_K = 32          # the tensor pass serves k <= 32 (scl_knn_query)
 
-    def __init__(self, X_local, index_offset, group=None, two_phase=True, pipelined=True):
+    def __init__(self, X_local, index_offset, group=None, two_phase=True, pipelined=False):
         import torch.distributed as dist
         self.group = group
         self.two_phase = bool(two_phase)
-        self.pipelined = bool(pipelined)      # two-phase: overlap the second phase of a query group with the tensor kernel
+        # two-phase: run the second phase per query group on a second stream under the tensor kernel.  Off by default:
+        # kernels that co-run with the persistent tensor kernel crawl (and slow it by 1-3 %), measured gain +0.7 % at
+        # N = 2 and none at N = 8
+        self.pipelined = bool(pipelined)
         self._side = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local = KDTree(X_local, index_offset=index_offset)

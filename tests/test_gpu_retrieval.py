@@ -440,6 +440,16 @@ def _nccl_worker(rank, world, port, out):
         d, i = tree.query_device(torch.tensor(qry, device="cuda"), k)
         d2, i2 = tree.query_from_host(torch.tensor(qry).pin_memory(), k)
         assert torch.equal(i, i2) and torch.equal(d, d2)
+        # the three protocol forms give the same bits: two-phase (default), two-phase per query group on a second
+        # stream (groups of 256 queries here), single phase
+        from soft_contrastive_learning_b200 import _lib
+        for kw, knobs in (({"pipelined": True}, {"SCL_KNN_GROUP_M": 1}), ({"two_phase": False}, {})):
+            with _lib.tuning(**knobs):
+                other = retrieval.ShardedKDTree.__new__(retrieval.ShardedKDTree)
+                other.__dict__.update(tree.__dict__)
+                other.two_phase, other.pipelined = kw.get("two_phase", True), kw.get("pipelined", False)
+                d3, i3 = other.query_device(torch.tensor(qry, device="cuda"), k)
+                assert torch.equal(i, i3) and torch.equal(d, d3), kw
         if rank == 0:
             np.savez(out, d=d.cpu().numpy(), i=i.cpu().numpy())
     finally:

@@ -44,6 +44,8 @@ class _OracleLocal:
         return orr.knn_bruteforce_exact(self.X, np.asarray(q), k)
 
     def _rows(self, state, group):
+        if group < 0:                                          # all queries (unpipelined protocol)
+            return slice(0, state[0].shape[0])
         gq = self.query_groups(self.D, state[0].shape[0])[1]
         return slice(group * gq, min(state[0].shape[0], (group + 1) * gq))
 
@@ -110,8 +112,11 @@ def _worker(rank, world, port, R, D, Q, k, out):
             out[1].copy_(i)
             return out
         retrieval.topk_merge_packed = merge_packed
-        tree = retrieval.ShardedKDTree(db[lo:hi], index_offset=lo)
+        tree = retrieval.ShardedKDTree(db[lo:hi], index_offset=lo, pipelined=True)     # per query group (two groups here)
         d, i = tree.query_device(qry, k)
+        whole = retrieval.ShardedKDTree(db[lo:hi], index_offset=lo)                    # default: all queries at once
+        dw, iw = whole.query_device(qry, k)
+        assert torch.equal(iw, i) and torch.equal(dw, d)
         if hi - lo >= k:                           # the two-phase protocol ran and trimmed the per-rank lists
             kept = torch.tensor([tree.local.kept])
             dist.all_reduce(kept)

@@ -26,14 +26,13 @@ def run(tag, **knobs):
             ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
         print(f"R={R} {tag:40s} prep+tensor {ms:7.3f} ms = {2.0*Q*R*D/(ms*1e-3)/1e12:6.0f} TF/s", flush=True)
-run("default")
-for w in (2, 8, 16, 64):
-    run(f"window={w}", SCL_KNN_SYNC_WINDOW=w)
-for s in (1, 2, 8):
-    run(f"subs={s}", SCL_KNN_SYNC_SUBS=s)
-run("no pacing", SCL_KNN_SYNC=0)
-for gm in (10, 40):
-    run(f"group_m={gm}", SCL_KNN_GROUP_M=gm)
-for nr in (18, 25, 49, 62):
-    run(f"ranges={nr}", SCL_KNN_RANGES=nr)
+run("default (variant 2)")
 run("variant 3 (256x512 tiles)", SCL_KNN_TC_VARIANT=3)
+for gm in (10, 20, 40):
+    run(f"variant 3, group_m={gm}", SCL_KNN_TC_VARIANT=3, SCL_KNN_GROUP_M=gm)
+for sb in (1, 2, 8):
+    run(f"variant 3, subs={sb}", SCL_KNN_TC_VARIANT=3, SCL_KNN_SYNC_SUBS=sb)
+for w in (2, 8):
+    run(f"variant 3, window={w}", SCL_KNN_TC_VARIANT=3, SCL_KNN_SYNC_WINDOW=w)
+for nr in (18, 25, 37, 49):
+    run(f"variant 3, ranges={nr}", SCL_KNN_TC_VARIANT=3, SCL_KNN_RANGES=nr)
