@@ -555,7 +555,12 @@ int make_tmap_3d(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, 
 
 static int tc_variant() {
   // 1 = single-CTA 128x256 tiles, 2 = CTA pairs 256x256 with double-buffered accumulators (default: the epilogue
-  // of tile i overlaps the MMAs of tile i+1), 3 = CTA pairs 256x512 (a quarter less L2->SM traffic, no overlap)
+  // of tile i overlaps the MMAs of tile i+1), 3 = CTA pairs 256x512 (a quarter less L2->SM traffic; ONE accumulator whose
+  // halves are released separately, so the next tile's MMAs start on the first half while the second is drained).
+  // Measured on a 125 000-row shard, 10 000 queries, one launch (round 2): variant 2 8.56 ms, variant 1 9.31 ms,
+  // variant 3 10.9 ms before and 10.8 ms after the separate release of the halves, 11.8 ms with software-pipelined
+  // tcgen05.ld in the epilogue (219-236 registers; reverted).  ncu of variant 3: L2->SM 62 GB (-25 %) at 6.2 TB/s,
+  // tensor pipe 50 %: it is neither L2- nor tensor-bound, its MMA warp waits for the 512-column drain.
   const int v = knob(KNOB_KNN_TC_VARIANT);
   return (v >= 1 && v <= 3) ? v : 2;
 }
