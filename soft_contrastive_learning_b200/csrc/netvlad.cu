@@ -227,9 +227,15 @@ __global__ void __launch_bounds__(256) nv_dcenters_kernel(const float* __restric
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * 64) return;
   const int k = i & 63;
-  float acc = 0.0f;
-  for (int b = 0; b < B; ++b) acc = fmaf(dV[size_t(b) * C * 64 + i], asum[b * 64 + k], acc);
-  dcenters[i] = acc;
+  // four independent chains (the 256 dependent loads of one chain made this 27 us at config 2); fixed order
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  int b = 0;
+  for (; b + 4 <= B; b += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = fmaf(dV[size_t(b + u) * C * 64 + i], asum[(b + u) * 64 + k], acc[u]);
+  }
+  for (; b < B; ++b) acc[0] = fmaf(dV[size_t(b) * C * 64 + i], asum[b * 64 + k], acc[0]);
+  dcenters[i] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
 // dasum[b,k] = sum_c dV[b,c,k] Cc[c,k]
@@ -365,6 +371,23 @@ extern "C" int scl_netvlad_bwd(const float* x, const float* assign_w, const floa
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NvWs w = nv_carve(workspace, workspace_bytes, B, HW, C, K);
   const long long P = (long long)B * HW;
+  const int prec = tc_gemm_precision();
+  if (nv_fused_ok(B, HW, C, K) && prec == 0 && workspace_bytes >= nv_ws_total(B, HW, C, K)) {
+    // One kernel per image for the head (normalisations' backward -> dV, dasum, operand splits), then two kernels with one
+    // pass over x each.  netvlad_fused.cu (the forward's skeleton): da = Xn dV[b], the soft-max backward, the row term of
+    // the l2-normalisation backward, dW.  netvlad_dx.cu: dx = inv ([A | dS] . [dV[b] | W]^T) - rb x on operands that are
+    // already fp16 hi / lo halves, through a shared-memory tile (TMA in, TMA out).
+    if (dx && !aligned16(dx)) return SCL_ERR_ALIGN;
+    const size_t base = nv_ws_bytes(B, HW, C, K);
+    const NvBwdHead head = {w.V, dout, w.nk, w.nt, centers};
+    rc = nv_fused_bwd(x, w.a, w.inv, w.dV, w.dasum, B, HW, C, w.da, w.rb, dassign_w, dx, static_cast<char*>(workspace) + base,
+                      workspace_bytes - base, stream, &head);
+    if (rc == SCL_OK && dcenters) {
+      nv_dcenters_kernel<<<(C * 64 + 255) / 256, 256, 0, stream>>>(w.dV, w.asum, B, C, dcenters);
+      SCL_LAUNCH_CHECK();
+    }
+    if (rc != SCL_ERR_UNSUPPORTED) return rc;        // (UNSUPPORTED is returned before anything is launched)
+  }
   nv_norm_bwd_kernel<<<B, 256, 0, stream>>>(w.V, dout, w.nk, w.nt, C, w.dV);
   SCL_LAUNCH_CHECK();
   if (dcenters) {
@@ -373,17 +396,6 @@ extern "C" int scl_netvlad_bwd(const float* x, const float* assign_w, const floa
   }
   nv_dasum_kernel<<<B, 256, 0, stream>>>(w.dV, centers, C, w.dasum);
   SCL_LAUNCH_CHECK();
-  const int prec = tc_gemm_precision();
-  if (nv_fused_ok(B, HW, C, K) && prec == 0 && workspace_bytes >= nv_ws_total(B, HW, C, K)) {
-    // Two kernels, one pass over x each.  netvlad_fused.cu (the forward's skeleton): da = Xn dV[b], the soft-max backward,
-    // the row term of the l2-normalisation backward, dW.  netvlad_dx.cu: dx = inv ([A | dS] . [dV[b] | W]^T) - rb x on
-    // operands that are already fp16 hi / lo halves, through a shared-memory tile (TMA in, TMA out).
-    if (dx && !aligned16(dx)) return SCL_ERR_ALIGN;
-    const size_t base = nv_ws_bytes(B, HW, C, K);
-    rc = nv_fused_bwd(x, w.a, w.inv, w.dV, w.dasum, B, HW, C, w.da, w.rb, dassign_w, dx, static_cast<char*>(workspace) + base,
-                      workspace_bytes - base, stream);
-    if (rc != SCL_ERR_UNSUPPORTED) return rc;
-  }
   // da[b] = (X[b] dV[b]) * inv[row]      M = HW, N = K, contraction over C; dV[b] [C,K] read MN-major
   {
     TcGemmDesc d = {};
