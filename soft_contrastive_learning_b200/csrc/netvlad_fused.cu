@@ -686,20 +686,20 @@ __global__ void __launch_bounds__(256) nv_wprep_kernel(const float* __restrict__
 // Tail, one CTA per image: V = sum of the partials + Cc * colsum(a); intra-normalisation per cluster; flatten (index
 // c*64 + k); l2-normalisation.  Few registers on purpose (every image's CTA is resident at once); the second pass re-reads
 // the V this CTA has just written (L2).
-__global__ void __launch_bounds__(256, 4) nv_fused_tail_kernel(const float* __restrict__ vpart, const float* __restrict__ aspart,
+__global__ void __launch_bounds__(1024) nv_fused_tail_kernel(const float* __restrict__ vpart, const float* __restrict__ aspart,
                                                                const float* __restrict__ centers, int C, int tpi, int units,
                                                                int G, int nslots, float* __restrict__ V,
                                                                float* __restrict__ asum, float* __restrict__ nk,
                                                                float* __restrict__ nt, float* __restrict__ out) {
-  __shared__ float s_as[64];
-  __shared__ float s_col[16][64];
-  __shared__ float s_ink[64];
+  __shared__ __align__(16) float s_as[64];
+  __shared__ __align__(16) float s_col[64][64];
+  __shared__ __align__(16) float s_ink[64];
   __shared__ float s_tot[2];
   __shared__ float s_nt;
   const int b = blockIdx.x;
   const int first = nv_cta_of_unit((long long)b * tpi, G, units);
   const int ns = nv_cta_of_unit((long long)b * tpi + tpi - 1, G, units) - first + 1;
-  const int k4 = (threadIdx.x & 15) * 4, grp = threadIdx.x >> 4;      // 16 row groups x 16 column quads
+  const int k4 = (threadIdx.x & 15) * 4, grp = threadIdx.x >> 4;      // 64 row groups x 16 column quads (1024 threads)
   if (threadIdx.x < 64) {
     float acc = 0.0f;
     for (int s = 0; s < ns; ++s)
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(256, 4) nv_fused_tail_kernel(const float* __re
   float4 ss = make_float4(0.f, 0.f, 0.f, 0.f);
   float* Vb = V + size_t(b) * C * 64;
 #pragma unroll 4
-  for (int c = grp; c < C; c += 16) {
+  for (int c = grp; c < C; c += 64) {
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < ns; ++s) {
       const float4 t = ldg_stream(reinterpret_cast<const float4*>(vpart + ((size_t(b) * nslots + s) * C + c) * 64 + k4));
@@ -727,8 +727,8 @@ __global__ void __launch_bounds__(256, 4) nv_fused_tail_kernel(const float* __re
   __syncthreads();
   if (threadIdx.x < 64) {
     float acc = 0.0f;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) acc += s_col[r][threadIdx.x];
+#pragma unroll 16
+    for (int r = 0; r < 64; ++r) acc += s_col[r][threadIdx.x];
     const float n = sqrtf(acc + 1e-12f);
     nk[b * 64 + threadIdx.x] = n;
     s_ink[threadIdx.x] = 1.0f / n;
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(256, 4) nv_fused_tail_kernel(const float* __re
   ik.x *= int_; ik.y *= int_; ik.z *= int_; ik.w *= int_;
   float* ob = out + size_t(b) * C * 64;
 #pragma unroll 4
-  for (int c = grp; c < C; c += 16) {
+  for (int c = grp; c < C; c += 64) {
     const float4 a = *reinterpret_cast<const float4*>(Vb + size_t(c) * 64 + k4);     // written by this thread above
     stg_stream(reinterpret_cast<float4*>(ob + size_t(c) * 64 + k4), make_float4(a.x * ik.x, a.y * ik.y, a.z * ik.z, a.w * ik.w));
   }
@@ -982,7 +982,7 @@ int nv_fused_fwd(const float* x, const float* assign_w, const float* centers, in
   SCL_LAUNCH_CHECK();
   int rc = nv_fused_launch(false, g, x, w.wt_hi, w.wt_lo, 64 * kWCopies, G, stream);
   if (rc) return rc;
-  nv_fused_tail_kernel<<<B, 256, 0, stream>>>(g.vpart, g.aspart, centers, C, tpi, int(units), G, g.nslots, V, asum, nk, nt, out);
+  nv_fused_tail_kernel<<<B, 1024, 0, stream>>>(g.vpart, g.aspart, centers, C, tpi, int(units), G, g.nslots, V, asum, nk, nt, out);
   SCL_LAUNCH_CHECK();
   nv_fused_trace_end(g, stream);
   return SCL_OK;
