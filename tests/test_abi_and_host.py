@@ -57,6 +57,13 @@ def test_pure_size_queries_work_without_a_gpu(L):
     assert L.scl_netvlad_workspace_bytes(2, 12, 512, 64, C.byref(n)) == 0
     assert L.scl_netvlad_workspace_bytes(2, 12, 512, 32, C.byref(n)) == -7        # only K=64 exists in the reference
     assert L.scl_knn_query_workspace_bytes(100000, 256, 64, 25, C.byref(n)) == 0 and n.value > 0
+    # query groups of the sharded two-phase protocol: a pure function of D and Q (every rank must see the same groups)
+    ng, gq = C.c_int(), C.c_int()
+    assert L.scl_knn_query_groups(4096, 10000, C.byref(ng), C.byref(gq)) == 0 and (ng.value, gq.value) == (2, 5120)
+    assert L.scl_knn_query_groups(4096, 300, C.byref(ng), C.byref(gq)) == 0 and (ng.value, gq.value) == (1, 300)
+    assert L.scl_knn_query_groups(4096, 5121, C.byref(ng), C.byref(gq)) == 0 and ng.value == 2 and gq.value * 2 >= 5121
+    assert L.scl_knn_query_groups(4095, 300, C.byref(ng), C.byref(gq)) == -1
+    assert L.scl_knn_query_groups(4096, 300, None, C.byref(gq)) == -1
 
 
 def test_compute_entry_points_fail_loudly_without_b200(L):
@@ -74,6 +81,16 @@ def test_compute_entry_points_fail_loudly_without_b200(L):
     rc = L.scl_wms_tuple_fwd_bwd(C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), 1, 4, 8, C.byref(p),
                                  C.cast(buf, C.c_void_p), None, None, None, C.cast(buf, C.c_void_p), 256, None)
     assert rc in (-5, -6)          # CUDA error / wrong arch: never a computed result
+    # the sharded two-phase entry points validate their arguments the same way
+    raw = (C.c_char * 1024)()
+    fb = C.c_void_p((C.addressof(raw) + 255) & ~255)               # 256-byte aligned like a workspace
+    assert L.scl_knn_query_begin(None, fb, 4096, 64, fb, 8, 5, fb, fb, 1 << 20, None) == -1
+    assert L.scl_knn_query_begin(fb, fb, 4096, 63, fb, 8, 5, fb, fb, 1 << 20, None) == -2          # D % 4
+    assert L.scl_knn_query_begin(fb, fb, 512, 64, fb, 8, 5, fb, fb, 1 << 20, None) == -7           # shard too small: plain query
+    assert L.scl_knn_query_begin(fb, fb, 4096, 64, fb, 8, 40, fb, fb, 1 << 20, None) == -7         # k > 32
+    assert L.scl_knn_bound_reduce(None, 2, 8, 5, fb, None) == -1
+    assert L.scl_knn_query_end(fb, fb, 4096, 64, fb, 8, 5, 0, None, fb, fb, None, fb, 1 << 20, None) == -1
+    assert L.scl_knn_query_begin(fb, fb, 4096, 64, fb, 8, 5, fb, fb, 1 << 20, None) in (-3, -5, -6)   # alignment / no device
 
 
 def test_product_never_imports_the_oracle():
